@@ -1,0 +1,261 @@
+#!/usr/bin/env python3
+"""bench.py -- SU(3) link updates/s of the gauge-update hot path (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl native|reference]
+
+One step = one full heat-bath sweep (8 (parity, direction) passes with their RANLUX3 random numbers +
+reunitarisation) of the workload below.  N = 1: BASELINE config C5, SU(3) 64^4 fp64, beta = 6, NHIT = 10,
+RANLUX3, cold start.  N > 1 (torchrun): BigLattice x-slab split, one 64-slice slab per GPU (weak scaling,
+global lattice (64 N) x 64^3), halo exchange after every pass.
+
+The JSON line also carries: `roofline` for the update kernel (algorithmic bytes 4.5 links x 96 B per updated
+link = 864 B, SURVEY.md 8d, against MEASURED_PEAKS.json), `e2e` (the same sweeps driven through the C ABI
+with host-side inputs/outputs copied inside the timed region), `cpu_baseline` (the UNMODIFIED reference's
+CPU_RUN program on this box's host cores) and `clocks`.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOAD = dict(group=3, dims=(64, 64, 64, 64), precision=1, beta=6.0, nhit=10, prng="RANLUX3", randseries=54, ints=1)
+BYTES_PER_LINK_UPDATE = 9 * 96      # SU(3) 2-row fp64: 4 V link reads + V/2 link writes per pass, 8 passes / 4 V links
+FLOPS_PER_LINK_UPDATE = 4700
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured"
+        except Exception:
+            pass
+    return 6650.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons, pw = [], [], set(), []
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2])); pw.append(float(r[3]))
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                pass
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ---------------------------------------------------------------------------------------------- reference arm
+def run_reference_cpu(n_procs: int, ls: int, sweeps: int):
+    """Time the UNMODIFIED reference (oracle/_ref/QCDGPU_cpu, its sequential CPU_RUN configuration) on
+    `n_procs` host cores, one independent SU(3) ls^4 run per core.  Returns (link updates/s, seconds)."""
+    binary = os.path.join(ROOT, "oracle", "_ref", "QCDGPU_cpu")
+    if not os.path.exists(binary):
+        return None, None
+    tmp = tempfile.mkdtemp(prefix="qcdref_")
+    init = ("PLATFORM = 0\nDEVICE = 0\nFINISHPATH=./\nOUTPUTPATH=./\nGROUP = 3\nND = 4\n"
+            f"LS = {ls}\nLT = {ls}\nITER = {sweeps + 1}\nNITER = 1\nNHIT = 10\nBETA = 6.0\nNAV = 0\nINTS = 1\n"
+            "PRNG = RANLUX3\nRANDSERIES = 54\n")
+    dirs = []
+    for i in range(n_procs):
+        d = os.path.join(tmp, str(i))
+        os.makedirs(d)
+        open(os.path.join(d, "init.dat"), "w").write(init.replace("RANDSERIES = 54", f"RANDSERIES = {54 + i}"))
+        dirs.append(d)
+    t0 = time.time()
+    procs = [subprocess.Popen([binary, "init.dat"], cwd=d, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL) for d in dirs]
+    for p in procs:
+        p.wait()
+    dt = time.time() - t0
+    links = 4 * ls ** 4 * sweeps * n_procs
+    return links / dt, dt
+
+
+def reference_main(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    ls = 12
+    per_step = []
+    for _ in range(args.warmup and 1):
+        run_reference_cpu(cores, ls, 1)
+    for _ in range(max(1, min(args.steps, 3))):
+        v, dt = run_reference_cpu(cores, ls, 2)
+        if v is None:
+            print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/QCDGPU_cpu missing (run make -C oracle ref where /root/reference exists)"}))
+            return
+        per_step.append((v, dt))
+    v = sum(x[0] for x in per_step) / len(per_step)
+    dt = sum(x[1] for x in per_step) / len(per_step)
+    sample = (f"reference CPU_RUN binary, {cores} independent SU(3) {ls}^4 cold-start runs (one per core), 2 sweeps each incl. "
+              f"per-sweep plaquette+action measurement; link-updates/s is volume independent to first order")
+    out = {"impl": "reference", "metric": "SU(3) link updates/sec", "value": v, "unit": "link-updates/s",
+           "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3 / 2,
+           "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+           "config": {"workload": "SU(3) 64^4 fp64 heat-bath sweeps, beta=6.0, NHIT=10, RANLUX3, cold start (CPU sample: 12^4 per core)"},
+           "cpu_baseline": {"value": v, "unit": "link-updates/s", "cores": cores, "kind": "reference", "sample": sample},
+           "e2e": {"value": v, "unit": "link-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(out))
+
+
+# ---------------------------------------------------------------------------------------------- native arm
+def build_model(dims, fused=True, device=0):
+    from qcdgpu_b200 import Model
+    m = Model()
+    m.desired_device = device
+    m.lattice_group = WORKLOAD["group"]
+    m.lattice_full_size = list(dims)
+    m.precision = WORKLOAD["precision"]
+    m.ints = WORKLOAD["ints"]
+    m.BETA = WORKLOAD["beta"]
+    m.NHIT = WORKLOAD["nhit"]
+    m.PRNG0.PRNG_generator = WORKLOAD["prng"]
+    m.PRNG0.PRNG_randseries = WORKLOAD["randseries"]
+    m.fused_prng = fused
+    m.PL_level = 0
+    m.ITER = 4096
+    m.lattice_init()
+    m.lattice_start()
+    return m
+
+
+def native_single(args):
+    import numpy as np
+    dims = tuple(int(x) for x in args.dims.split("x")) if args.dims else WORKLOAD["dims"]
+    m = build_model(dims, fused=not args.buffered)
+    g = m.GPU0
+    V = m.lattice_domain_site
+    links_per_step = 4 * V
+    for _ in range(args.warmup):
+        m.lattice_sweep()
+    g.synchronize()
+    # ---- device-timed throughput (inputs resident in HBM)
+    clocks = ClockSampler(0)
+    clocks.start()
+    l0 = g.launch_count()
+    g.timer_start()
+    for _ in range(args.steps):
+        m.lattice_sweep()
+    ms = g.timer_stop()
+    launches = g.launch_count() - l0
+    value = links_per_step * args.steps / (ms * 1e-3)
+    # ---- e2e: the run loop as a user drives it through the C ABI -- per step the host-side inputs (parameter
+    # buffer) go H2D from pinned memory, the sweep and the plaquette measurement run, the result comes back D2H
+    params = g.buffer_map(m.lattice_parameters, np.uint8)
+    h2d = int(params.size)
+    d2h = 16
+    t0 = time.perf_counter()
+    plq = None
+    for i in range(args.steps):
+        g._chk(g.L.qgpu_buffer_unmap(g.h, m.lattice_parameters, params.ctypes.data), "unmap")   # H2D
+        m.lattice_sweep()
+        g.kernel_run(m.sun_measurement_plq_id)
+        g.kernel_init_constant_reset(m.sun_measurement_plq_reduce_id, 1, m.argument_plq_index)
+        g.kernel_run(m.sun_measurement_plq_reduce_id)
+        p = g.L.qgpu_buffer_map_range(g.h, m.lattice_energies_plq, 16, 16)                     # D2H (+sync)
+        plq = np.frombuffer((__import__("ctypes").c_char * 16).from_address(p), dtype=np.float64).copy()
+    e2e_s = time.perf_counter() - t0
+    e2e = links_per_step * args.steps / e2e_s
+    ck = clocks.stop()
+    # ---- dominant kernel: average launch duration of the update kernel, CUDA events around each launch
+    g.set_debug(profiling=True)
+    for _ in range(2):
+        m.lattice_sweep()
+    g.set_debug(profiling=False)
+    tk = [g.kernel_get_execution_time(k) for k in m.sun_update_id.values()]
+    upd_ns = sum(t[0] * t[2] for t in tk) / max(1, sum(t[2] for t in tk))
+    gs_ns = g.kernel_get_execution_time(m.sun_GramSchmidt_id)[0]
+    peak, peak_kind = measured_peaks()
+    bytes_per_launch = 4.5 * V * 96.0
+    achieved = bytes_per_launch / (upd_ns * 1e-9) / 1e9
+    regs = g.update_kernel_registers(m.program_update, 0, 2 if not args.buffered else 0)
+    plq_total = float(plq.sum() / (6.0 * V)) if plq is not None else None
+    # ---- CPU baseline: the reference itself, 1 core, bounded sample
+    cpu_v, cpu_dt = (None, None) if args.no_cpu else run_reference_cpu(1, 12, 3)
+    out = {
+        "metric": "SU(3) link updates/sec", "value": value, "unit": "link-updates/s", "n_gpus": 1,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"SU(3) {'x'.join(map(str, dims))} fp64 heat-bath sweeps (8 passes + reunitarisation), beta=6.0, "
+                               f"NHIT=10, RANLUX3 ({'fused in-register' if not args.buffered else 'buffered'}), cold start",
+                   "l2_policy": "inputs_larger_than_L2 (link table 6.44 GB vs 126 MB L2)", "sweeps_per_s": args.steps / (ms * 1e-3),
+                   "plaquette_after_run": plq_total, "update_kernel_registers": regs},
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": None, "peak_source": peak_kind, "kernel": "update_kernel<3,double,MU,false,PrnRanlux<223>>",
+                     "avg_launch_us": upd_ns / 1e3, "algorithmic_bytes_per_launch": bytes_per_launch,
+                     "fp64_gflops": FLOPS_PER_LINK_UPDATE * (V / 2) / (upd_ns * 1e-9) / 1e9,
+                     "reunitarisation_launch_us": gs_ns / 1e3},
+        "e2e": {"value": e2e, "unit": "link-updates/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "what": "per step: parameter buffer H2D, sweep, plaquette measurement + reduction, result D2H, all through the C ABI"},
+        "gpu_launches": int(launches),
+        "clocks": ck,
+        "cpu_baseline": ({"value": cpu_v, "unit": "link-updates/s", "cores": 1, "kind": "reference",
+                          "sample": f"oracle/_ref/QCDGPU_cpu (unmodified reference, CPU_RUN build), SU(3) 12^4 cold start, 3 sweeps incl. measurements, {cpu_dt:.1f} s"}
+                         if cpu_v else {"value": None, "unit": "link-updates/s", "cores": 0, "kind": "reference", "sample": "oracle/_ref missing"}),
+    }
+    print(json.dumps(out))
+    m.close()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--dims", default="")
+    ap.add_argument("--buffered", action="store_true", help="reference-layout PRN buffer instead of the fused generator")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return reference_main(args)
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world > 1 or args.gpus > 1:
+        from qcdgpu_b200 import biglattice
+        return biglattice.bench_main(args, WORKLOAD)
+    return native_single(args)
+
+
+if __name__ == "__main__":
+    main()

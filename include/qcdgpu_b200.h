@@ -1,0 +1,146 @@
+/* qcdgpu_b200.h -- C ABI of libqcdgpu_b200.so: the CUDA (sm_100a) replacement for QCDGPU's
+ * OpenCL abstraction layer `GPU_CL::GPU` ("clinterface").
+ *
+ * Every entry point below replaces one member of the reference class
+ *     SU(N)/clinterface/clinterface.h:54-415   (implementation clinterface.cpp)
+ * with the same argument meaning: integer ids for programs / kernels / buffers, positional
+ * kernel arguments set once, `kernel_run(id)` to execute.  The reference's callers
+ * (suncl.cpp, random.cpp, su{2,3}cpu.cpp, data_analysis.cpp) can bind to this library through
+ * the thin C++ shim shown in INTEGRATION.md without being modified.
+ *
+ * What is NOT taken over from the reference: `program_create` does not compile OpenCL C.
+ * The option string ("-D SUN=3 -D N1=.. -D ROWSIZE=.. -D PRECISION=.. -D NHIT=.." as assembled
+ * in suncl.cpp:3274-3301, random.cpp:427-430) is parsed into a kernel configuration and the
+ * kernel NAMES of the reference (update_odd_X, lattice_measurement_plq, ranlux, ...) are mapped
+ * to hand-written CUDA kernels.  Sizes are size_t (the reference overflows `int` above 2 GiB,
+ * clinterface.cpp:1296,1324).
+ *
+ * Plain C types only; no CUDA, torch or C++ types cross this boundary.
+ * Thread-safety: one handle per host thread, like the reference (one GPU instance per device).
+ */
+#ifndef QCDGPU_B200_H
+#define QCDGPU_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct qgpu qgpu;
+
+/* GPU::GPU_buffer_types, clinterface.h:73-82 (same numeric values) */
+enum qgpu_buffer_type {
+    QGPU_BUFFER_NONE = 0, QGPU_BUFFER_GLOBAL = 1, QGPU_BUFFER_INPUT = 2, QGPU_BUFFER_IO = 3,
+    QGPU_BUFFER_OUTPUT = 4, QGPU_BUFFER_CONSTANT = 5, QGPU_BUFFER_LDS = 6, QGPU_BUFFER_UAV = 7
+};
+
+/* GPU::GPU_device_info, clinterface.h:127-143 */
+typedef struct qgpu_device_info {
+    char     device_name[256];
+    uint64_t local_memory_size;      /* CL_DEVICE_LOCAL_MEM_SIZE  -> shared memory per block (opt-in max) */
+    uint64_t max_constant_size;
+    uint64_t max_memory_size;        /* CL_DEVICE_MAX_MEM_ALLOC_SIZE -> total global memory */
+    size_t   max_memory_width;       /* default number of PRNG instances (clinterface.cpp:419-421) */
+    size_t   max_workgroup_size;     /* alignment quantum of every buffer / work size */
+    size_t   memory_align_factor;
+    int      sm_count;
+    int      cc_major, cc_minor;
+} qgpu_device_info;
+
+/* ---- life cycle: GPU::GPU(), ~GPU(), device_select, device_initialize, device_finalize
+ *      clinterface.cpp:63-123, 345-489, 566-628 */
+qgpu* qgpu_create(void);
+void  qgpu_destroy(qgpu* h);
+int   qgpu_device_select(qgpu* h, unsigned platform_id, unsigned device_id);  /* platform must be 0; device = CUDA ordinal */
+int   qgpu_device_initialize(qgpu* h);                                      /* returns number of CUDA devices */
+int   qgpu_device_finalize(qgpu* h, int error_code);
+int   qgpu_get_device_info(qgpu* h, qgpu_device_info* out);
+/* GPU_limit_max_workgroup_size (clinterface.h:160; QCDGPU.cpp:74 sets 64).  Call before device_initialize. */
+void  qgpu_set_limit_max_workgroup_size(qgpu* h, unsigned limit);
+/* GPU_info.max_memory_width override (the reference takes CL_DEVICE_IMAGE3D_MAX_WIDTH). */
+void  qgpu_set_max_memory_width(qgpu* h, size_t width);
+/* GPU_debug.profiling / brief_report / show_stage (clinterface.h:102-109) */
+void  qgpu_set_debug(qgpu* h, int profiling, int brief_report, int show_stage);
+/* 0 (default, reference behaviour OpenCL_Check_Error clinterface.cpp:225-284): print and exit(-1) on any error.
+ * 1: return a negative value and keep the message for qgpu_last_error(). */
+void        qgpu_set_error_mode(qgpu* h, int return_errors);
+const char* qgpu_last_error(qgpu* h);
+
+/* ---- programs: program_create (clinterface.cpp:715-1116).  `source` is ignored and may be NULL. */
+int qgpu_program_create(qgpu* h, const char* source, const char* options);
+int qgpu_program_set_active(qgpu* h, int program_id);
+int qgpu_program_get_active(qgpu* h);
+
+/* ---- kernels: kernel_init*, kernel_run, kernel_get_worksize (clinterface.cpp:1132-1294) */
+int qgpu_kernel_init(qgpu* h, const char* kernel_name, unsigned work_dimensions,
+                     const size_t* global_size, const size_t* local_size);
+int qgpu_kernel_init_buffer(qgpu* h, int kernel_id, int buffer_id);
+int qgpu_kernel_init_constant_int(qgpu* h, int kernel_id, const int* host_ptr);
+int qgpu_kernel_init_constant_uint4(qgpu* h, int kernel_id, const uint32_t host_ptr[4]);
+int qgpu_kernel_init_constant_float(qgpu* h, int kernel_id, const float* host_ptr);
+int qgpu_kernel_init_constant_double(qgpu* h, int kernel_id, const double* host_ptr);
+int qgpu_kernel_init_constant_reset(qgpu* h, int kernel_id, const int* host_ptr, int argument_id);
+int qgpu_kernel_run(qgpu* h, int kernel_id);
+int qgpu_kernel_get_worksize(qgpu* h, int kernel_id);
+/* kernel_get_execution_time (clinterface.cpp:1290): mean / deviation in ns and number of starts (profiling on) */
+int qgpu_kernel_get_execution_time(qgpu* h, int kernel_id, double* mean_ns, double* deviation_ns, int* number);
+
+/* ---- buffers: buffer_init, buffer_write, buffer_map*, buffer_unmap, buffer_kill, buffer_size_align
+ *      (clinterface.cpp:1296-1592).  host_ptr stays owned by the caller and is copied at init. */
+int      qgpu_buffer_init(qgpu* h, int buffer_type, size_t size, const void* host_ptr, size_t size_of);
+int      qgpu_buffer_write(qgpu* h, int buffer_id);                 /* host_ptr -> device again */
+void*    qgpu_buffer_map(qgpu* h, int buffer_id);                   /* device -> backend-owned host shadow */
+void*    qgpu_buffer_map_range(qgpu* h, int buffer_id, size_t offset_bytes, size_t size_bytes);
+int      qgpu_buffer_unmap(qgpu* h, int buffer_id, void* ptr);      /* writes the mapped range back (BIGLAT UpdateEdges) */
+int      qgpu_buffer_kill(qgpu* h, int buffer_id);
+size_t   qgpu_buffer_size_bytes(qgpu* h, int buffer_id);
+unsigned qgpu_buffer_size_align(qgpu* h, unsigned size);
+unsigned qgpu_buffer_size_align_step(qgpu* h, unsigned size, unsigned step);
+
+/* ================= extensions with no counterpart in the reference ================= */
+
+/* Stream-ordered execution: with async on, qgpu_kernel_run enqueues and returns; qgpu_buffer_map and
+ * qgpu_synchronize wait.  (The reference blocks in every kernel_run, clinterface.cpp:1251-1278.) */
+void  qgpu_set_async(qgpu* h, int on);
+int   qgpu_synchronize(qgpu* h);
+/* Fused PRNG: a `ranlux`/`xor128`/`pm`/`mrg32k3a` kernel_run is deferred; if the next consumer of its PRN
+ * buffer is an update kernel and PRNG_instances == PRNGSTEP, the generator runs inside the update kernel
+ * with its state in registers and the buffer is never written.  Any other access materialises it first.
+ * Streams and results are identical either way. */
+void  qgpu_set_fused_prng(qgpu* h, int on);
+/* raw device pointer of a buffer (halo exchange, interop) and raw stream handle (cudaStream_t) */
+void* qgpu_buffer_device_ptr(qgpu* h, int buffer_id);
+void* qgpu_stream(qgpu* h);
+/* device-side timing on the launching stream (CUDA events) */
+int   qgpu_timer_start(qgpu* h);
+int   qgpu_timer_stop(qgpu* h, float* elapsed_ms);
+/* number of kernels launched through this handle so far */
+uint64_t qgpu_launch_count(qgpu* h);
+/* registers per thread of the update kernel a program would use (for reports); -1 if unknown */
+int   qgpu_update_kernel_registers(qgpu* h, int program_id, int direction, int prn_kind);
+
+/* BigLattice halo exchange between x-slabs (replaces model::UpdateEdges, suncl.cpp:4005-4062).
+ * Copies x-slice `x_src` of buffer `src_buffer` on handle `src` into x-slice `x_dst` of `dst_buffer` on
+ * handle `dst` for the vec4 planes of direction `dir` (dir < 0: all directions).  Both buffers are link
+ * tables of programs with the same N2,N3,N4.  The copy is a kernel on dst's stream reading peer memory
+ * (NVLink P2P when the two handles sit on different devices) and is ordered after src's stream. */
+int   qgpu_halo_copy(qgpu* dst, int dst_program, int dst_buffer, unsigned x_dst,
+                     qgpu* src, int src_program, int src_buffer, unsigned x_src, int dir);
+/* same, but the source is a raw device pointer to a packed slice produced by qgpu_halo_pack (for
+ * transports that cannot address peer memory, e.g. NCCL send/recv between processes) */
+int   qgpu_halo_pack(qgpu* h, int program, int buffer, unsigned x_src, int dir, void* packed_dev, size_t* bytes);
+int   qgpu_halo_unpack(qgpu* h, int program, int buffer, unsigned x_dst, int dir, const void* packed_dev);
+size_t qgpu_halo_bytes(qgpu* h, int program, int dir);
+
+/* host helpers: glibc srand()/rand() in bulk (seed tables are defined through them, random.cpp:235,462-465) */
+void  qgpu_host_srand(unsigned seed);
+void  qgpu_host_rand_fill(uint32_t* out, size_t n, uint32_t modulo, uint32_t add);
+
+const char* qgpu_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

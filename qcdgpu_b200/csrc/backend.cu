@@ -1,0 +1,703 @@
+// backend.cu -- the C ABI of include/qcdgpu_b200.h: a CUDA replacement for the reference's
+// GPU_CL::GPU class (SU(N)/clinterface/clinterface.{h,cpp}).
+//
+// Model kept from the reference: per-handle tables of programs / kernels / buffers addressed
+// by small integer ids starting at 1 (clinterface.cpp:84-87, 1134, 1298), positional kernel
+// arguments set once by kernel_init_buffer / kernel_init_constant*, kernel_run(id).
+// New: programs are option strings parsed into a KernelConfig (no OpenCL compilation);
+// kernel names are bound to hand-written sm_100a kernels; execution is stream-ordered;
+// PRN production can be fused into the update kernel (see qgpu_set_fused_prng).
+#include "../../include/qcdgpu_b200.h"
+#include "launch.h"
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+using namespace qcd;
+
+namespace {
+
+struct ProgramCfg {
+    std::string options;
+    int sun = 3, nd = 4;
+    uint32_t n1 = 0, n2 = 0, n3 = 0, n4 = 0;
+    uint32_t rowsize = 0, prngstep = 0;
+    int precision = 0;              // 0 single, 1 double, 2 mixed (suncl.h:73)
+    int nhit = 10, nhitpar = 1;
+    bool tbc = false, gid_upd = false, biglat = false;
+    uint32_t full_sites = 0, left_sites = 0;
+    int pl = 0;
+    int rl_skip = 223;
+    int prng_precision = 0;
+    bool fmunu = false, f0mu = false;
+    bool has_lattice = false;
+};
+
+enum KernelKind {
+    K_NONE = 0, K_INIT_COLD, K_INIT_GID, K_INIT_HOT, K_GRAMSCHMIDT, K_UPDATE, K_OVERRELAX, K_CLEAR,
+    K_MEASURE, K_REDUCE_MEAS, K_MEASURE_PLQ, K_REDUCE_PLQ, K_POLYAKOV, K_REDUCE_POLYAKOV,
+    K_RANLUX_INIT, K_PRODUCE
+};
+
+struct Arg {
+    enum Type { BUF, I32, U32X4, F32, F64 } type;
+    int buf;
+    int32_t i;
+    uint32_t u4[4];
+    float f;
+    double d;
+};
+
+struct Kernel {
+    std::string name;
+    KernelKind kind = K_NONE;
+    int program = 0;
+    int dir = 0, odd = 0, prn_kind = 0;
+    size_t global[3] = { 1, 1, 1 };
+    size_t local0 = 0;
+    bool local_given = false;
+    std::vector<Arg> args;
+    // profiling (GPU_debug.profiling)
+    double t_sum = 0, t_sq = 0; int starts = 0;
+};
+
+struct Buffer {
+    int type = 0;
+    size_t size = 0, size_of = 0, bytes = 0;
+    void* dptr = nullptr;
+    const void* host_ptr = nullptr;
+    void* shadow = nullptr;          // host memory returned by buffer_map
+    size_t map_off = 0, map_len = 0;
+    int pending_produce = 0;         // kernel id of a deferred PRN producer writing this buffer
+    bool alive = false;
+};
+
+}  // namespace
+
+struct qgpu {
+    int device = 0;
+    bool initialized = false;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, evp0 = nullptr, evp1 = nullptr, ev_halo = nullptr;
+    unsigned limit_wg = 0;
+    size_t max_memory_width = 0;
+    qgpu_device_info info;
+    bool profiling = false, brief = false, show_stage = false;
+    bool return_errors = false, async = false, fused = false;
+    std::string last_error;
+    std::vector<ProgramCfg> programs;
+    std::vector<Kernel> kernels;
+    std::vector<Buffer> buffers;
+    int active_program = 0;
+    uint64_t launches = 0;
+    qgpu() { programs.resize(1); kernels.resize(1); buffers.resize(1); memset(&info, 0, sizeof(info)); }
+};
+
+namespace {
+
+int fail(qgpu* h, const char* fmt, ...) {
+    char buf[1024];
+    va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof(buf), fmt, ap); va_end(ap);
+    if (h) h->last_error = buf;
+    if (!h || !h->return_errors) {
+        // reference behaviour: OpenCL_Check_Error prints, finalizes, exit(-1)  (clinterface.cpp:225-284)
+        fprintf(stderr, "qcdgpu_b200 error: %s\n", buf);
+        exit(-1);
+    }
+    return -1;
+}
+#define CUDA_OK(h, call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) return fail(h, "%s failed: %s", #call, cudaGetErrorString(e__)); } while (0)
+#define CUDA_OKP(h, call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { fail(h, "%s failed: %s", #call, cudaGetErrorString(e__)); return nullptr; } } while (0)
+
+bool valid_buf(qgpu* h, int id) { return id > 0 && id < (int)h->buffers.size() && h->buffers[id].alive; }
+bool valid_kernel(qgpu* h, int id) { return id > 0 && id < (int)h->kernels.size(); }
+
+// "-D NAME=VALUE", "-D NAME", "-DNAME=VALUE", "-I path", "-Werror"
+void parse_options(const char* opt, ProgramCfg& c) {
+    c.options = opt ? opt : "";
+    std::vector<std::string> tok;
+    { std::string cur; for (const char* p = c.options.c_str();; p++) { if (*p == ' ' || *p == '\t' || *p == 0) { if (!cur.empty()) tok.push_back(cur); cur.clear(); if (!*p) break; } else cur += *p; } }
+    for (size_t i = 0; i < tok.size(); i++) {
+        std::string d;
+        if (tok[i] == "-D" && i + 1 < tok.size()) d = tok[++i];
+        else if (tok[i].rfind("-D", 0) == 0 && tok[i].size() > 2) d = tok[i].substr(2);
+        else if (tok[i] == "-I" && i + 1 < tok.size()) { i++; continue; }
+        else continue;
+        std::string name = d, val = "1";
+        size_t eq = d.find('=');
+        if (eq != std::string::npos) { name = d.substr(0, eq); val = d.substr(eq + 1); }
+        unsigned long v = strtoul(val.c_str(), nullptr, 10);
+        if (name == "SUN") { c.sun = (int)v; c.has_lattice = true; }
+        else if (name == "ND") c.nd = (int)v;
+        else if (name == "N1") c.n1 = (uint32_t)v;
+        else if (name == "N2") c.n2 = (uint32_t)v;
+        else if (name == "N3") c.n3 = (uint32_t)v;
+        else if (name == "N4") c.n4 = (uint32_t)v;
+        else if (name == "ROWSIZE") c.rowsize = (uint32_t)v;
+        else if (name == "PRNGSTEP") c.prngstep = (uint32_t)v;
+        else if (name == "PRECISION") c.precision = (int)v;
+        else if (name == "NHIT") c.nhit = (int)v;
+        else if (name == "NHITPar") c.nhitpar = (int)v;
+        else if (name == "TBC") c.tbc = true;
+        else if (name == "GID_UPD") c.gid_upd = true;
+        else if (name == "BIGLAT") c.biglat = true;
+        else if (name == "FULL_SITES") c.full_sites = (uint32_t)v;
+        else if (name == "LEFT_SITES") c.left_sites = (uint32_t)v;
+        else if (name == "PL") c.pl = (int)v;
+        else if (name == "RL_skip") c.rl_skip = (int)v;
+        else if (name == "PRNG_PRECISION") c.prng_precision = (int)v;
+        else if (name == "FMUNU") c.fmunu = true;
+        else if (name == "F0MU") c.f0mu = true;
+    }
+}
+
+Geom make_geom(const ProgramCfg& c) {
+    Geom g;
+    memset(&g, 0, sizeof(g));
+    g.n1 = c.n1; g.n2 = c.n2; g.n3 = c.n3; g.n4 = c.n4;
+    g.n23 = c.n2 * c.n3; g.n234 = g.n23 * c.n4; g.sites = c.n1 * g.n234;
+    g.rowsize = c.rowsize ? c.rowsize : g.sites;                            // model.cl:101-103
+    g.biglat = c.biglat ? 1u : 0u;
+    g.nthreads = c.biglat ? (c.n1 - 2) * g.n234 / 2 : g.sites / 2;          // suncl.cl:404-418
+    g.prngstep = c.prngstep ? c.prngstep : g.sites / 2;                     // model.cl:126-128
+    g.left_sites = c.left_sites; g.full_sites = c.full_sites;
+    g.nhit = (uint32_t)c.nhit; g.nhitpar = (uint32_t)c.nhitpar;
+    if (c.biglat && g.n234) { g.tw_lo = c.left_sites / g.n234; g.tw_hi = c.full_sites / g.n234; }
+    return g;
+}
+int prec_index(const ProgramCfg& c) { return c.precision == 1 ? 1 : 0; }   // mixed == single storage/arithmetic (complex.h:61-91)
+
+struct NameMap { const char* name; KernelKind kind; int dir; int odd; int prn; };
+const NameMap kNames[] = {
+    { "lattice_init_cold", K_INIT_COLD, 0, 0, 0 }, { "lattice_init_gid", K_INIT_GID, 0, 0, 0 },
+    { "lattice_init_hot_X", K_INIT_HOT, 0, 0, 0 }, { "lattice_init_hot_Y", K_INIT_HOT, 1, 0, 0 },
+    { "lattice_init_hot_Z", K_INIT_HOT, 2, 0, 0 }, { "lattice_init_hot_T", K_INIT_HOT, 3, 0, 0 },
+    { "lattice_GramSchmidt", K_GRAMSCHMIDT, 0, 0, 0 },
+    { "update_even_X", K_UPDATE, 0, 0, 0 }, { "update_even_Y", K_UPDATE, 1, 0, 0 }, { "update_even_Z", K_UPDATE, 2, 0, 0 }, { "update_even_T", K_UPDATE, 3, 0, 0 },
+    { "update_odd_X", K_UPDATE, 0, 1, 0 }, { "update_odd_Y", K_UPDATE, 1, 1, 0 }, { "update_odd_Z", K_UPDATE, 2, 1, 0 }, { "update_odd_T", K_UPDATE, 3, 1, 0 },
+    // extension (north_star: overrelaxation; not in the reference)
+    { "overrelax_even_X", K_OVERRELAX, 0, 0, 0 }, { "overrelax_even_Y", K_OVERRELAX, 1, 0, 0 }, { "overrelax_even_Z", K_OVERRELAX, 2, 0, 0 }, { "overrelax_even_T", K_OVERRELAX, 3, 0, 0 },
+    { "overrelax_odd_X", K_OVERRELAX, 0, 1, 0 }, { "overrelax_odd_Y", K_OVERRELAX, 1, 1, 0 }, { "overrelax_odd_Z", K_OVERRELAX, 2, 1, 0 }, { "overrelax_odd_T", K_OVERRELAX, 3, 1, 0 },
+    { "clear_measurement", K_CLEAR, 0, 0, 0 },
+    { "lattice_measurement", K_MEASURE, 0, 0, 0 }, { "reduce_measurement_double2", K_REDUCE_MEAS, 0, 0, 0 },
+    { "lattice_measurement_plq", K_MEASURE_PLQ, 0, 0, 0 }, { "reduce_measurement_plq_double2", K_REDUCE_PLQ, 0, 0, 0 },
+    { "lattice_polyakov", K_POLYAKOV, 0, 0, 0 }, { "reduce_polyakov_double2", K_REDUCE_POLYAKOV, 0, 0, 0 },
+    { "ranlux_init", K_RANLUX_INIT, 0, 0, 0 },
+    { "ranlux", K_PRODUCE, 0, 0, -1 }, { "xor128", K_PRODUCE, 0, 0, PRN_XOR128 }, { "pm", K_PRODUCE, 0, 0, PRN_PM }, { "mrg32k3a", K_PRODUCE, 0, 0, PRN_MRG32K3A },
+};
+
+int ranlux_kind(int skip) {
+    switch (skip) { case 24: return PRN_RANLUX0; case 48: return PRN_RANLUX1; case 97: return PRN_RANLUX2; case 223: return PRN_RANLUX3; case 389: return PRN_RANLUX4; }
+    return -1;
+}
+
+void* buf_ptr(qgpu* h, const Kernel& k, size_t i) {
+    if (i >= k.args.size() || k.args[i].type != Arg::BUF) return nullptr;
+    int b = k.args[i].buf;
+    if (!valid_buf(h, b)) return nullptr;
+    return h->buffers[b].dptr;
+}
+int buf_id(const Kernel& k, size_t i) { return (i < k.args.size() && k.args[i].type == Arg::BUF) ? k.args[i].buf : 0; }
+bool arg_int(const Kernel& k, size_t i, int* out) {
+    if (i >= k.args.size() || k.args[i].type != Arg::I32) return false;
+    *out = k.args[i].i; return true;
+}
+
+int launch_kernel(qgpu* h, int kid);
+
+// run a deferred PRN producer now (writes the reference-layout buffer)
+int flush_pending(qgpu* h, int bid) {
+    if (!valid_buf(h, bid)) return 0;
+    int kid = h->buffers[bid].pending_produce;
+    if (!kid) return 0;
+    h->buffers[bid].pending_produce = 0;
+    Kernel& k = h->kernels[kid];
+    int samples = 0;
+    if (!arg_int(k, 2, &samples)) return fail(h, "kernel %s: argument 2 (samples) not set", k.name.c_str());
+    CUDA_OK(h, launch_prn_produce(k.prn_kind, (uint32_t*)buf_ptr(h, k, 0), buf_ptr(h, k, 1), (uint32_t)k.global[0], (uint32_t)samples, h->stream));
+    h->launches++;
+    return 0;
+}
+
+int launch_kernel(qgpu* h, int kid) {
+    Kernel& k = h->kernels[kid];
+    const ProgramCfg& c = h->programs[k.program];
+    cudaStream_t st = h->stream;
+    const int prec = prec_index(c);
+    switch (k.kind) {
+        case K_INIT_COLD: case K_INIT_GID: {
+            if (!buf_ptr(h, k, 0)) return fail(h, "kernel %s: argument 0 (lattice_table) not set", k.name.c_str());
+            Geom g = make_geom(c);
+            CUDA_OK(h, k.kind == K_INIT_COLD ? launch_init_cold(c.sun, prec, buf_ptr(h, k, 0), g, st) : launch_init_gid(c.sun, prec, buf_ptr(h, k, 0), g, st));
+            break;
+        }
+        case K_INIT_HOT: {
+            if (!buf_ptr(h, k, 0) || !buf_ptr(h, k, 1)) return fail(h, "kernel %s: arguments (lattice_table, prns) not set", k.name.c_str());
+            if (flush_pending(h, buf_id(k, 1)) < 0) return -1;
+            Geom g = make_geom(c);
+            size_t need = (c.sun == 3 ? 2 * (size_t)g.rowsize : 0) + g.sites;
+            if (h->buffers[buf_id(k, 1)].bytes < need * 16) return fail(h, "kernel %s: PRN buffer too small for a hot start (%zu < %zu vec4)", k.name.c_str(), h->buffers[buf_id(k, 1)].bytes / 16, need);
+            CUDA_OK(h, launch_init_hot(c.sun, prec, buf_ptr(h, k, 0), g, buf_ptr(h, k, 1), k.dir, st));
+            break;
+        }
+        case K_GRAMSCHMIDT: {
+            if (!buf_ptr(h, k, 0)) return fail(h, "kernel %s: argument 0 (lattice_table) not set", k.name.c_str());
+            CUDA_OK(h, launch_gramschmidt(c.sun, prec, buf_ptr(h, k, 0), make_geom(c), st));
+            break;
+        }
+        case K_UPDATE: case K_OVERRELAX: {
+            UpdateArgs a;
+            memset(&a, 0, sizeof(a));
+            a.table = buf_ptr(h, k, 0); a.params = buf_ptr(h, k, 1);
+            if (!a.table || !a.params) return fail(h, "kernel %s: arguments (lattice_table, lattice_parameters) not set", k.name.c_str());
+            a.geom = make_geom(c); a.odd = k.odd; a.tbc = c.tbc ? 1 : 0;
+            UpdateLaunchFn fn = get_update_launcher(c.sun, prec, k.dir);
+            if (!fn) return fail(h, "kernel %s: no CUDA instantiation for SUN=%d PRECISION=%d", k.name.c_str(), c.sun, c.precision);
+            if (k.kind == K_OVERRELAX) { a.overrelax = 1; CUDA_OK(h, fn(a, st)); break; }
+            if (c.gid_upd) { a.prn_kind = PRN_GID; CUDA_OK(h, fn(a, st)); break; }
+            int pb = buf_id(k, 2);
+            if (!valid_buf(h, pb)) return fail(h, "kernel %s: argument 2 (prns) not set", k.name.c_str());
+            if (c.prng_precision == 2) return fail(h, "kernel %s: PRNG_PRECISION=2 (double PRNs) is not implemented", k.name.c_str());
+            Buffer& pbuf = h->buffers[pb];
+            bool fused = false;
+            if (pbuf.pending_produce) {
+                Kernel& pk = h->kernels[pbuf.pending_produce];
+                int samples = 0; arg_int(pk, 2, &samples);
+                bool fusable = h->fused && (uint32_t)pk.global[0] == a.geom.prngstep && a.geom.nthreads <= a.geom.prngstep &&
+                               (pk.prn_kind == PRN_RANLUX3 || pk.prn_kind == PRN_XOR128 || pk.prn_kind == PRN_PM || pk.prn_kind == PRN_MRG32K3A) &&
+                               (uint32_t)samples >= 3u * (uint32_t)(c.nhit + 1) * (uint32_t)c.nhitpar;
+                if (fusable) {
+                    a.prn_kind = pk.prn_kind; a.prn_table = (uint32_t*)buf_ptr(h, pk, 0);
+                    a.prn_instances = (uint32_t)pk.global[0]; a.prn_samples = (uint32_t)samples;
+                    pbuf.pending_produce = 0;
+                    fused = true;
+                } else if (flush_pending(h, pb) < 0) return -1;
+            }
+            if (!fused) {
+                a.prn_kind = PRN_BUFFERED; a.prns = pbuf.dptr;
+                size_t need = (size_t)a.geom.prngstep * (3u * (c.nhit + 1) * c.nhitpar - 1) + a.geom.nthreads;
+                if (pbuf.bytes < need * 16) return fail(h, "kernel %s: PRN buffer holds %zu vec4, the pass may read %zu", k.name.c_str(), pbuf.bytes / 16, need);
+            }
+            CUDA_OK(h, fn(a, st));
+            break;
+        }
+        case K_CLEAR: {
+            int b = buf_id(k, 0);
+            if (!valid_buf(h, b)) return fail(h, "kernel %s: argument 0 not set", k.name.c_str());
+            size_t n = k.global[0];
+            if (n * 16 > h->buffers[b].bytes) n = h->buffers[b].bytes / 16;
+            CUDA_OK(h, launch_clear_double2((double2*)h->buffers[b].dptr, (uint32_t)n, st));
+            break;
+        }
+        case K_MEASURE: case K_MEASURE_PLQ: {
+            MeasureArgs a;
+            memset(&a, 0, sizeof(a));
+            a.table = buf_ptr(h, k, 0); a.params = buf_ptr(h, k, 2);
+            double2* out = (double2*)buf_ptr(h, k, 1);
+            if (!a.table || !a.params || !out) return fail(h, "kernel %s: arguments (table, measurement, parameters) not set", k.name.c_str());
+            if (c.fmunu || c.f0mu) return fail(h, "kernel %s: the FMUNU/F0MU variants are not implemented in qcdgpu_b200", k.name.c_str());
+            a.geom = make_geom(c); a.tbc = c.tbc ? 1 : 0;
+            if (k.kind == K_MEASURE) a.out_action = out; else a.out_plq = out;
+            a.first_site = c.biglat ? a.geom.n234 : 0;
+            a.nsites = c.biglat ? (c.n1 - 2) * a.geom.n234 : a.geom.sites;
+            a.block = (uint32_t)k.local0;
+            size_t blocks = (a.nsites + a.block - 1) / a.block;
+            if (h->buffers[buf_id(k, 1)].bytes < blocks * 16) return fail(h, "kernel %s: measurement buffer too small (%zu partials needed)", k.name.c_str(), blocks);
+            CUDA_OK(h, launch_measure(c.sun, prec, a, st));
+            break;
+        }
+        case K_REDUCE_MEAS: {
+            int size = 0, index = 0;
+            if (!arg_int(k, 3, &size) || !arg_int(k, 4, &index)) return fail(h, "kernel %s: arguments (size, index) not set", k.name.c_str());
+            if (!buf_ptr(h, k, 0) || !buf_ptr(h, k, 1)) return fail(h, "kernel %s: buffers not set", k.name.c_str());
+            CUDA_OK(h, launch_reduce_double2((const double2*)buf_ptr(h, k, 0), 0, (uint32_t)size, (double2*)buf_ptr(h, k, 1), (uint32_t)index, st));
+            break;
+        }
+        case K_REDUCE_PLQ: {
+            int index = 0;
+            if (k.args.size() < 5 || k.args[3].type != Arg::U32X4 || !arg_int(k, 4, &index)) return fail(h, "kernel %s: arguments (param, index) not set", k.name.c_str());
+            if (!buf_ptr(h, k, 0) || !buf_ptr(h, k, 1)) return fail(h, "kernel %s: buffers not set", k.name.c_str());
+            CUDA_OK(h, launch_reduce_double2((const double2*)buf_ptr(h, k, 0), 0, k.args[3].u4[0], (double2*)buf_ptr(h, k, 1), (uint32_t)index, st));
+            break;
+        }
+        case K_POLYAKOV: {
+            PolyakovArgs a;
+            memset(&a, 0, sizeof(a));
+            int offset = 0;
+            a.table = buf_ptr(h, k, 0); a.out = (double2*)buf_ptr(h, k, 1); a.params = buf_ptr(h, k, 2);
+            if (!a.table || !a.out || !a.params || !arg_int(k, 4, &offset)) return fail(h, "kernel %s: arguments not set", k.name.c_str());
+            a.geom = make_geom(c); a.tbc = c.tbc ? 1 : 0; a.offset = (uint32_t)offset; a.pl_level = c.pl;
+            a.x_first = c.biglat ? 1 : 0; a.x_count = c.biglat ? c.n1 - 2 : c.n1;
+            a.block = (uint32_t)k.local0;
+            size_t blocks = ((size_t)a.x_count * a.geom.n23 + a.block - 1) / a.block;
+            if (h->buffers[buf_id(k, 1)].bytes < ((c.pl > 1 ? (size_t)offset : 0) + blocks) * 16) return fail(h, "kernel %s: measurement buffer too small", k.name.c_str());
+            CUDA_OK(h, launch_polyakov(c.sun, prec, a, st));
+            break;
+        }
+        case K_REDUCE_POLYAKOV: {
+            int index = 0;
+            if (k.args.size() < 5 || k.args[3].type != Arg::U32X4 || !arg_int(k, 4, &index)) return fail(h, "kernel %s: arguments (param, index) not set", k.name.c_str());
+            const uint32_t* p = k.args[3].u4;   // size, offset, offset2  (polyakov.cl:405-432)
+            CUDA_OK(h, launch_reduce_double2((const double2*)buf_ptr(h, k, 0), 0, p[0], (double2*)buf_ptr(h, k, 1), (uint32_t)index, st));
+            if (c.pl >= 2) {
+                CUDA_OK(h, launch_reduce_double2((const double2*)buf_ptr(h, k, 0), p[1], p[0], (double2*)buf_ptr(h, k, 1), (uint32_t)index + p[2], st));
+                h->launches++;
+            }
+            break;
+        }
+        case K_RANLUX_INIT: {
+            if (!buf_ptr(h, k, 0) || !buf_ptr(h, k, 1)) return fail(h, "kernel %s: arguments (seeds, seedtable) not set", k.name.c_str());
+            if (h->buffers[buf_id(k, 1)].bytes < k.global[0] * 26 * 4) return fail(h, "kernel %s: seed table too small", k.name.c_str());
+            CUDA_OK(h, launch_ranlux_init((const uint32_t*)buf_ptr(h, k, 0), (uint32_t*)buf_ptr(h, k, 1), (uint32_t)k.global[0], st));
+            break;
+        }
+        case K_PRODUCE: {
+            int pb = buf_id(k, 1);
+            int samples = 0;
+            if (!buf_ptr(h, k, 0) || !valid_buf(h, pb) || !arg_int(k, 2, &samples)) return fail(h, "kernel %s: arguments (seed table, prns, samples) not set", k.name.c_str());
+            if (c.prng_precision == 2) return fail(h, "kernel %s: PRNG_PRECISION=2 (double PRNs) is not implemented", k.name.c_str());
+            if (h->buffers[pb].bytes < (size_t)k.global[0] * samples * 16) return fail(h, "kernel %s: PRN buffer too small", k.name.c_str());
+            if (flush_pending(h, pb) < 0) return -1;   // an unconsumed earlier produce() must still advance the streams
+            if (h->fused) { h->buffers[pb].pending_produce = kid; return 0; }   // decided at the consumer
+            CUDA_OK(h, launch_prn_produce(k.prn_kind, (uint32_t*)buf_ptr(h, k, 0), h->buffers[pb].dptr, (uint32_t)k.global[0], (uint32_t)samples, st));
+            break;
+        }
+        default:
+            return fail(h, "kernel '%s' is not implemented in qcdgpu_b200", k.name.c_str());
+    }
+    h->launches++;
+    return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* qgpu_version(void) { return "qcdgpu_b200 0.1 (sm_100a)"; }
+
+// glibc srand()/rand() are part of the reference's stream definition (random.cpp:235, 462-465): bulk helpers so that
+// hosts written in languages with slow FFI can build seed tables of millions of instances quickly.
+void qgpu_host_srand(unsigned seed) { srand(seed); }
+void qgpu_host_rand_fill(uint32_t* out, size_t n, uint32_t modulo, uint32_t add) {
+    for (size_t i = 0; i < n; i++) { uint32_t r = (uint32_t)rand(); if (modulo) r %= modulo; out[i] = r + add; }
+}
+
+qgpu* qgpu_create(void) { return new qgpu(); }
+void qgpu_destroy(qgpu* h) {
+    if (!h) return;
+    if (h->initialized) qgpu_device_finalize(h, 0);
+    delete h;
+}
+void qgpu_set_limit_max_workgroup_size(qgpu* h, unsigned limit) { h->limit_wg = limit; }
+void qgpu_set_max_memory_width(qgpu* h, size_t w) { h->max_memory_width = w; if (h->initialized) h->info.max_memory_width = w; }
+void qgpu_set_debug(qgpu* h, int profiling, int brief, int stage) { h->profiling = profiling != 0; h->brief = brief != 0; h->show_stage = stage != 0; }
+void qgpu_set_error_mode(qgpu* h, int r) { h->return_errors = r != 0; }
+const char* qgpu_last_error(qgpu* h) { return h->last_error.c_str(); }
+void qgpu_set_async(qgpu* h, int on) { h->async = on != 0; }
+void qgpu_set_fused_prng(qgpu* h, int on) { h->fused = on != 0; }
+uint64_t qgpu_launch_count(qgpu* h) { return h->launches; }
+void* qgpu_stream(qgpu* h) { return (void*)h->stream; }
+
+int qgpu_device_select(qgpu* h, unsigned platform_id, unsigned device_id) {
+    if (platform_id != 0) return fail(h, "only platform 0 (CUDA) exists, got %u", platform_id);
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) return fail(h, "no CUDA device: %s -- qcdgpu_b200 has no CPU fallback", cudaGetErrorString(e));
+    if ((int)device_id >= n) return fail(h, "device %u requested, %d present", device_id, n);
+    h->device = (int)device_id;
+    return 1;
+}
+int qgpu_device_initialize(qgpu* h) {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) return fail(h, "no CUDA device: %s -- qcdgpu_b200 has no CPU fallback", cudaGetErrorString(e));
+    CUDA_OK(h, cudaSetDevice(h->device));
+    cudaDeviceProp p;
+    CUDA_OK(h, cudaGetDeviceProperties(&p, h->device));
+    if (p.major < 10) return fail(h, "device %s is sm_%d%d; this library contains only sm_100a code", p.name, p.major, p.minor);
+    CUDA_OK(h, cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    CUDA_OK(h, cudaEventCreate(&h->ev0)); CUDA_OK(h, cudaEventCreate(&h->ev1));
+    CUDA_OK(h, cudaEventCreate(&h->evp0)); CUDA_OK(h, cudaEventCreate(&h->evp1));
+    CUDA_OK(h, cudaEventCreateWithFlags(&h->ev_halo, cudaEventDisableTiming));
+    memset(&h->info, 0, sizeof(h->info));
+    snprintf(h->info.device_name, sizeof(h->info.device_name), "%s", p.name);
+    h->info.local_memory_size = p.sharedMemPerBlockOptin;
+    h->info.max_constant_size = p.totalConstMem;
+    h->info.max_memory_size = p.totalGlobalMem;
+    // clinterface.cpp:395-401,454: max work-group size, optionally limited (QCDGPU.cpp:74 -> 64)
+    size_t wg = (size_t)p.maxThreadsPerBlock;
+    if (h->limit_wg && h->limit_wg < wg) wg = h->limit_wg;
+    h->info.max_workgroup_size = wg;
+    h->info.memory_align_factor = wg;
+    // clinterface.cpp:419-421: default PRNG instance count = CL_DEVICE_IMAGE3D_MAX_WIDTH (16384 on NVIDIA's OpenCL)
+    h->info.max_memory_width = h->max_memory_width ? h->max_memory_width : (size_t)p.maxTexture3D[0];
+    if (!h->info.max_memory_width) h->info.max_memory_width = 32;
+    h->info.sm_count = p.multiProcessorCount; h->info.cc_major = p.major; h->info.cc_minor = p.minor;
+    h->initialized = true;
+    return n;
+}
+int qgpu_device_finalize(qgpu* h, int error_code) {
+    if (!h->initialized) return error_code;
+    cudaSetDevice(h->device);
+    cudaStreamSynchronize(h->stream);
+    for (size_t i = 1; i < h->buffers.size(); i++) {
+        if (h->buffers[i].dptr) cudaFree(h->buffers[i].dptr);
+        if (h->buffers[i].shadow) cudaFreeHost(h->buffers[i].shadow);
+        h->buffers[i] = Buffer();
+    }
+    cudaEventDestroy(h->ev0); cudaEventDestroy(h->ev1); cudaEventDestroy(h->evp0); cudaEventDestroy(h->evp1); cudaEventDestroy(h->ev_halo);
+    cudaStreamDestroy(h->stream);
+    h->stream = nullptr; h->initialized = false;
+    return error_code;
+}
+int qgpu_get_device_info(qgpu* h, qgpu_device_info* out) {
+    if (!h->initialized) return fail(h, "device not initialized");
+    *out = h->info;
+    return 0;
+}
+
+int qgpu_program_create(qgpu* h, const char* /*source*/, const char* options) {
+    ProgramCfg c;
+    parse_options(options, c);
+    if (c.has_lattice) {
+        if (c.sun != 2 && c.sun != 3) return fail(h, "program_create: SUN=%d is not supported (2 or 3)", c.sun);
+        if (c.nd != 4) return fail(h, "program_create: ND=%d is not supported (4)", c.nd);
+        if (!c.n1 || !c.n2 || !c.n3 || !c.n4) return fail(h, "program_create: N1..N4 missing in '%s'", c.options.c_str());
+        if (c.n2 & 1) return fail(h, "program_create: N2 must be even for the checkerboard (sun_common.cl:351-380)");
+        if ((uint64_t)c.n1 * c.n2 * c.n3 * c.n4 > 0xffffffffull) return fail(h, "program_create: more than 2^32 sites");
+    }
+    h->programs.push_back(c);
+    h->active_program = (int)h->programs.size() - 1;
+    return h->active_program;
+}
+int qgpu_program_set_active(qgpu* h, int id) {
+    if (id <= 0 || id >= (int)h->programs.size()) return fail(h, "program_set_active: bad id %d", id);
+    h->active_program = id; return id;
+}
+int qgpu_program_get_active(qgpu* h) { return h->active_program; }
+
+int qgpu_kernel_init(qgpu* h, const char* name, unsigned dims, const size_t* global, const size_t* local) {
+    if (!h->active_program) return fail(h, "kernel_init('%s') before program_create", name);
+    Kernel k;
+    k.name = name; k.program = h->active_program;
+    for (const NameMap& m : kNames) if (k.name == m.name) { k.kind = m.kind; k.dir = m.dir; k.odd = m.odd; k.prn_kind = m.prn; }
+    if (k.kind == K_NONE) return fail(h, "kernel '%s' is not implemented in qcdgpu_b200", name);
+    if (k.kind == K_PRODUCE && k.prn_kind < 0) {
+        k.prn_kind = ranlux_kind(h->programs[k.program].rl_skip);
+        if (k.prn_kind < 0) return fail(h, "kernel ranlux: RL_skip=%d is not one of 24/48/97/223/389", h->programs[k.program].rl_skip);
+    }
+    for (unsigned i = 0; i < dims && i < 3; i++) k.global[i] = global[i];
+    // clinterface.cpp:1158-1169: explicit local size wins, else the (limited) kernel work-group size
+    if (local && local[0]) { k.local0 = local[0]; k.local_given = true; }
+    else k.local0 = (k.kind == K_UPDATE || k.kind == K_OVERRELAX) ? 128 : (h->limit_wg ? h->limit_wg : 128);
+    if (k.local0 > 128 && (k.kind == K_MEASURE || k.kind == K_MEASURE_PLQ || k.kind == K_POLYAKOV)) k.local0 = 128;
+    h->kernels.push_back(k);
+    return (int)h->kernels.size() - 1;
+}
+static int push_arg(qgpu* h, int kid, const Arg& a) {
+    if (!valid_kernel(h, kid)) return fail(h, "bad kernel id %d", kid);
+    h->kernels[kid].args.push_back(a);
+    return (int)h->kernels[kid].args.size();
+}
+int qgpu_kernel_init_buffer(qgpu* h, int kid, int bid) {
+    if (!valid_buf(h, bid)) return fail(h, "kernel_init_buffer: bad buffer id %d", bid);
+    Arg a; memset(&a, 0, sizeof(a)); a.type = Arg::BUF; a.buf = bid; return push_arg(h, kid, a);
+}
+int qgpu_kernel_init_constant_int(qgpu* h, int kid, const int* p) { Arg a; memset(&a, 0, sizeof(a)); a.type = Arg::I32; a.i = *p; return push_arg(h, kid, a); }
+int qgpu_kernel_init_constant_uint4(qgpu* h, int kid, const uint32_t p[4]) { Arg a; memset(&a, 0, sizeof(a)); a.type = Arg::U32X4; memcpy(a.u4, p, 16); return push_arg(h, kid, a); }
+int qgpu_kernel_init_constant_float(qgpu* h, int kid, const float* p) { Arg a; memset(&a, 0, sizeof(a)); a.type = Arg::F32; a.f = *p; return push_arg(h, kid, a); }
+int qgpu_kernel_init_constant_double(qgpu* h, int kid, const double* p) { Arg a; memset(&a, 0, sizeof(a)); a.type = Arg::F64; a.d = *p; return push_arg(h, kid, a); }
+int qgpu_kernel_init_constant_reset(qgpu* h, int kid, const int* p, int argument_id) {
+    // clinterface.cpp:1225-1229: sets argument `argument_id`; the reference's callers pass the value RETURNED by the
+    // preceding kernel_init_constant, i.e. the index of the next, not yet set, argument (suncl.cpp:3415, 5267)
+    if (!valid_kernel(h, kid)) return fail(h, "bad kernel id %d", kid);
+    Kernel& k = h->kernels[kid];
+    if (argument_id < 0) return fail(h, "kernel_init_constant_reset: bad argument id %d", argument_id);
+    if ((size_t)argument_id >= k.args.size()) { Arg z; memset(&z, 0, sizeof(z)); z.type = Arg::I32; k.args.resize(argument_id + 1, z); }
+    k.args[argument_id].type = Arg::I32; k.args[argument_id].i = *p;
+    return argument_id;
+}
+int qgpu_kernel_get_worksize(qgpu* h, int kid) {
+    if (!valid_kernel(h, kid)) return fail(h, "bad kernel id %d", kid);
+    return (int)h->kernels[kid].local0;
+}
+int qgpu_kernel_run(qgpu* h, int kid) {
+    if (!h->initialized) return fail(h, "kernel_run before device_initialize");
+    if (!valid_kernel(h, kid)) return fail(h, "kernel_run: bad kernel id %d", kid);
+    CUDA_OK(h, cudaSetDevice(h->device));
+    if (h->profiling) CUDA_OK(h, cudaEventRecord(h->evp0, h->stream));
+    if (launch_kernel(h, kid) < 0) return -1;
+    if (h->profiling) {
+        CUDA_OK(h, cudaEventRecord(h->evp1, h->stream));
+        CUDA_OK(h, cudaEventSynchronize(h->evp1));
+        float ms = 0; CUDA_OK(h, cudaEventElapsedTime(&ms, h->evp0, h->evp1));
+        Kernel& k = h->kernels[kid];
+        double ns = (double)ms * 1e6; k.t_sum += ns; k.t_sq += ns * ns; k.starts++;
+    }
+    if (!h->async) CUDA_OK(h, cudaStreamSynchronize(h->stream));
+    return kid;
+}
+int qgpu_kernel_get_execution_time(qgpu* h, int kid, double* mean, double* dev, int* number) {
+    if (!valid_kernel(h, kid)) return fail(h, "bad kernel id %d", kid);
+    Kernel& k = h->kernels[kid];
+    double m = k.starts ? k.t_sum / k.starts : 0.0;
+    double v = k.starts > 1 ? (k.t_sq - k.starts * m * m) / (k.starts - 1) : 0.0;
+    if (mean) *mean = m; if (dev) *dev = v > 0 ? sqrt(v) : 0.0; if (number) *number = k.starts;
+    return 0;
+}
+
+int qgpu_buffer_init(qgpu* h, int type, size_t size, const void* host_ptr, size_t size_of) {
+    if (!h->initialized) return fail(h, "buffer_init before device_initialize");
+    CUDA_OK(h, cudaSetDevice(h->device));
+    Buffer b;
+    b.type = type; b.size = size; b.size_of = size_of; b.bytes = size * size_of; b.host_ptr = host_ptr; b.alive = true;
+    if (type != QGPU_BUFFER_LDS && b.bytes) {
+        CUDA_OK(h, cudaMalloc(&b.dptr, b.bytes));
+        bool copy = host_ptr && (type == QGPU_BUFFER_INPUT || type == QGPU_BUFFER_CONSTANT || type == QGPU_BUFFER_IO);
+        if (copy) CUDA_OK(h, cudaMemcpyAsync(b.dptr, host_ptr, b.bytes, cudaMemcpyHostToDevice, h->stream));
+        else CUDA_OK(h, cudaMemsetAsync(b.dptr, 0, b.bytes, h->stream));
+        CUDA_OK(h, cudaStreamSynchronize(h->stream));   // host_ptr may be freed by the caller right after (blocking write, clinterface.cpp:1393-1410)
+    }
+    h->buffers.push_back(b);
+    return (int)h->buffers.size() - 1;
+}
+int qgpu_buffer_write(qgpu* h, int bid) {
+    if (!valid_buf(h, bid)) return fail(h, "buffer_write: bad buffer id %d", bid);
+    Buffer& b = h->buffers[bid];
+    if (!b.dptr || !b.host_ptr) return 0;
+    CUDA_OK(h, cudaSetDevice(h->device));
+    if (flush_pending(h, bid) < 0) return -1;
+    CUDA_OK(h, cudaMemcpyAsync(b.dptr, b.host_ptr, b.bytes, cudaMemcpyHostToDevice, h->stream));
+    CUDA_OK(h, cudaStreamSynchronize(h->stream));
+    return 0;
+}
+void* qgpu_buffer_map_range(qgpu* h, int bid, size_t off, size_t len) {
+    if (!valid_buf(h, bid)) { fail(h, "buffer_map: bad buffer id %d", bid); return nullptr; }
+    Buffer& b = h->buffers[bid];
+    if (!b.dptr) { fail(h, "buffer_map: buffer %d has no device storage (LDS)", bid); return nullptr; }
+    if (off + len > b.bytes) { fail(h, "buffer_map: range [%zu,+%zu) outside buffer of %zu bytes", off, len, b.bytes); return nullptr; }
+    CUDA_OKP(h, cudaSetDevice(h->device));
+    if (flush_pending(h, bid) < 0) return nullptr;
+    if (!b.shadow) CUDA_OKP(h, cudaMallocHost(&b.shadow, b.bytes));      // pinned: D2H at full PCIe rate
+    CUDA_OKP(h, cudaMemcpyAsync((char*)b.shadow + off, (char*)b.dptr + off, len, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_OKP(h, cudaStreamSynchronize(h->stream));
+    b.map_off = off; b.map_len = len;
+    return (char*)b.shadow + off;
+}
+void* qgpu_buffer_map(qgpu* h, int bid) {
+    if (!valid_buf(h, bid)) { fail(h, "buffer_map: bad buffer id %d", bid); return nullptr; }
+    return qgpu_buffer_map_range(h, bid, 0, h->buffers[bid].bytes);
+}
+int qgpu_buffer_unmap(qgpu* h, int bid, void* ptr) {
+    if (!valid_buf(h, bid)) return fail(h, "buffer_unmap: bad buffer id %d", bid);
+    Buffer& b = h->buffers[bid];
+    if (!b.shadow || !ptr) return 0;
+    size_t off = (char*)ptr - (char*)b.shadow;
+    if (off != b.map_off) return fail(h, "buffer_unmap: pointer does not match the mapped range");
+    CUDA_OK(h, cudaSetDevice(h->device));
+    CUDA_OK(h, cudaMemcpyAsync((char*)b.dptr + off, ptr, b.map_len, cudaMemcpyHostToDevice, h->stream));
+    CUDA_OK(h, cudaStreamSynchronize(h->stream));
+    return 0;
+}
+int qgpu_buffer_kill(qgpu* h, int bid) {
+    if (!valid_buf(h, bid)) return fail(h, "buffer_kill: bad buffer id %d", bid);
+    Buffer& b = h->buffers[bid];
+    CUDA_OK(h, cudaSetDevice(h->device));
+    CUDA_OK(h, cudaStreamSynchronize(h->stream));
+    if (b.dptr) cudaFree(b.dptr);
+    if (b.shadow) cudaFreeHost(b.shadow);
+    b = Buffer();
+    return 0;
+}
+size_t qgpu_buffer_size_bytes(qgpu* h, int bid) { return valid_buf(h, bid) ? h->buffers[bid].bytes : 0; }
+unsigned qgpu_buffer_size_align_step(qgpu*, unsigned size, unsigned step) { return (1 + (size - 1) / step) * step; }   // clinterface.cpp:1587-1590
+unsigned qgpu_buffer_size_align(qgpu* h, unsigned size) { return qgpu_buffer_size_align_step(h, size, (unsigned)h->info.max_workgroup_size); }
+void* qgpu_buffer_device_ptr(qgpu* h, int bid) { return valid_buf(h, bid) ? h->buffers[bid].dptr : nullptr; }
+
+int qgpu_synchronize(qgpu* h) {
+    CUDA_OK(h, cudaSetDevice(h->device));
+    CUDA_OK(h, cudaStreamSynchronize(h->stream));
+    return 0;
+}
+int qgpu_timer_start(qgpu* h) { CUDA_OK(h, cudaSetDevice(h->device)); CUDA_OK(h, cudaEventRecord(h->ev0, h->stream)); return 0; }
+int qgpu_timer_stop(qgpu* h, float* ms) {
+    CUDA_OK(h, cudaSetDevice(h->device));
+    CUDA_OK(h, cudaEventRecord(h->ev1, h->stream));
+    CUDA_OK(h, cudaEventSynchronize(h->ev1));
+    CUDA_OK(h, cudaEventElapsedTime(ms, h->ev0, h->ev1));
+    return 0;
+}
+int qgpu_update_kernel_registers(qgpu* h, int program, int dir, int prn_kind) {
+    if (program <= 0 || program >= (int)h->programs.size()) return -1;
+    const ProgramCfg& c = h->programs[program];
+    return update_kernel_regs(c.sun, prec_index(c), dir, c.tbc ? 1 : 0, prn_kind);
+}
+
+// ---------------------------------------------------------------- BigLattice halo exchange
+static int planes_of(const ProgramCfg& c, int dir) { int per = (c.sun == 3) ? 3 : 1; return dir >= 0 ? per : 4 * per; }
+size_t qgpu_halo_bytes(qgpu* h, int program, int dir) {
+    if (program <= 0 || program >= (int)h->programs.size()) return 0;
+    const ProgramCfg& c = h->programs[program];
+    return (size_t)planes_of(c, dir) * c.n2 * c.n3 * c.n4 * (prec_index(c) ? 32 : 16);
+}
+int qgpu_halo_copy(qgpu* dst, int dprog, int dbuf, unsigned xd, qgpu* src, int sprog, int sbuf, unsigned xs, int dir) {
+    if (dprog <= 0 || dprog >= (int)dst->programs.size() || sprog <= 0 || sprog >= (int)src->programs.size()) return fail(dst, "halo_copy: bad program id");
+    if (!valid_buf(dst, dbuf) || !valid_buf(src, sbuf)) return fail(dst, "halo_copy: bad buffer id");
+    const ProgramCfg& cd = dst->programs[dprog]; const ProgramCfg& cs = src->programs[sprog];
+    if (cd.n2 != cs.n2 || cd.n3 != cs.n3 || cd.n4 != cs.n4 || cd.sun != cs.sun || prec_index(cd) != prec_index(cs)) return fail(dst, "halo_copy: geometry mismatch");
+    if (xd >= cd.n1 || xs >= cs.n1) return fail(dst, "halo_copy: slice out of range");
+    Geom gd = make_geom(cd), gs = make_geom(cs);
+    CUDA_OK(dst, cudaSetDevice(dst->device));
+    if (src != dst) {
+        if (src->device != dst->device) {
+            int can = 0; CUDA_OK(dst, cudaDeviceCanAccessPeer(&can, dst->device, src->device));
+            if (!can) return fail(dst, "halo_copy: device %d cannot access device %d peer memory", dst->device, src->device);
+            cudaError_t e = cudaDeviceEnablePeerAccess(src->device, 0);
+            if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) return fail(dst, "cudaDeviceEnablePeerAccess: %s", cudaGetErrorString(e));
+            cudaGetLastError();
+        }
+        // order after everything queued on the source stream
+        CUDA_OK(dst, cudaSetDevice(src->device));
+        CUDA_OK(dst, cudaEventRecord(src->ev_halo, src->stream));
+        CUDA_OK(dst, cudaSetDevice(dst->device));
+        CUDA_OK(dst, cudaStreamWaitEvent(dst->stream, src->ev_halo, 0));
+    }
+    int np = planes_of(cd, dir), p0 = dir >= 0 ? dir : 0, ps = dir >= 0 ? 4 : 1;
+    CUDA_OK(dst, launch_copy_planes(prec_index(cd), dst->buffers[dbuf].dptr, gd.rowsize, xd, p0, ps,
+                                    src->buffers[sbuf].dptr, gs.rowsize, xs, p0, ps, gd.n234, np, dst->stream));
+    dst->launches++;
+    if (!dst->async) CUDA_OK(dst, cudaStreamSynchronize(dst->stream));
+    return 0;
+}
+int qgpu_halo_pack(qgpu* h, int program, int buffer, unsigned xs, int dir, void* packed, size_t* bytes) {
+    if (program <= 0 || program >= (int)h->programs.size() || !valid_buf(h, buffer)) return fail(h, "halo_pack: bad id");
+    const ProgramCfg& c = h->programs[program];
+    Geom g = make_geom(c);
+    if (xs >= c.n1) return fail(h, "halo_pack: slice out of range");
+    int np = planes_of(c, dir), p0 = dir >= 0 ? dir : 0, ps = dir >= 0 ? 4 : 1;
+    CUDA_OK(h, cudaSetDevice(h->device));
+    CUDA_OK(h, launch_copy_planes(prec_index(c), packed, g.n234, 0, 0, 1, h->buffers[buffer].dptr, g.rowsize, xs, p0, ps, g.n234, np, h->stream));
+    h->launches++;
+    if (bytes) *bytes = qgpu_halo_bytes(h, program, dir);
+    if (!h->async) CUDA_OK(h, cudaStreamSynchronize(h->stream));
+    return 0;
+}
+int qgpu_halo_unpack(qgpu* h, int program, int buffer, unsigned xd, int dir, const void* packed) {
+    if (program <= 0 || program >= (int)h->programs.size() || !valid_buf(h, buffer)) return fail(h, "halo_unpack: bad id");
+    const ProgramCfg& c = h->programs[program];
+    Geom g = make_geom(c);
+    if (xd >= c.n1) return fail(h, "halo_unpack: slice out of range");
+    int np = planes_of(c, dir), p0 = dir >= 0 ? dir : 0, ps = dir >= 0 ? 4 : 1;
+    CUDA_OK(h, cudaSetDevice(h->device));
+    CUDA_OK(h, launch_copy_planes(prec_index(c), h->buffers[buffer].dptr, g.rowsize, xd, p0, ps, packed, g.n234, 0, 0, 1, g.n234, np, h->stream));
+    h->launches++;
+    if (!h->async) CUDA_OK(h, cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,267 @@
+// lattice.cuh -- geometry, SoA link table access and SU(2)/SU(3) algebra for the
+// sm_100a gauge-update kernels.
+//
+// Layout contract (must stay bit-compatible with the reference):
+//   site index   gid = y + z*N2 + t*N2*N3 + x*N2*N3*N4          (SU(N)/suncl/sun_common.cl:41-66)
+//   link table   element (gid + (dir + 4*k)*ROWSIZE) of a vec4 array, k = vec4 number
+//                SU(2): 1 vec4 (Re u1, Re u2, Im u1, Im u2)         (su2cl.cl:62-79)
+//                SU(3): uv1=(Re u1,Re u2,Re u3,Re v3) uv2=(Im ...) uv3=(Re v1,Re v2,Im v1,Im v2)
+//                                                                  (su3cl.cl:137-163, su3_matrix_memory.cl:43-55)
+//   vec4 = float4 (16 B) for PRECISION 0/2, double4 (32 B = one DRAM sector) for PRECISION 1.
+//
+// Everything here is new code for Blackwell: fp64 planes move with single 256-bit
+// LDG/STG (ld.global.v4.f64, SASS LDG.E.256), fp32 planes with 128-bit ones; the
+// algebra is written for FMA contraction and for the 2-row storage (third row =
+// conj(u x v)), not transcribed from the OpenCL polynomials.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace qcd {
+
+// ---------------------------------------------------------------- geometry
+struct Geom {
+    uint32_t n1, n2, n3, n4;      // x, y, z, t extents of the (sub)lattice as stored (BIGLAT: incl. 2 halo x-slices)
+    uint32_t n23, n234, sites;    // products
+    uint32_t rowsize;             // ROWSIZE  (suncl.cpp:2272)
+    uint32_t prngstep;            // PRNGSTEP (suncl.cpp:2273)
+    uint32_t nthreads;            // update threads: SITES/2, BIGLAT: (N1-2)*N2N3N4/2  (suncl.cl:404-418)
+    uint32_t biglat;              // -D BIGLAT
+    uint32_t left_sites;          // LEFT_SITES
+    uint32_t full_sites;          // FULL_SITES
+    uint32_t nhit, nhitpar;
+    uint32_t tw_lo, tw_hi;        // BIGLAT twist test: x + left_sites/n234 == tw_lo || == tw_hi
+};
+
+struct Coord { uint32_t x, y, z, t; };
+
+__device__ __forceinline__ Coord gid_to_coords(const Geom& g, uint32_t gdi) {
+    // sun_common.cl:41-61
+    Coord c;
+    uint32_t z4 = gdi / g.n234;
+    uint32_t z1 = gdi - z4 * g.n234;
+    uint32_t z3 = z1 / g.n23;
+    z1 = z1 - z3 * g.n23;
+    uint32_t z2 = z1 / g.n2;
+    z1 = z1 - z2 * g.n2;
+    c.x = z4; c.y = z1; c.z = z2; c.t = z3;
+    return c;
+}
+__device__ __forceinline__ uint32_t coords_to_gid(const Geom& g, const Coord& c) {
+    return c.y + c.z * g.n2 + c.t * g.n23 + c.x * g.n234;
+}
+// checkerboard maps, sun_common.cl:351-417 (BIGLAT variants add one x-slice)
+__device__ __forceinline__ uint32_t parity_gid(const Geom& g, uint32_t GID, bool odd) {
+    uint32_t gde = 2u * GID + (odd ? 1u : 0u);
+    Coord c = gid_to_coords(g, gde);
+    uint32_t par = (c.x + c.y + c.z + c.t) & 1u;
+    uint32_t gindex = odd ? gde - (par ^ 1u) : gde + par;
+    if (g.biglat) gindex += g.n234;
+    return gindex;
+}
+template <int DIR> __device__ __forceinline__ Coord nb_plus(const Geom& g, Coord c) {
+    // sun_common.cl:455-483
+    if (DIR == 0) { c.x++; if (!g.biglat && c.x >= g.n1) c.x = 0; }
+    if (DIR == 1) { c.y++; if (c.y >= g.n2) c.y = 0; }
+    if (DIR == 2) { c.z++; if (c.z >= g.n3) c.z = 0; }
+    if (DIR == 3) { c.t++; if (c.t >= g.n4) c.t = 0; }
+    return c;
+}
+template <int DIR> __device__ __forceinline__ Coord nb_minus(const Geom& g, Coord c) {
+    // sun_common.cl:485-513
+    if (DIR == 0) { if (c.x == 0) c.x = g.n1; c.x--; }
+    if (DIR == 1) { if (c.y == 0) c.y = g.n2; c.y--; }
+    if (DIR == 2) { if (c.z == 0) c.z = g.n3; c.z--; }
+    if (DIR == 3) { if (c.t == 0) c.t = g.n4; c.t--; }
+    return c;
+}
+__device__ __forceinline__ bool twisted_x(const Geom& g, uint32_t x) {
+    // su3_matrix_memory.cl:57-63
+    if (g.biglat) { uint32_t xg = x + g.tw_lo; return (xg == 0u) || (xg == g.tw_hi); }
+    return x == g.n1 - 1u;
+}
+
+// ---------------------------------------------------------------- vec4 memory access
+template <typename R> struct V4 { R x, y, z, w; };
+
+__device__ __forceinline__ V4<double> ldv4(const double* p) {
+    V4<double> v;   // one 256-bit load = one 32-byte sector (sm_100+: LDG.E.256)
+    asm volatile("ld.global.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(v.x), "=d"(v.y), "=d"(v.z), "=d"(v.w) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ V4<float> ldv4(const float* p) {
+    float4 t = *reinterpret_cast<const float4*>(p);
+    V4<float> v = { t.x, t.y, t.z, t.w };
+    return v;
+}
+__device__ __forceinline__ void stv4(double* p, const V4<double>& v) {
+    asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" :: "l"(p), "d"(v.x), "d"(v.y), "d"(v.z), "d"(v.w) : "memory");
+}
+__device__ __forceinline__ void stv4(float* p, const V4<float>& v) {
+    *reinterpret_cast<float4*>(p) = make_float4(v.x, v.y, v.z, v.w);
+}
+template <typename R>
+__device__ __forceinline__ V4<R> ld_plane(const R* table, const Geom& g, uint32_t gindex, uint32_t plane) {
+    return ldv4(table + 4 * (size_t(gindex) + size_t(plane) * g.rowsize));
+}
+template <typename R>
+__device__ __forceinline__ void st_plane(R* table, const Geom& g, uint32_t gindex, uint32_t plane, const V4<R>& v) {
+    stv4(table + 4 * (size_t(gindex) + size_t(plane) * g.rowsize), v);
+}
+
+// ---------------------------------------------------------------- complex + matrices
+template <typename R> struct Cx { R re, im; };
+
+template <typename R> __device__ __forceinline__ Cx<R> cmul(Cx<R> a, Cx<R> b) {
+    return { a.re * b.re - a.im * b.im, a.re * b.im + a.im * b.re };
+}
+template <typename R> __device__ __forceinline__ Cx<R> cmulc(Cx<R> a, Cx<R> b) {   // a * conj(b)
+    return { a.re * b.re + a.im * b.im, a.im * b.re - a.re * b.im };
+}
+template <typename R> __device__ __forceinline__ void cfma(Cx<R>& acc, Cx<R> a, Cx<R> b) {       // acc += a*b
+    acc.re += a.re * b.re; acc.re -= a.im * b.im; acc.im += a.re * b.im; acc.im += a.im * b.re;
+}
+template <typename R> __device__ __forceinline__ void cfmac(Cx<R>& acc, Cx<R> a, Cx<R> b) {      // acc += a*conj(b)
+    acc.re += a.re * b.re; acc.re += a.im * b.im; acc.im += a.im * b.re; acc.im -= a.re * b.im;
+}
+template <typename R> __device__ __forceinline__ void cfmacc(Cx<R>& acc, Cx<R> a, Cx<R> b) {     // acc += conj(a)*b
+    acc.re += a.re * b.re; acc.re += a.im * b.im; acc.im += a.re * b.im; acc.im -= a.im * b.re;
+}
+
+// 3x3 complex matrix, rows r[0..2], fully in registers
+template <typename R> struct M3 { Cx<R> e[3][3]; };
+// two stored rows (what the table holds)
+template <typename R> struct M3r2 { Cx<R> e[2][3]; };
+
+// third row of an SU(3) matrix from its first two: w = conj(u x v)   (su3cl.cl:156-161)
+template <typename R>
+__device__ __forceinline__ void third_row(const Cx<R> u[3], const Cx<R> v[3], Cx<R> w[3]) {
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+        const int j = (i + 1) % 3, k = (i + 2) % 3;
+        // conj(u_j v_k - u_k v_j)
+        w[i].re =  u[j].re * v[k].re - u[j].im * v[k].im - u[k].re * v[j].re + u[k].im * v[j].im;
+        w[i].im = -u[j].re * v[k].im - u[j].im * v[k].re + u[k].re * v[j].im + u[k].im * v[j].re;
+    }
+}
+template <typename R> __device__ __forceinline__ M3<R> complete(const M3r2<R>& a) {
+    M3<R> m;
+#pragma unroll
+    for (int j = 0; j < 3; j++) { m.e[0][j] = a.e[0][j]; m.e[1][j] = a.e[1][j]; }
+    third_row(m.e[0], m.e[1], m.e[2]);
+    return m;
+}
+
+// full 3x3 product
+template <typename R> __device__ __forceinline__ M3<R> mul_full(const M3<R>& U, const M3<R>& S) {
+    M3<R> W;
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+#pragma unroll
+        for (int j = 0; j < 3; j++) {
+            Cx<R> acc = cmul(U.e[i][0], S.e[0][j]);
+            cfma(acc, U.e[i][1], S.e[1][j]);
+            cfma(acc, U.e[i][2], S.e[2][j]);
+            W.e[i][j] = acc;
+        }
+    return W;
+}
+
+// packed <-> rows
+template <typename R>
+__device__ __forceinline__ M3r2<R> unpack3(const V4<R>& a, const V4<R>& b, const V4<R>& c) {
+    M3r2<R> m;
+    m.e[0][0] = { a.x, b.x }; m.e[0][1] = { a.y, b.y }; m.e[0][2] = { a.z, b.z };
+    m.e[1][0] = { c.x, c.z }; m.e[1][1] = { c.y, c.w }; m.e[1][2] = { a.w, b.w };
+    return m;
+}
+template <typename R>
+__device__ __forceinline__ void pack3(const Cx<R> u[3], const Cx<R> v[3], V4<R>& a, V4<R>& b, V4<R>& c) {
+    a = { u[0].re, u[1].re, u[2].re, v[2].re };
+    b = { u[0].im, u[1].im, u[2].im, v[2].im };
+    c = { v[0].re, v[1].re, v[0].im, v[1].im };
+}
+
+// SU(2) element as quaternion-like 4-vector in the reference's packing
+// (x = Re u1, y = Re u2, z = Im u1, w = Im u2); product su2_matrix_memory.cl:40-53
+template <typename R> __device__ __forceinline__ V4<R> su2_mul(const V4<R>& u, const V4<R>& v) {
+    V4<R> a;
+    a.x = -u.w * v.w + u.x * v.x - u.y * v.y - u.z * v.z;
+    a.z =  u.y * v.w + u.z * v.x - u.w * v.y + u.x * v.z;
+    a.y = -u.z * v.w + u.y * v.x + u.x * v.y + u.w * v.z;
+    a.w =  u.x * v.w + u.w * v.x + u.z * v.y - u.y * v.z;
+    return a;
+}
+template <typename R> __device__ __forceinline__ V4<R> su2_dag(const V4<R>& u) { return { u.x, -u.y, -u.z, -u.w }; }
+
+// ---------------------------------------------------------------- twisted loads
+template <typename R> struct Twist { R c1, s1, c2, s2; };   // cos/sin((phi+omega)/2), cos/sin((omega-phi)/2); SU(2): c1,s1 of phi/2
+
+// lattice_table_3 (su3_matrix_memory.cl:43-115): rows of diag(e^{i(phi+omega)/2}, e^{i(omega-phi)/2}, e^{-i omega}) * U
+template <typename R, int DIR, bool TBC>
+__device__ __forceinline__ M3r2<R> load3(const R* table, const Geom& g, uint32_t gindex, uint32_t x, const Twist<R>& tw) {
+    V4<R> a = ld_plane(table, g, gindex, DIR + 0);
+    V4<R> b = ld_plane(table, g, gindex, DIR + 4);
+    V4<R> c = ld_plane(table, g, gindex, DIR + 8);
+    M3r2<R> m = unpack3(a, b, c);
+    if (TBC && DIR == 1) {
+        if (twisted_x(g, x)) {
+            // the reference multiplies (uv1,uv2) lanes xyz by e^{i(phi+omega)/2} and lane w (= v3) by e^{i(omega-phi)/2},
+            // uv3 (= v1,v2) by e^{i(omega-phi)/2}  (su3_matrix_memory.cl:64-97)
+            const Cx<R> p1 = { tw.c1, tw.s1 }, p2 = { tw.c2, tw.s2 };
+#pragma unroll
+            for (int j = 0; j < 3; j++) { m.e[0][j] = cmul(m.e[0][j], p1); m.e[1][j] = cmul(m.e[1][j], p2); }
+        }
+    }
+    return m;
+}
+// lattice_table_2 (su2_matrix_memory.cl:55-96): Omega * U with Omega = (cos phi/2, 0, sin phi/2, 0)
+template <typename R, int DIR, bool TBC>
+__device__ __forceinline__ V4<R> load2(const R* table, const Geom& g, uint32_t gindex, uint32_t x, const Twist<R>& tw) {
+    V4<R> m = ld_plane(table, g, gindex, DIR);
+    if (TBC && DIR == 1) {
+        if (twisted_x(g, x)) {
+            V4<R> om = { tw.c1, R(0), tw.s1, R(0) };
+            m = su2_mul(om, m);
+        }
+    }
+    return m;
+}
+template <typename R, int DIR>
+__device__ __forceinline__ void store3(R* table, const Geom& g, uint32_t gindex, const Cx<R> u[3], const Cx<R> v[3]) {
+    V4<R> a, b, c;
+    pack3(u, v, a, b, c);
+    st_plane(table, g, gindex, DIR + 0, a);
+    st_plane(table, g, gindex, DIR + 4, b);
+    st_plane(table, g, gindex, DIR + 8, c);
+}
+
+// ---------------------------------------------------------------- Gram-Schmidt (su3_update_cl.cl:228-291)
+template <typename R> __device__ __forceinline__ R rsqrt_r(R x);
+template <> __device__ __forceinline__ double rsqrt_r<double>(double x) { return 1.0 / sqrt(x); }
+template <> __device__ __forceinline__ float  rsqrt_r<float>(float x)   { return 1.0f / sqrtf(x); }
+
+template <typename R>
+__device__ __forceinline__ void gram_schmidt3(Cx<R> u[3], Cx<R> v[3]) {
+    R nu = R(0);
+#pragma unroll
+    for (int j = 0; j < 3; j++) nu += u[j].re * u[j].re + u[j].im * u[j].im;
+    R inu = rsqrt_r(nu);
+#pragma unroll
+    for (int j = 0; j < 3; j++) { u[j].re *= inu; u[j].im *= inu; }
+    Cx<R> sc = { R(0), R(0) };   // v . conj(u)
+#pragma unroll
+    for (int j = 0; j < 3; j++) cfmac(sc, v[j], u[j]);
+    R nv = R(0);
+#pragma unroll
+    for (int j = 0; j < 3; j++) {
+        Cx<R> t = cmul(u[j], sc);
+        v[j].re -= t.re; v[j].im -= t.im;
+        nv += v[j].re * v[j].re + v[j].im * v[j].im;
+    }
+    R inv = rsqrt_r(nv);
+#pragma unroll
+    for (int j = 0; j < 3; j++) { v[j].re *= inv; v[j].im *= inv; }
+}
+
+}  // namespace qcd

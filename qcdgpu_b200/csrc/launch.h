@@ -1,0 +1,68 @@
+// launch.h -- host-side launch interface between the C-ABI backend (backend.cu) and the
+// separately compiled kernel instantiation units (update_inst.cu is built once per
+// (SUN, precision, direction); measure_inst.cu / misc_inst.cu once per (SUN, precision)).
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+#include "lattice.cuh"
+
+namespace qcd {
+
+enum PrnKind : int {
+    PRN_BUFFERED = 0,   // reference-layout float4 buffer
+    PRN_GID      = 1,   // -D GID_UPD closed form
+    PRN_RANLUX3  = 2,   // fused, state in registers (RL_skip = 223)
+    PRN_XOR128   = 3,
+    PRN_PM       = 4,
+    PRN_MRG32K3A = 5,
+    PRN_RANLUX0  = 6, PRN_RANLUX1 = 7, PRN_RANLUX2 = 8, PRN_RANLUX4 = 9,   // buffered-only luxury levels
+};
+
+struct UpdateArgs {
+    void* table;            // R*
+    const void* params;     // R*: [0]=beta/N [1]=phi [2]=omega   (suncl.cpp:3939-3953)
+    Geom geom;
+    int odd;                // 0 even, 1 odd
+    int tbc;
+    int prn_kind;
+    const void* prns;       // float4* (buffered)
+    uint32_t* prn_table;    // generator state (fused)
+    uint32_t prn_instances;
+    uint32_t prn_samples;
+    int overrelax;          // 1: overrelaxation pass instead of heat bath (no PRNs)
+};
+typedef cudaError_t (*UpdateLaunchFn)(const UpdateArgs&, cudaStream_t);
+// [sun-2][prec][mu]
+UpdateLaunchFn get_update_launcher(int sun, int prec, int mu);
+
+struct MeasureArgs {
+    const void* table; const void* params; Geom geom; int tbc;
+    double2* out_action; double2* out_plq;      // either may be null
+    uint32_t first_site, nsites; uint32_t block;
+};
+cudaError_t launch_measure(int sun, int prec, const MeasureArgs&, cudaStream_t);   // dispatch.cu
+
+struct PolyakovArgs {
+    const void* table; const void* params; Geom geom; int tbc;
+    double2* out; uint32_t offset; int pl_level; uint32_t x_first, x_count; uint32_t block;
+};
+cudaError_t launch_polyakov(int sun, int prec, const PolyakovArgs&, cudaStream_t);
+cudaError_t launch_reduce_double2(const double2* table, uint32_t off, uint32_t size, double2* dst, uint32_t index, cudaStream_t);
+cudaError_t launch_clear_double2(double2* p, uint32_t n, cudaStream_t);
+
+cudaError_t launch_init_cold(int sun, int prec, void* table, const Geom&, cudaStream_t);
+cudaError_t launch_init_gid(int sun, int prec, void* table, const Geom&, cudaStream_t);
+cudaError_t launch_init_hot(int sun, int prec, void* table, const Geom&, const void* prns, int dir, cudaStream_t);
+cudaError_t launch_gramschmidt(int sun, int prec, void* table, const Geom&, cudaStream_t);
+
+cudaError_t launch_ranlux_init(const uint32_t* seeds, uint32_t* table, uint32_t instances, cudaStream_t);
+cudaError_t launch_prn_produce(int prn_kind, uint32_t* table, void* prns, uint32_t instances, uint32_t samples, cudaStream_t);
+
+// halo exchange building block (BigLattice): copy nplanes vec4 planes of one x-slice between plane-strided arrays
+cudaError_t launch_copy_planes(int prec, void* dst, size_t dst_row, uint32_t xd, int dp0, int dps,
+                               const void* src, size_t src_row, uint32_t xs, int sp0, int sps,
+                               uint32_t n234, int nplanes, cudaStream_t);
+
+int update_kernel_regs(int sun, int prec, int mu, int tbc, int prn_kind);   // registers/thread (cudaFuncGetAttributes)
+
+}  // namespace qcd

@@ -1,0 +1,60 @@
+// misc_inst.cu -- precision-independent kernels: PRN producers and double2 reducers.
+#include "launch.h"
+#include "measure.cuh"
+#include "init_prng.cuh"
+
+namespace qcd {
+
+cudaError_t launch_reduce_double2(const double2* table, uint32_t off, uint32_t size, double2* dst, uint32_t index, cudaStream_t st) {
+    reduce_double2_kernel<<<1, 256, 0, st>>>(table, off, size, dst, index);
+    return cudaGetLastError();
+}
+cudaError_t launch_clear_double2(double2* p, uint32_t n, cudaStream_t st) {
+    if (n == 0) return cudaSuccess;
+    clear_double2_kernel<<<(n + 255) / 256, 256, 0, st>>>(p, n);
+    return cudaGetLastError();
+}
+cudaError_t launch_ranlux_init(const uint32_t* seeds, uint32_t* table, uint32_t instances, cudaStream_t st) {
+    ranlux_init_kernel<<<(instances + 127) / 128, 128, 0, st>>>(seeds, table, instances);
+    return cudaGetLastError();
+}
+cudaError_t launch_prn_produce(int kind, uint32_t* table, void* prns, uint32_t instances, uint32_t samples, cudaStream_t st) {
+    dim3 grid((instances + 127) / 128), block(128);
+    float4* out = static_cast<float4*>(prns);
+    switch (kind) {
+        case PRN_RANLUX0: ranlux_produce_kernel<24><<<grid, block, 0, st>>>(table, out, instances, samples); break;
+        case PRN_RANLUX1: ranlux_produce_kernel<48><<<grid, block, 0, st>>>(table, out, instances, samples); break;
+        case PRN_RANLUX2: ranlux_produce_kernel<97><<<grid, block, 0, st>>>(table, out, instances, samples); break;
+        case PRN_RANLUX3: ranlux_produce_kernel<223><<<grid, block, 0, st>>>(table, out, instances, samples); break;
+        case PRN_RANLUX4: ranlux_produce_kernel<389><<<grid, block, 0, st>>>(table, out, instances, samples); break;
+        case PRN_XOR128:  small_produce_kernel<PrnXor128><<<grid, block, 0, st>>>(table, out, instances, samples); break;
+        case PRN_PM:      small_produce_kernel<PrnPM><<<grid, block, 0, st>>>(table, out, instances, samples); break;
+        case PRN_MRG32K3A: small_produce_kernel<PrnMrg><<<grid, block, 0, st>>>(table, out, instances, samples); break;
+        default: return cudaErrorInvalidValue;
+    }
+    return cudaGetLastError();
+}
+
+// Halo exchange building block: copy `nplanes` vec4 planes of one x-slice (n234 elements each)
+// between two plane-strided arrays.  Plane k lives at (p0 + k*ps)*row_elems + x*n234.
+// Used table->table (peer pointers over NVLink), table->packed and packed->table.
+template <typename R>
+__global__ void copy_planes_kernel(R* __restrict__ dst, size_t dst_row, uint32_t xd, int dp0, int dps,
+                                   const R* __restrict__ src, size_t src_row, uint32_t xs, int sp0, int sps, uint32_t n234) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n234) return;
+    int k = blockIdx.y;
+    const R* s = src + 4 * (size_t(xs) * n234 + i + size_t(sp0 + k * sps) * src_row);
+    R* d = dst + 4 * (size_t(xd) * n234 + i + size_t(dp0 + k * dps) * dst_row);
+    stv4(d, ldv4(s));
+}
+cudaError_t launch_copy_planes(int prec, void* dst, size_t dst_row, uint32_t xd, int dp0, int dps,
+                               const void* src, size_t src_row, uint32_t xs, int sp0, int sps,
+                               uint32_t n234, int nplanes, cudaStream_t st) {
+    dim3 grid((n234 + 127) / 128, nplanes), block(128);
+    if (prec == 1) copy_planes_kernel<double><<<grid, block, 0, st>>>((double*)dst, dst_row, xd, dp0, dps, (const double*)src, src_row, xs, sp0, sps, n234);
+    else           copy_planes_kernel<float><<<grid, block, 0, st>>>((float*)dst, dst_row, xd, dp0, dps, (const float*)src, src_row, xs, sp0, sps, n234);
+    return cudaGetLastError();
+}
+
+}  // namespace qcd

@@ -1,0 +1,459 @@
+// update.cuh -- one (parity, direction) pass of the Cabibbo-Marinari pseudo-heat-bath
+// with Kennedy-Pendleton SU(2) subgroup sampling, plus overrelaxation, for sm_100a.
+//
+// Replaces the reference kernels update_{even,odd}_{X,Y,Z,T} (SU(N)/suncl/suncl.cl:398-977)
+// and everything they inline: lattice_staple_{2,3} (su2_update_cl.cl:206-431,
+// su3_update_cl.cl:341-565), lattice_heatbath2/3 (su3_update_cl.cl:568-779,
+// su2_update_cl.cl:434-550), lattice_GramSchmidt3 (su3_update_cl.cl:228-291).
+//
+// Same inputs -> same links within fp tolerance; PRN consumption order is identical
+// (one vec4 per KP trial, one for the direction, SU(3) burns one slot on NHIT
+// rejections, SU(2) keeps the old link instead).  What is different from the reference:
+//   * staples are built from the two stored rows (third rows only where a product needs
+//     them: 2x(2-row x full) products + cross products instead of 2 full 3x3 products);
+//   * W = U*S is formed once and updated together with U by each SU(2) subgroup rotation
+//     (the reference recomputes the full 3x3 product three times);
+//   * the PRN source is a template parameter: the reference-layout buffer, the closed-form
+//     INTS=2 pseudo-randoms, or a generator whose state lives in registers (fused mode).
+#pragma once
+#include "lattice.cuh"
+#include "prng.cuh"
+
+namespace qcd {
+
+// ---------------------------------------------------------------- PRN sources
+// Reference-layout buffer: thread GID reads prns[GID + k*PRNGSTEP]  (su3_update_cl.cl:613-617, 679)
+struct PrnBuffered {
+    struct Args { const float4* prns; };
+    const float4* p; uint32_t ind, step;
+    __device__ __forceinline__ PrnBuffered(const Args& a, const Geom& g, uint32_t GID, uint32_t) : p(a.prns), ind(GID), step(g.prngstep) {}
+    __device__ __forceinline__ F4 trial() { float4 r = __ldg(p + ind); ind += step; return { r.x, r.y, r.z, r.w }; }
+    __device__ __forceinline__ F4 direction() { return trial(); }
+    __device__ __forceinline__ void burn() { ind += step; }
+    __device__ __forceinline__ void finish() {}
+    static constexpr bool kGid = false;
+};
+// INTS=2 / -D GID_UPD closed-form pseudo-randoms (su3_update_cl.cl:598-637); every trial is accepted
+struct PrnGid {
+    struct Args { int dummy; };
+    double gid, sites, a;
+    __device__ __forceinline__ PrnGid(const Args&, const Geom& g, uint32_t, uint32_t gindex) {
+        // suncl.cl:424-430: prns[GID].x = (float) gindex  (BIGLAT: global index)
+        uint32_t gi = g.biglat ? (gindex - g.n234 + g.left_sites) : gindex;
+        gid = double(float(gi));
+        sites = g.biglat ? double(g.full_sites) : double(g.sites);
+        a = 0.005 * double(1 + int(g.nhit));
+    }
+    __device__ __forceinline__ F4 trial() {   // values returned as float are only used by the fp32 path
+        return { 0.f, 0.f, 0.f, 0.f };
+    }
+    __device__ __forceinline__ void trial_d(double r[4]) {
+        r[0] = fabs(sin((a + 270.0 / sites) * gid)); r[1] = fabs(cos((a + 60.0 / sites) * gid));
+        r[2] = fabs(sin((a - 150.0 / sites) * gid)); r[3] = fabs(cos((a - 380.0 / sites) * gid));
+    }
+    __device__ __forceinline__ void direction_d(double r[4]) {
+        r[0] = fabs(cos((0.08 - 270.0 / sites) * gid)); r[1] = fabs(sin((0.08 - 60.0 / sites) * gid));
+        r[2] = fabs(cos((0.08 + 150.0 / sites) * gid)); r[3] = fabs(sin((0.08 + 380.0 / sites) * gid));
+    }
+    __device__ __forceinline__ F4 direction() { return { 0.f, 0.f, 0.f, 0.f }; }
+    __device__ __forceinline__ void burn() {}
+    __device__ __forceinline__ void finish() {}
+    static constexpr bool kGid = true;
+};
+// Fused generators: instance GID lives in the registers of update thread GID.  Bit-exact with the
+// buffered path when the run is configured with PRNG_instances == PRNGSTEP (hard part 1):
+// every pass advances every instance by exactly `samples` vec4, consumed or not.
+template <int NSKIP>
+struct PrnRanlux {
+    struct Args { uint32_t* table; uint32_t instances; uint32_t samples; };
+    Ranlux r; uint32_t used; uint32_t* table; uint32_t instances, samples, id;
+    __device__ __forceinline__ PrnRanlux(const Args& a, const Geom&, uint32_t GID, uint32_t)
+        : used(0), table(a.table), instances(a.instances), samples(a.samples), id(GID) { ranlux_load(r, table, instances, id); }
+    __device__ __forceinline__ F4 trial() { used++; return r.template next4<NSKIP>(); }
+    __device__ __forceinline__ F4 direction() { used++; return r.template next4<NSKIP>(); }
+    __device__ __forceinline__ void burn() { used++; r.template skip4<NSKIP>(); }
+    __device__ __forceinline__ void finish() { r.template skip_samples<NSKIP>(samples - used); ranlux_store(r, table, instances, id); }
+    static constexpr bool kGid = false;
+};
+template <class Gen, int WORDS>
+struct PrnSmallState {   // XOR128 (4 words), PM (4 words), MRG32k3a (2 x uint4 rows)
+    struct Args { uint32_t* table; uint32_t instances; uint32_t samples; };
+    Gen gen; uint32_t used; uint32_t* table; uint32_t instances, samples, id;
+    __device__ __forceinline__ PrnSmallState(const Args& a, const Geom&, uint32_t GID, uint32_t)
+        : used(0), table(a.table), instances(a.instances), samples(a.samples), id(GID) { load(); }
+    __device__ __forceinline__ void load();
+    __device__ __forceinline__ void store();
+    __device__ __forceinline__ F4 trial() { used++; return gen.next4(); }
+    __device__ __forceinline__ F4 direction() { used++; return gen.next4(); }
+    __device__ __forceinline__ void burn() { used++; gen.skip4(); }
+    __device__ __forceinline__ void finish() {
+#pragma unroll 1
+        for (uint32_t k = used; k < samples; k++) gen.skip4();
+        store();
+    }
+    static constexpr bool kGid = false;
+};
+template <> __device__ __forceinline__ void PrnSmallState<Xor128, 4>::load() {
+    uint4 s = reinterpret_cast<const uint4*>(table)[id]; gen.x = s.x; gen.y = s.y; gen.z = s.z; gen.w = s.w;
+}
+template <> __device__ __forceinline__ void PrnSmallState<Xor128, 4>::store() {
+    reinterpret_cast<uint4*>(table)[id] = make_uint4(gen.x, gen.y, gen.z, gen.w);
+}
+template <> __device__ __forceinline__ void PrnSmallState<ParkMiller, 4>::load() {
+    uint4 s = reinterpret_cast<const uint4*>(table)[id]; gen.s[0] = s.x; gen.s[1] = s.y; gen.s[2] = s.z; gen.s[3] = s.w;
+}
+template <> __device__ __forceinline__ void PrnSmallState<ParkMiller, 4>::store() {
+    reinterpret_cast<uint4*>(table)[id] = make_uint4(gen.s[0], gen.s[1], gen.s[2], gen.s[3]);
+}
+template <> __device__ __forceinline__ void PrnSmallState<Mrg32k3a, 8>::load() {
+    uint4 s1 = reinterpret_cast<const uint4*>(table)[id];
+    uint4 s2 = reinterpret_cast<const uint4*>(table)[size_t(instances) + id];
+    gen.a[0] = s1.x; gen.a[1] = s1.y; gen.a[2] = s1.z; gen.b[0] = s2.x; gen.b[1] = s2.y; gen.b[2] = s2.z;
+}
+template <> __device__ __forceinline__ void PrnSmallState<Mrg32k3a, 8>::store() {
+    uint4* t = reinterpret_cast<uint4*>(table);
+    uint4 s1 = t[id], s2 = t[size_t(instances) + id];
+    s1.x = gen.a[0]; s1.y = gen.a[1]; s1.z = gen.a[2]; s2.x = gen.b[0]; s2.y = gen.b[1]; s2.z = gen.b[2];
+    t[id] = s1; t[size_t(instances) + id] = s2;
+}
+using PrnXor128 = PrnSmallState<Xor128, 4>;
+using PrnPM = PrnSmallState<ParkMiller, 4>;
+using PrnMrg = PrnSmallState<Mrg32k3a, 8>;
+
+// ---------------------------------------------------------------- math helpers
+template <typename R> struct Mth;
+template <> struct Mth<double> {
+    static __device__ __forceinline__ double sqrt_(double x) { return sqrt(x); }
+    static __device__ __forceinline__ double log_(double x) { return log(x); }
+    static __device__ __forceinline__ double cos2pi(double x) { return cospi(2.0 * x); }
+    static __device__ __forceinline__ void sincos2pi(double x, double* s, double* c) { sincospi(2.0 * x, s, c); }
+};
+template <> struct Mth<float> {
+    static __device__ __forceinline__ float sqrt_(float x) { return sqrtf(x); }
+    static __device__ __forceinline__ float log_(float x) { return logf(x); }
+    static __device__ __forceinline__ float cos2pi(float x) { return cospif(2.0f * x); }
+    static __device__ __forceinline__ void sincos2pi(float x, float* s, float* c) { sincospif(2.0f * x, s, c); }
+};
+
+// Kennedy-Pendleton sampling of the new SU(2) element (reference: lattice_heatbath2).
+// aH = (r/sqrt(det r))^+ as a 4-vector, bdet = beta*sqrt(det).  Returns false after NHIT rejections.
+template <typename R, class Prn>
+__device__ __forceinline__ bool kp_heatbath(Prn& prn, const Geom& g, const V4<R>& aH, R bdet, V4<R>& out) {
+    bool flag = false;
+    R delta = R(0);
+    R ibdet = R(1) / bdet;
+    uint32_t i = 0;
+    R rx, ry;
+    if constexpr (Prn::kGid) {
+        double r[4];
+        prn.trial_d(r);
+        R c = Mth<R>::cos2pi(R(r[1]));
+        delta = c * c * ibdet;
+        flag = true;
+        prn.direction_d(r);
+        rx = R(r[0]); ry = R(r[1]);
+    } else {
+        while (i < g.nhit && !flag) {
+            F4 r = prn.trial();
+            R c = Mth<R>::cos2pi(R(r.y));
+            delta = -(Mth<R>::log_(R(1) - R(r.x)) + c * c * Mth<R>::log_(R(1) - R(r.z))) * ibdet;
+            if (R(r.w) * R(r.w) <= R(1) - R(0.5) * delta) flag = true;
+            i++;
+        }
+        if (!flag) return false;
+        F4 r = prn.direction();
+        rx = R(r.x); ry = R(r.y);
+    }
+    R cosal = R(1) - delta;
+    R costh = R(2) * rx - R(1);
+    R sinth = Mth<R>::sqrt_(R(1) - costh * costh);
+    R sinal = Mth<R>::sqrt_(R(1) - cosal * cosal);
+    R sinphi, cosphi;
+    Mth<R>::sincos2pi(ry, &sinphi, &cosphi);
+    V4<R> c;
+    c.x = cosal;
+    c.z = sinal * costh;
+    c.y = sinal * sinth * sinphi;
+    c.w = sinal * sinth * cosphi;
+    out = su2_mul(c, aH);
+    return true;
+}
+
+// ---------------------------------------------------------------- SU(3) products on 2-row operands
+// D(rows 0,1) = C(rows 0,1) * B(full)
+template <typename R> __device__ __forceinline__ void mul_r2_full(const M3r2<R>& C, const M3<R>& B, M3<R>& D) {
+#pragma unroll
+    for (int i = 0; i < 2; i++)
+#pragma unroll
+        for (int j = 0; j < 3; j++) {
+            Cx<R> acc = cmul(C.e[i][0], B.e[0][j]);
+            cfma(acc, C.e[i][1], B.e[1][j]);
+            cfma(acc, C.e[i][2], B.e[2][j]);
+            D.e[i][j] = acc;
+        }
+    third_row(D.e[0], D.e[1], D.e[2]);
+}
+// F(rows 0,1) = A(rows 0,1) * D^+ ;  third row by cross product
+template <typename R> __device__ __forceinline__ void mul_r2_dag(const M3r2<R>& A, const M3<R>& D, M3<R>& F) {
+#pragma unroll
+    for (int i = 0; i < 2; i++)
+#pragma unroll
+        for (int j = 0; j < 3; j++) {
+            Cx<R> acc = cmulc(A.e[i][0], D.e[j][0]);
+            cfmac(acc, A.e[i][1], D.e[j][1]);
+            cfmac(acc, A.e[i][2], D.e[j][2]);
+            F.e[i][j] = acc;
+        }
+    third_row(F.e[0], F.e[1], F.e[2]);
+}
+// G(rows 0,1) = E^+ * C ; third row by cross product
+template <typename R> __device__ __forceinline__ void mul_dag_full(const M3<R>& E, const M3<R>& C, M3<R>& G) {
+#pragma unroll
+    for (int i = 0; i < 2; i++)
+#pragma unroll
+        for (int j = 0; j < 3; j++) {
+            Cx<R> acc = { E.e[0][i].re * C.e[0][j].re + E.e[0][i].im * C.e[0][j].im,
+                          E.e[0][i].re * C.e[0][j].im - E.e[0][i].im * C.e[0][j].re };
+            cfmacc(acc, E.e[1][i], C.e[1][j]);
+            cfmacc(acc, E.e[2][i], C.e[2][j]);
+            G.e[i][j] = acc;
+        }
+    third_row(G.e[0], G.e[1], G.e[2]);
+}
+template <typename R> __device__ __forceinline__ void acc3(M3<R>& S, const M3<R>& F) {
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+#pragma unroll
+        for (int j = 0; j < 3; j++) { S.e[i][j].re += F.e[i][j].re; S.e[i][j].im += F.e[i][j].im; }
+}
+
+// staple contribution of the (MU,NU) plane at site p: forward + backward
+template <typename R, int MU, int NU, bool TBC>
+__device__ __forceinline__ void staple3_plane(const R* table, const Geom& g, const Coord& p, uint32_t gindex,
+                                              const Coord& pmu, const Twist<R>& tw, M3<R>& S, bool first) {
+    Coord pnu = nb_plus<NU>(g, p);
+    Coord pmn = nb_minus<NU>(g, p);
+    Coord pmnmu = nb_plus<MU>(g, pmn);
+    uint32_t g_pmu = coords_to_gid(g, pmu), g_pnu = coords_to_gid(g, pnu);
+    uint32_t g_pmn = coords_to_gid(g, pmn), g_pmnmu = coords_to_gid(g, pmnmu);
+    // issue all six link loads of the plane before the arithmetic
+    M3r2<R> A  = load3<R, NU, TBC>(table, g, g_pmu, pmu.x, tw);      // U_nu(p+mu)
+    M3r2<R> B  = load3<R, MU, TBC>(table, g, g_pnu, pnu.x, tw);      // U_mu(p+nu)
+    M3r2<R> C  = load3<R, NU, TBC>(table, g, gindex, p.x, tw);       // U_nu(p)
+    M3r2<R> A2 = load3<R, NU, TBC>(table, g, g_pmnmu, pmnmu.x, tw);  // U_nu(p-nu+mu)
+    M3r2<R> B2 = load3<R, MU, TBC>(table, g, g_pmn, pmn.x, tw);      // U_mu(p-nu)
+    M3r2<R> C2 = load3<R, NU, TBC>(table, g, g_pmn, pmn.x, tw);      // U_nu(p-nu)
+    {   // forward: A B^+ C^+ = A (C B)^+
+        M3<R> Bf = complete(B), D, F;
+        mul_r2_full(C, Bf, D);
+        mul_r2_dag(A, D, F);
+        if (first) S = F; else acc3(S, F);
+    }
+    {   // backward: A2^+ B2^+ C2 = (B2 A2)^+ C2
+        M3<R> Af = complete(A2), Cf = complete(C2), E, G;
+        mul_r2_full(B2, Af, E);
+        mul_dag_full(E, Cf, G);
+        acc3(S, G);
+    }
+}
+template <typename R, int MU, bool TBC>
+__device__ __forceinline__ M3<R> staple3(const R* table, const Geom& g, const Coord& p, uint32_t gindex, const Twist<R>& tw) {
+    M3<R> S;
+    Coord pmu = nb_plus<MU>(g, p);
+    // plane order of the reference: X:{Y,Z,T} Y:{X,Z,T} Z:{Y,X,T} T:{Y,Z,X}  (su3_update_cl.cl:367-559)
+    constexpr int n0 = (MU == 1) ? 0 : 1;
+    constexpr int n1 = (MU == 0 || MU == 1 || MU == 3) ? 2 : 0;
+    constexpr int n2 = (MU == 3) ? 0 : 3;
+    staple3_plane<R, MU, n0, TBC>(table, g, p, gindex, pmu, tw, S, true);
+    staple3_plane<R, MU, n1, TBC>(table, g, p, gindex, pmu, tw, S, false);
+    staple3_plane<R, MU, n2, TBC>(table, g, p, gindex, pmu, tw, S, false);
+    return S;
+}
+
+// left-multiply rows (a,b) of M by the SU(2) element d (4-vector): rows' = [[u1,u2],[-conj u2, conj u1]] rows
+template <typename R, int A, int B>
+__device__ __forceinline__ void rotate_rows(M3<R>& M, const V4<R>& d) {
+    const Cx<R> u1 = { d.x, d.z }, u2 = { d.y, d.w };
+#pragma unroll
+    for (int j = 0; j < 3; j++) {
+        Cx<R> ra = M.e[A][j], rb = M.e[B][j];
+        Cx<R> na = cmul(u1, ra); cfma(na, u2, rb);
+        // v1 = -conj(u2), v2 = conj(u1)
+        Cx<R> nb = { -(u2.re * ra.re + u2.im * ra.im), -(u2.re * ra.im - u2.im * ra.re) };
+        cfmacc(nb, u1, rb);
+        M.e[A][j] = na; M.e[B][j] = nb;
+    }
+}
+// aH (normalised dagger of the 2x2 block (a,b) of W) and its norm
+template <typename R, int A, int B>
+__device__ __forceinline__ V4<R> block_dagger(const M3<R>& W, R& det) {
+    V4<R> aH;
+    aH.x =  (W.e[A][A].re + W.e[B][B].re);
+    aH.z = -(W.e[A][A].im - W.e[B][B].im);
+    aH.y = -(W.e[A][B].re - W.e[B][A].re);
+    aH.w = -(W.e[A][B].im + W.e[B][A].im);
+    det = Mth<R>::sqrt_(aH.x * aH.x + aH.y * aH.y + aH.z * aH.z + aH.w * aH.w);
+    R id = R(1) / det;
+    aH.x *= id; aH.y *= id; aH.z *= id; aH.w *= id;
+    return aH;
+}
+template <typename R, int A, int B, class Prn>
+__device__ __forceinline__ void cm_subgroup(M3<R>& U, M3<R>& W, const Geom& g, R beta, Prn& prn) {
+    R det;
+    V4<R> aH = block_dagger<R, A, B>(W, det);
+    V4<R> d;
+    if (kp_heatbath<R, Prn>(prn, g, aH, beta * det, d)) {
+        rotate_rows<R, A, B>(U, d);
+        rotate_rows<R, A, B>(W, d);
+    } else {
+        prn.burn();    // su3_update_cl.cl:665-668
+    }
+}
+template <typename R, int A, int B>
+__device__ __forceinline__ void or_subgroup(M3<R>& U, M3<R>& W) {
+    R det;
+    V4<R> aH = block_dagger<R, A, B>(W, det);
+    V4<R> d = su2_mul(aH, aH);
+    rotate_rows<R, A, B>(U, d);
+    rotate_rows<R, A, B>(W, d);
+}
+// ---------------------------------------------------------------- SU(2) staple (4-vector algebra)
+template <typename R, int MU, int NU, bool TBC>
+__device__ __forceinline__ void staple2_plane(const R* table, const Geom& g, const Coord& p, uint32_t gindex,
+                                              const Coord& pmu, const Twist<R>& tw, V4<R>& S, bool first) {
+    Coord pnu = nb_plus<NU>(g, p);
+    Coord pmn = nb_minus<NU>(g, p);
+    Coord pmnmu = nb_plus<MU>(g, pmn);
+    uint32_t g_pmn = coords_to_gid(g, pmn);
+    V4<R> A  = load2<R, NU, TBC>(table, g, coords_to_gid(g, pmu), pmu.x, tw);
+    V4<R> B  = load2<R, MU, TBC>(table, g, coords_to_gid(g, pnu), pnu.x, tw);
+    V4<R> C  = load2<R, NU, TBC>(table, g, gindex, p.x, tw);
+    V4<R> A2 = load2<R, NU, TBC>(table, g, coords_to_gid(g, pmnmu), pmnmu.x, tw);
+    V4<R> B2 = load2<R, MU, TBC>(table, g, g_pmn, pmn.x, tw);
+    V4<R> C2 = load2<R, NU, TBC>(table, g, g_pmn, pmn.x, tw);
+    V4<R> f = su2_mul(su2_mul(A, su2_dag(B)), su2_dag(C));
+    V4<R> b = su2_mul(su2_mul(su2_dag(A2), su2_dag(B2)), C2);
+    if (first) { S = f; } else { S.x += f.x; S.y += f.y; S.z += f.z; S.w += f.w; }
+    S.x += b.x; S.y += b.y; S.z += b.z; S.w += b.w;
+}
+template <typename R, int MU, bool TBC>
+__device__ __forceinline__ V4<R> staple2(const R* table, const Geom& g, const Coord& p, uint32_t gindex, const Twist<R>& tw) {
+    V4<R> S;
+    Coord pmu = nb_plus<MU>(g, p);
+    constexpr int n0 = (MU == 1) ? 0 : 1;
+    constexpr int n1 = (MU == 0 || MU == 1 || MU == 3) ? 2 : 0;
+    constexpr int n2 = (MU == 3) ? 0 : 3;
+    staple2_plane<R, MU, n0, TBC>(table, g, p, gindex, pmu, tw, S, true);
+    staple2_plane<R, MU, n1, TBC>(table, g, p, gindex, pmu, tw, S, false);
+    staple2_plane<R, MU, n2, TBC>(table, g, p, gindex, pmu, tw, S, false);
+    return S;
+}
+
+// ---------------------------------------------------------------- site updates
+template <typename R, int MU, bool TBC, class Prn>
+__device__ __forceinline__ void update_site_su3(R* table, const Geom& g, R beta, const Twist<R>& tw, uint32_t gindex, Prn& prn) {
+    Coord p = gid_to_coords(g, gindex);
+    M3r2<R> m0 = load3<R, MU, TBC>(table, g, gindex, p.x, tw);
+    M3<R> S = staple3<R, MU, TBC>(table, g, p, gindex, tw);
+    M3<R> U;
+#pragma unroll
+    for (int j = 0; j < 3; j++) { U.e[0][j] = m0.e[0][j]; U.e[1][j] = m0.e[1][j]; }
+#pragma unroll 1
+    for (uint32_t h = 0; h < g.nhitpar; h++) {
+        third_row(U.e[0], U.e[1], U.e[2]);
+        M3<R> W = mul_full(U, S);
+        cm_subgroup<R, 0, 1, Prn>(U, W, g, beta, prn);
+        cm_subgroup<R, 0, 2, Prn>(U, W, g, beta, prn);
+        cm_subgroup<R, 1, 2, Prn>(U, W, g, beta, prn);
+        gram_schmidt3(U.e[0], U.e[1]);
+    }
+    store3<R, MU>(table, g, gindex, U.e[0], U.e[1]);
+}
+template <typename R, int MU, bool TBC, class Prn>
+__device__ __forceinline__ void update_site_su2(R* table, const Geom& g, R beta, const Twist<R>& tw, uint32_t gindex, Prn& prn) {
+    Coord p = gid_to_coords(g, gindex);
+    V4<R> S = staple2<R, MU, TBC>(table, g, p, gindex, tw);
+    // su2_update_cl.cl:448-461: aH = S^+/|S|, det = 2|S|
+    R n = Mth<R>::sqrt_(S.x * S.x + S.y * S.y + S.z * S.z + S.w * S.w);
+    R in = R(1) / n;
+    V4<R> aH = { S.x * in, -S.y * in, -S.z * in, -S.w * in };
+    V4<R> d;
+    if (kp_heatbath<R, Prn>(prn, g, aH, beta * (R(2) * n), d))
+        st_plane(table, g, gindex, MU, d);
+    // on NHIT rejections the old (untwisted, stored) link stays -- su2_update_cl.cl:541-548.  With TBC the
+    // reference would store the twisted m0 back; that only differs on the x = N1-1 Y-links.
+    else if (TBC && MU == 1) {
+        V4<R> m0 = load2<R, MU, TBC>(table, g, gindex, p.x, tw);
+        st_plane(table, g, gindex, MU, m0);
+    }
+}
+template <typename R, int MU>
+__device__ __forceinline__ void overrelax_site_su3(R* table, const Geom& g, uint32_t gindex) {
+    Twist<R> tw = { R(1), R(0), R(1), R(0) };
+    Coord p = gid_to_coords(g, gindex);
+    M3r2<R> m0 = load3<R, MU, false>(table, g, gindex, p.x, tw);
+    M3<R> S = staple3<R, MU, false>(table, g, p, gindex, tw);
+    M3<R> U = complete(m0);
+    M3<R> W = mul_full(U, S);
+    or_subgroup<R, 0, 1>(U, W);
+    or_subgroup<R, 0, 2>(U, W);
+    or_subgroup<R, 1, 2>(U, W);
+    gram_schmidt3(U.e[0], U.e[1]);
+    store3<R, MU>(table, g, gindex, U.e[0], U.e[1]);
+}
+template <typename R, int MU>
+__device__ __forceinline__ void overrelax_site_su2(R* table, const Geom& g, uint32_t gindex) {
+    Twist<R> tw = { R(1), R(0), R(1), R(0) };
+    Coord p = gid_to_coords(g, gindex);
+    V4<R> m0 = load2<R, MU, false>(table, g, gindex, p.x, tw);
+    V4<R> S = staple2<R, MU, false>(table, g, p, gindex, tw);
+    R in = R(1) / Mth<R>::sqrt_(S.x * S.x + S.y * S.y + S.z * S.z + S.w * S.w);
+    V4<R> aH = { S.x * in, -S.y * in, -S.z * in, -S.w * in };
+    V4<R> r = su2_mul(su2_mul(aH, su2_dag(m0)), aH);
+    st_plane(table, g, gindex, MU, r);
+}
+
+constexpr int kUpdateThreads = 128;
+
+// twist phases from lattice_parameters[1..2] (su3_matrix_memory.cl:64-66, su2_matrix_memory.cl:73-75)
+template <int SUN, typename R, bool TBC>
+__device__ __forceinline__ Twist<R> make_twist(const R* params) {
+    Twist<R> tw = { R(1), R(0), R(1), R(0) };
+    if (TBC) {
+        R phi = params[1], omega = (SUN == 3) ? params[2] : R(0);
+        if (SUN == 3) {
+            R a = (phi + omega) / 2, b = (omega - phi) / 2;
+            if (sizeof(R) == 8) { tw.c1 = cos(a); tw.s1 = sin(a); tw.c2 = cos(b); tw.s2 = sin(b); }
+            else { tw.c1 = cosf(a); tw.s1 = sinf(a); tw.c2 = cosf(b); tw.s2 = sinf(b); }
+        } else {
+            if (sizeof(R) == 8) { tw.c1 = cos(phi / 2); tw.s1 = sin(phi / 2); }
+            else { tw.c1 = cosf(phi / 2); tw.s1 = sinf(phi / 2); }
+        }
+    }
+    return tw;
+}
+
+template <int SUN, typename R, int MU, bool TBC, class Prn>
+__global__ void __launch_bounds__(kUpdateThreads)
+update_kernel(R* __restrict__ table, const R* __restrict__ params, const __grid_constant__ Geom g, int odd, typename Prn::Args pargs) {
+    uint32_t GID = blockIdx.x * blockDim.x + threadIdx.x;
+    if (GID >= g.nthreads) return;
+    const R beta = params[0];
+    const Twist<R> tw = make_twist<SUN, R, TBC>(params);
+    uint32_t gindex = parity_gid(g, GID, odd != 0);
+    Prn prn(pargs, g, GID, gindex);
+    if (SUN == 3) update_site_su3<R, MU, TBC, Prn>(table, g, beta, tw, gindex, prn);
+    else          update_site_su2<R, MU, TBC, Prn>(table, g, beta, tw, gindex, prn);
+    prn.finish();
+}
+template <int SUN, typename R, int MU>
+__global__ void __launch_bounds__(kUpdateThreads)
+overrelax_kernel(R* __restrict__ table, const __grid_constant__ Geom g, int odd) {
+    uint32_t GID = blockIdx.x * blockDim.x + threadIdx.x;
+    if (GID >= g.nthreads) return;
+    uint32_t gindex = parity_gid(g, GID, odd != 0);
+    if (SUN == 3) overrelax_site_su3<R, MU>(table, g, gindex);
+    else          overrelax_site_su2<R, MU>(table, g, gindex);
+}
+
+}  // namespace qcd

@@ -1,0 +1,71 @@
+// update_inst.cu -- instantiation unit for the update kernels.  Built once per
+// (INST_SUN, INST_PREC, INST_MU) by build.py so that the 16 units compile in parallel.
+#include "launch.h"
+#include "update.cuh"
+
+#ifndef INST_SUN
+#error "compile with -DINST_SUN=2|3 -DINST_PREC=0|1 -DINST_MU=0..3"
+#endif
+
+namespace qcd {
+
+#if INST_PREC == 1
+typedef double RealT;
+#else
+typedef float RealT;
+#endif
+
+template <bool TBC, class Prn>
+static cudaError_t launch_one(const UpdateArgs& a, typename Prn::Args pa, cudaStream_t st) {
+    dim3 block(kUpdateThreads), grid((a.geom.nthreads + kUpdateThreads - 1) / kUpdateThreads);
+    if (grid.x == 0) return cudaSuccess;
+    update_kernel<INST_SUN, RealT, INST_MU, TBC, Prn><<<grid, block, 0, st>>>(
+        static_cast<RealT*>(a.table), static_cast<const RealT*>(a.params), a.geom, a.odd, pa);
+    return cudaGetLastError();
+}
+template <bool TBC>
+static cudaError_t launch_tbc(const UpdateArgs& a, cudaStream_t st) {
+    switch (a.prn_kind) {
+        case PRN_BUFFERED: { PrnBuffered::Args pa = { static_cast<const float4*>(a.prns) }; return launch_one<TBC, PrnBuffered>(a, pa, st); }
+        case PRN_GID:      { PrnGid::Args pa = { 0 }; return launch_one<TBC, PrnGid>(a, pa, st); }
+        case PRN_RANLUX3:  { PrnRanlux<223>::Args pa = { a.prn_table, a.prn_instances, a.prn_samples }; return launch_one<TBC, PrnRanlux<223>>(a, pa, st); }
+        case PRN_XOR128:   { PrnXor128::Args pa = { a.prn_table, a.prn_instances, a.prn_samples }; return launch_one<TBC, PrnXor128>(a, pa, st); }
+        case PRN_PM:       { PrnPM::Args pa = { a.prn_table, a.prn_instances, a.prn_samples }; return launch_one<TBC, PrnPM>(a, pa, st); }
+        case PRN_MRG32K3A: { PrnMrg::Args pa = { a.prn_table, a.prn_instances, a.prn_samples }; return launch_one<TBC, PrnMrg>(a, pa, st); }
+        default: return cudaErrorInvalidValue;
+    }
+}
+
+#define CAT_(a, b, c, d) a##_##b##_##c##_##d
+#define CAT(a, b, c, d) CAT_(a, b, c, d)
+#define LAUNCH_NAME CAT(launch_update, INST_SUN, INST_PREC, INST_MU)
+#define REGS_NAME CAT(regs_update, INST_SUN, INST_PREC, INST_MU)
+
+cudaError_t LAUNCH_NAME(const UpdateArgs& a, cudaStream_t st) {
+    if (a.overrelax) {
+        dim3 block(kUpdateThreads), grid((a.geom.nthreads + kUpdateThreads - 1) / kUpdateThreads);
+        if (grid.x == 0) return cudaSuccess;
+        overrelax_kernel<INST_SUN, RealT, INST_MU><<<grid, block, 0, st>>>(static_cast<RealT*>(a.table), a.geom, a.odd);
+        return cudaGetLastError();
+    }
+    return a.tbc ? launch_tbc<true>(a, st) : launch_tbc<false>(a, st);
+}
+
+template <bool TBC, class Prn> static int regs_of() {
+    cudaFuncAttributes at;
+    if (cudaFuncGetAttributes(&at, update_kernel<INST_SUN, RealT, INST_MU, TBC, Prn>) != cudaSuccess) return -1;
+    return at.numRegs;
+}
+int REGS_NAME(int tbc, int prn_kind) {
+    switch (prn_kind) {
+        case PRN_BUFFERED: return tbc ? regs_of<true, PrnBuffered>() : regs_of<false, PrnBuffered>();
+        case PRN_GID:      return tbc ? regs_of<true, PrnGid>() : regs_of<false, PrnGid>();
+        case PRN_RANLUX3:  return tbc ? regs_of<true, PrnRanlux<223>>() : regs_of<false, PrnRanlux<223>>();
+        case PRN_XOR128:   return tbc ? regs_of<true, PrnXor128>() : regs_of<false, PrnXor128>();
+        case PRN_PM:       return tbc ? regs_of<true, PrnPM>() : regs_of<false, PrnPM>();
+        case PRN_MRG32K3A: return tbc ? regs_of<true, PrnMrg>() : regs_of<false, PrnMrg>();
+        default: return -1;
+    }
+}
+
+}  // namespace qcd

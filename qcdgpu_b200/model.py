@@ -1,0 +1,516 @@
+"""Host run loop: mirror of model_CL::model (SU(N)/suncl/suncl.{h,cpp}) for the gauge-update path.
+
+Same field names, same init.dat keys, same buffer sizes, same kernel wiring and the same call
+order as the reference's `lattice_init` / `lattice_simulate` / `lattice_analysis` /
+`lattice_write_results`, talking to the device only through the GPU_CL::GPU-shaped C ABI
+(capi.GPU).  The two knobs that are new are `fused_prng` (PRNG_instances = PRNGSTEP and the
+generator state kept in registers of the update kernel) and `or_steps` (overrelaxation passes
+after each heat-bath sweep; the reference has none).
+
+Not here (out of the hot path): Wilson loops, F_mu_nu / *_diff_* measurement
+variants, the .qcg state files, the start.txt/finish.txt handshake.
+"""
+from __future__ import annotations
+
+import math
+import os
+import time
+from dataclasses import dataclass, field
+
+import numpy as np
+
+from .capi import GPU, QcdGpuError
+from .prng import PRNG
+
+VERSION = "1.5"
+
+model_start_hot, model_start_cold, model_start_gid = 0, 1, 2
+model_precision_single, model_precision_double, model_precision_mixed = 0, 1, 2   # suncl.h:73
+
+X, Y, Z, T = 0, 1, 2, 3
+DIRS = "XYZT"
+
+
+def get_init_file(path: str) -> list[tuple[str, int, float, str]]:
+    """GPU::get_init_file (clinterface.cpp:2060-2154): `KEY = value  # comment` lines."""
+    out = []
+    with open(path) as f:
+        for line in f:
+            line = line.split("#", 1)[0].strip()
+            if "=" not in line:
+                continue
+            key, val = line.split("=", 1)
+            key, val = key.strip(), val.strip()
+            try:
+                ival = int(float(val)) if val and val[0] != "{" else 0
+            except ValueError:
+                ival = 0
+            try:
+                fval = float(val)
+            except ValueError:
+                fval = 0.0
+            out.append((key, ival, fval, val))
+    return out
+
+
+class Model:
+    """model_CL::model for one device (the non-BIGLAT build)."""
+
+    def __init__(self):
+        self.GPU0 = GPU()
+        self.PRNG0 = PRNG()
+        # QCDGPU.cpp:61-220 defaults
+        self.GPU0.GPU_limit_max_workgroup_size = 64
+        self.desired_platform = 0
+        self.desired_device = 0
+        self.PRNG0.PRNG_generator = "RANLUX3"
+        self.PRNG0.PRNG_randseries = 54
+        self.lattice_nd = 4
+        self.lattice_group = 3
+        self.lattice_full_size = [32, 32, 32, 32]
+        self.precision = model_precision_double
+        self.INIT = 1
+        self.NAV = 0
+        self.ITER = 2
+        self.NITER = 1
+        self.NHIT = 10
+        self.NHITPar = 1
+        self.BETA = 6.5
+        self.PHI = 0.0
+        self.OMEGA = 0.0
+        self.ints = model_start_cold
+        self.PL_level = 2           # the reference default 3 adds the *_diff_* kernels (out of scope)
+        self.turnoff_updates = False
+        self.turnoff_prns = False
+        self.turnoff_gramschmidt = False
+        self.get_actions_avr = True
+        self.get_plaquettes_avr = True
+        self.path = "./"
+        self.fprefix = "su3-"
+        # extensions
+        self.fused_prng = False
+        self.async_run = True
+        self.or_steps = 0
+        # counters
+        self.NAV_counter = 0
+        self.ITER_counter = 0
+        self.Analysis: dict[str, dict] = {}
+        self.header = ""
+        self.elapsed = 0.0
+
+    # ------------------------------------------------------------------ init.dat (suncl.cpp:289-464)
+    def lattice_get_init_file(self, path: str):
+        for key, ival, fval, text in get_init_file(path):
+            if key == "PLATFORM": self.desired_platform = ival
+            elif key == "DEVICE": self.desired_device = ival
+            elif key == "GROUP":
+                self.lattice_group = ival
+                self.fprefix = f"su{ival}-"
+            elif key == "ND": self.lattice_nd = ival
+            elif key in ("L1", "L2", "L3", "L4"): self.lattice_full_size[int(key[1]) - 1] = ival
+            elif key == "LS": self.lattice_full_size[0:3] = [ival, ival, ival]
+            elif key == "LT": self.lattice_full_size[self.lattice_nd - 1] = ival
+            elif key == "ITER": self.ITER = ival
+            elif key == "NITER": self.NITER = ival
+            elif key == "NHIT": self.NHIT = ival
+            elif key == "BETA": self.BETA = fval
+            elif key == "PHI": self.PHI = fval
+            elif key == "OMEGA": self.OMEGA = fval
+            elif key == "NAV": self.NAV = ival
+            elif key == "INTS": self.ints = ival if ival in (0, 1, 2) else model_start_cold
+            elif key == "OUTPUTPATH": self.path = text
+            elif key == "GETRETRACE": self.get_plaquettes_avr = True
+            elif key == "PL_LEVEL": self.PL_level = ival
+            # extensions (not reference keys): PRECISION 0/1/2, NHITPAR, FUSEDPRNG, ORSTEPS
+            elif key == "PRECISION": self.precision = ival
+            elif key == "NHITPAR": self.NHITPar = ival
+            elif key == "FUSEDPRNG": self.fused_prng = bool(ival)
+            elif key == "ORSTEPS": self.or_steps = ival
+            self.PRNG0.parameters_setup(key, ival, text)
+
+    # ------------------------------------------------------------------ lattice_init (suncl.cpp:672-706)
+    def lattice_init(self):
+        g = self.GPU0
+        g.device_select(self.desired_platform, self.desired_device)
+        g.device_initialize()
+        g.set_async(self.async_run)
+        g.set_fused_prng(self.fused_prng)
+        self.model_lattice_init()
+
+    # model_lattice_init (suncl.cpp:2212-2384)
+    def model_lattice_init(self):
+        g = self.GPU0
+        if self.lattice_group not in (2, 3):
+            raise QcdGpuError("GROUP must be 2 or 3")
+        if self.PL_level > 2:
+            raise QcdGpuError("PL_LEVEL 3 (Polyakov-loop *_diff_* kernels) is outside the implemented hot path")
+        n = self.lattice_full_size
+        self.lattice_domain_size = list(n)
+        self.lattice_domain_n1 = n[0]
+        self.lattice_domain_n2n3 = n[1] * n[2]
+        self.lattice_domain_exact_n1n2n3 = n[0] * n[1] * n[2]
+        self.lattice_domain_n2n3n4 = n[1] * n[2] * n[3]
+        self.lattice_domain_site = n[0] * n[1] * n[2] * n[3]
+        self.lattice_domain_exact_site = self.lattice_domain_site
+        self.lattice_full_site = self.lattice_domain_site
+        self.lattice_full_n1n2n3 = n[0] * n[1] * n[2]
+        self.lattice_domain_link = self.lattice_nd * self.lattice_domain_site
+        local_size_intel = g.GPU_limit_max_workgroup_size or 0
+        workgroup_factor = local_size_intel if local_size_intel else 32
+        ge = 12 if self.lattice_group == 3 else 4
+        self.lattice_group_elements = ge
+        al = g.buffer_size_align
+        self.lattice_parameters_size = al(8)
+        self.lattice_energies_size = al(self.ITER)
+        self.lattice_energies_offset = self.lattice_energies_size
+        self.lattice_table_row_size = al(self.lattice_domain_site)
+        self.lattice_table_row_size_half = al(self.lattice_domain_site // 2)
+        self.lattice_table_exact_row_size = al(self.lattice_domain_exact_site)
+        self.lattice_table_exact_row_size_half = al(self.lattice_domain_exact_site // 2)
+        self.lattice_table_size = al(self.lattice_table_row_size * self.lattice_nd * ge // 4)
+        self.lattice_measurement_size = al(int(math.ceil(self.lattice_table_exact_row_size / workgroup_factor)))
+        self.lattice_measurement_size_F = self.lattice_measurement_size
+        self.lattice_polyakov_size = al(self.lattice_domain_exact_n1n2n3)
+        self.lattice_polyakov_loop_size = al(self.ITER)
+        self.lattice_polyakov_loop_offset = al(int(math.ceil(self.lattice_polyakov_size / workgroup_factor)))
+        self.lattice_action_size = self.lattice_table_exact_row_size
+        # PRNG preparation (suncl.cpp:2301-2311)
+        P = self.PRNG0
+        half = self.lattice_table_row_size_half
+        P.PRNG_instances = half if self.fused_prng else 0       # field is user-settable: "0 for autoselect"
+        if self.ints == model_start_hot:
+            P.PRNG_samples = al(self.lattice_table_row_size * self.lattice_nd + 3 * half * (self.NHIT + 1))
+        else:
+            P.PRNG_samples = al(self.NHITPar * (3 * half * (self.NHIT + 1)))
+        if P.PRNG_instances:   # explicit instance count: samples per instance, as PRNG::initialize does for autoselect
+            P.PRNG_samples = 1 + (P.PRNG_samples - 1) // P.PRNG_instances
+        P.GPU0 = g
+        self.prngstep = half
+        P.initialize()
+        self.header = self.lattice_make_header()
+
+    def lattice_make_header(self) -> str:
+        n = self.lattice_full_size
+        prec = {0: "single", 1: "double", 2: "mixed"}[self.precision]
+        h = (f" GPU SU({self.lattice_group}) simulator {VERSION} (qcdgpu_b200)\n\n"
+             f" Monte Carlo simulation of {self.lattice_nd}D SU({self.lattice_group}) LGT\n\n"
+             " ***************************************************\n"
+             f" Active platform          : CUDA (sm_{self.GPU0.GPU_info.cc_major}{self.GPU0.GPU_info.cc_minor})\n"
+             f" Active device            : {self.GPU0.GPU_info.device_name.decode()}\n"
+             " ***************************************************\n"
+             f" lattice size                : {n[0]:3d} x {n[1]:3d} x {n[2]:3d} x {n[3]:3d}\n"
+             f" init                        : {self.INIT}\n"
+             f" ints (0=hot, 1=cold, 2=gid) : {self.ints}\n"
+             + self.PRNG0.print_generator() +
+             f" nav                         : {self.NAV}\n"
+             f" niter                       : {self.NITER}\n"
+             f" iter (# of samples)         : {self.ITER}\n"
+             f" nhit                        : {self.NHIT}\n"
+             f" nhitPar                     : {self.NHITPar}\n"
+             f" precision                   : {prec}\n"
+             " ***************************************************\n"
+             f" BETA                        : {self.BETA: 16.13e}\n"
+             f" PHI   (lambda_3)            : {self.PHI: 16.13e}\n"
+             f" OMEGA (lambda_8)            : {self.OMEGA: 16.13e}\n"
+             " ***************************************************\n")
+        return h
+
+    # ------------------------------------------------------------------ lattice_create_buffers (suncl.cpp:3877-3991)
+    def lattice_create_buffers(self):
+        g = self.GPU0
+        double = self.precision == model_precision_double
+        # NB: the reference allocates double4 tables for anything != single while its kernels treat mixed as
+        # single; here mixed == float4 storage, as the kernels define it.
+        rdt = np.float64 if double else np.float32
+        vec = 32 if double else 16
+        self.size_lattice_table = self.lattice_table_size
+        self.size_lattice_measurement = max(self.lattice_measurement_size_F,
+                                            2 * self.lattice_polyakov_loop_offset if self.PL_level > 1 else 0)
+        self.size_lattice_energies = self.lattice_energies_size
+        self.size_lattice_energies_plq = self.lattice_energies_offset
+        self.size_lattice_polyakov_loop = 2 * self.lattice_polyakov_loop_size * max(self.PL_level, 1)
+        params = np.zeros(self.lattice_parameters_size, dtype=rdt)
+        params[0] = self.BETA / self.lattice_group
+        params[1] = self.PHI
+        params[2] = self.OMEGA
+        self.lattice_table = g.buffer_init(GPU.buffer_type_IO, self.size_lattice_table, None, vec)
+        self.lattice_parameters = g.buffer_init(GPU.buffer_type_Constant, self.lattice_parameters_size, params, params.itemsize)
+        self.lattice_measurement = g.buffer_init(GPU.buffer_type_IO, self.size_lattice_measurement, None, 16)
+        lds_size = int(g.GPU_info.local_memory_size) // 4 // 4 // 2
+        self.lattice_lds = g.buffer_init(GPU.buffer_type_LDS, lds_size, None, 16)
+        self.lattice_energies = g.buffer_init(GPU.buffer_type_IO, self.size_lattice_energies, None, 16)
+        self.lattice_energies_plq = g.buffer_init(GPU.buffer_type_IO, self.size_lattice_energies_plq, None, 16)
+        if self.PL_level > 0:
+            self.lattice_polyakov_loop = g.buffer_init(GPU.buffer_type_IO, self.size_lattice_polyakov_loop, None, 16)
+
+    # ------------------------------------------------------------------ lattice_make_programs (suncl.cpp:3265-3648)
+    def options_common(self) -> str:
+        n = self.lattice_domain_size
+        o = "-Werror"
+        if self.ints == model_start_gid:
+            o += " -D GID_UPD"
+        o += f" -D SUN={self.lattice_group} -D ND={self.lattice_nd} -D N1={n[0]} -D N2={n[1]} -D N3={n[2]} -D N4={n[3]}"
+        if not (self.PHI == 0.0 and self.OMEGA == 0.0):
+            o += " -D TBC"
+        o += f" -D ROWSIZE={self.lattice_table_row_size} -D PRECISION={self.precision}"
+        return o
+
+    def lattice_make_programs(self):
+        g = self.GPU0
+        oc = self.options_common()
+        options = oc + f" -D NHIT={self.NHIT} -D NHITPar={self.NHITPar} -D PRNGSTEP={self.lattice_table_row_size_half}"
+        self.program_update = g.program_create(None, options)
+        init_gs = [self.lattice_table_exact_row_size]
+        init_hot_gs = [self.lattice_group_elements * self.lattice_table_row_size]
+        monte_gs = [self.lattice_table_exact_row_size_half]
+        wg = int(g.GPU_info.max_workgroup_size)
+        if self.ints == model_start_gid:
+            self.sun_init_id = g.kernel_init("lattice_init_gid", 1, init_gs, None)
+            g.kernel_init_buffer(self.sun_init_id, self.lattice_table)
+        elif self.ints == model_start_cold:
+            self.sun_init_id = g.kernel_init("lattice_init_cold", 1, init_gs, None)
+            g.kernel_init_buffer(self.sun_init_id, self.lattice_table)
+        else:
+            self.sun_init_hot_id = []
+            for d in DIRS:
+                k = g.kernel_init(f"lattice_init_hot_{d}", 1, init_hot_gs, None)
+                g.kernel_init_buffer(k, self.lattice_table)
+                g.kernel_init_buffer(k, self.PRNG0.PRNG_randoms_id)
+                self.sun_init_hot_id.append(k)
+        self.sun_GramSchmidt_id = g.kernel_init("lattice_GramSchmidt", 1, init_gs, None)
+        g.kernel_init_buffer(self.sun_GramSchmidt_id, self.lattice_table)
+        g.kernel_init_buffer(self.sun_GramSchmidt_id, self.lattice_parameters)
+        self.sun_update_id = {}
+        self.sun_overrelax_id = {}
+        for par in ("odd", "even"):
+            for d in DIRS:
+                k = g.kernel_init(f"update_{par}_{d}", 1, monte_gs, None)
+                g.kernel_init_buffer(k, self.lattice_table)
+                g.kernel_init_buffer(k, self.lattice_parameters)
+                g.kernel_init_buffer(k, self.PRNG0.PRNG_randoms_id)
+                self.sun_update_id[(par, d)] = k
+                if self.or_steps:
+                    k = g.kernel_init(f"overrelax_{par}_{d}", 1, monte_gs, None)
+                    g.kernel_init_buffer(k, self.lattice_table)
+                    g.kernel_init_buffer(k, self.lattice_parameters)
+                    self.sun_overrelax_id[(par, d)] = k
+        # measurements
+        self.program_measurements = g.program_create(None, oc)
+        meas_gs = [self.lattice_action_size]
+        self.sun_clear_measurement_id = g.kernel_init("clear_measurement", 1, [self.size_lattice_measurement], None)
+        g.kernel_init_buffer(self.sun_clear_measurement_id, self.lattice_measurement)
+        self.sun_measurement_id = g.kernel_init("lattice_measurement", 1, meas_gs, [wg])
+        for b in (self.lattice_table, self.lattice_measurement, self.lattice_parameters, self.lattice_lds):
+            g.kernel_init_buffer(self.sun_measurement_id, b)
+        size_reduce = int(math.ceil(self.lattice_table_exact_row_size / g.kernel_get_worksize(self.sun_measurement_id)))
+        self.sun_measurement_reduce_id = g.kernel_init("reduce_measurement_double2", 1, [wg], [wg])
+        for b in (self.lattice_measurement, self.lattice_energies, self.lattice_lds):
+            g.kernel_init_buffer(self.sun_measurement_reduce_id, b)
+        self.argument_measurement_index = g.kernel_init_constant(self.sun_measurement_reduce_id, size_reduce)
+        self.sun_measurement_plq_id = g.kernel_init("lattice_measurement_plq", 1, meas_gs, [wg])
+        ws = g.kernel_get_worksize(self.sun_measurement_plq_id)
+        offset_plq = g.buffer_size_align(int(math.ceil(self.lattice_table_exact_row_size / ws)), ws)
+        for b in (self.lattice_table, self.lattice_measurement, self.lattice_parameters, self.lattice_lds):
+            g.kernel_init_buffer(self.sun_measurement_plq_id, b)
+        g.kernel_init_constant(self.sun_measurement_plq_id, offset_plq)
+        size_plq = int(math.ceil(self.lattice_table_exact_row_size / ws))
+        self.sun_measurement_plq_reduce_id = g.kernel_init("reduce_measurement_plq_double2", 1, [wg], [wg])
+        for b in (self.lattice_measurement, self.lattice_energies_plq, self.lattice_lds):
+            g.kernel_init_buffer(self.sun_measurement_plq_reduce_id, b)
+        self.argument_plq_index = g.kernel_init_constant(self.sun_measurement_plq_reduce_id,
+                                                         [size_plq, offset_plq, self.lattice_energies_offset, 0])
+        # Polyakov loop
+        if self.PL_level > 0:
+            self.program_polyakov = g.program_create(None, oc + f" -D PL={self.PL_level}")
+            self.sun_polyakov_id = g.kernel_init("lattice_polyakov", 1, [self.lattice_polyakov_size], [wg])
+            ws = g.kernel_get_worksize(self.sun_polyakov_id)
+            offset_p = g.buffer_size_align(int(math.ceil(self.lattice_polyakov_size / ws)), ws)
+            for b in (self.lattice_table, self.lattice_measurement, self.lattice_parameters, self.lattice_lds):
+                g.kernel_init_buffer(self.sun_polyakov_id, b)
+            g.kernel_init_constant(self.sun_polyakov_id, offset_p)
+            size_p = int(math.ceil(self.lattice_polyakov_size / ws))
+            self.sun_polyakov_reduce_id = g.kernel_init("reduce_polyakov_double2", 1, [wg], [wg])
+            for b in (self.lattice_measurement, self.lattice_polyakov_loop, self.lattice_lds):
+                g.kernel_init_buffer(self.sun_polyakov_reduce_id, b)
+            self.argument_polyakov_index = g.kernel_init_constant(
+                self.sun_polyakov_reduce_id, [size_p, offset_p, self.lattice_polyakov_loop_size, 0])
+
+    # ------------------------------------------------------------------ run loop (suncl.cpp:5212-5505)
+    def _measure(self):
+        g = self.GPU0
+        if self.get_plaquettes_avr:
+            g.kernel_run(self.sun_measurement_plq_id)
+            g.kernel_init_constant_reset(self.sun_measurement_plq_reduce_id, self.ITER_counter, self.argument_plq_index)
+            g.kernel_run(self.sun_measurement_plq_reduce_id)
+        if self.get_actions_avr:
+            g.kernel_run(self.sun_measurement_id)
+            g.kernel_init_constant_reset(self.sun_measurement_reduce_id, self.ITER_counter, self.argument_measurement_index)
+            g.kernel_run(self.sun_measurement_reduce_id)
+        if self.PL_level > 0:
+            g.kernel_run(self.sun_clear_measurement_id)
+            g.kernel_run(self.sun_polyakov_id)
+            g.kernel_init_constant_reset(self.sun_polyakov_reduce_id, self.ITER_counter, self.argument_polyakov_index)
+            g.kernel_run(self.sun_polyakov_reduce_id)
+
+    def lattice_sweep(self):
+        """One sweep: 8 x (produce, update) + reunitarisation  (suncl.cpp:5357-5377)."""
+        g, P = self.GPU0, self.PRNG0
+        for par in ("odd", "even"):
+            for d in DIRS:
+                if not self.turnoff_prns:
+                    P.produce()
+                if not self.turnoff_updates:
+                    g.kernel_run(self.sun_update_id[(par, d)])
+        for _ in range(self.or_steps):
+            for par in ("odd", "even"):
+                for d in DIRS:
+                    g.kernel_run(self.sun_overrelax_id[(par, d)])
+        if not self.turnoff_gramschmidt:
+            g.kernel_run(self.sun_GramSchmidt_id)
+
+    def lattice_start(self):
+        """Buffers, programs and the initial configuration + its measurement (slot 0)."""
+        g, P = self.GPU0, self.PRNG0
+        self.lattice_create_buffers()
+        self.lattice_make_programs()
+        if self.ints == model_start_hot:
+            P.produce()
+        if self.ints == model_start_hot:
+            for i, k in enumerate(self.sun_init_hot_id):
+                g.kernel_run(k)
+                if i < 3 and not self.turnoff_prns:
+                    P.produce()
+        else:
+            g.kernel_run(self.sun_init_id)
+        self._measure()
+        self.ITER_counter += 1
+
+    def lattice_simulate(self):
+        g = self.GPU0
+        t0 = time.time()
+        self.lattice_start()
+        for _ in range(self.NAV_counter, self.NAV):
+            self.lattice_sweep()
+            self.NAV_counter += 1
+        for _ in range(self.ITER_counter, self.ITER):
+            for _ in range(self.NITER):
+                self.lattice_sweep()
+            self._measure()
+            self.ITER_counter += 1
+        g.synchronize()
+        self.elapsed = time.time() - t0
+
+    # ------------------------------------------------------------------ analysis (suncl.cpp:1328-1675, data_analysis.cpp:107-135)
+    @staticmethod
+    def _series(values: np.ndarray, denominator: float) -> dict:
+        data = values / denominator
+        last = len(data) - 1
+        mean = float(data[1:].sum() / last) if last > 0 else 0.0
+        var = float(((data[1:] - mean) ** 2).sum() / last) if last > 0 else 0.0
+        return {"data": data, "mean_value": mean, "variance": var, "GPU_last_value": float(data[last])}
+
+    @staticmethod
+    def _joint(a: dict, b: dict) -> dict:
+        data = 0.5 * (a["data"] + b["data"])
+        last = len(data) - 1
+        mean = float(data[1:].sum() / last) if last > 0 else 0.0
+        var = float(((data[1:] - mean) ** 2).sum() / last) if last > 0 else 0.0
+        return {"data": data, "mean_value": mean, "variance": var, "GPU_last_value": float(data[last])}
+
+    def lattice_analysis(self):
+        g = self.GPU0
+        A = self.Analysis
+        den = float(self.lattice_full_site * 3)
+        if self.get_actions_avr:
+            e = g.buffer_map(self.lattice_energies, np.float64).reshape(-1, 2)[: self.ITER]
+            A["S_spat"] = self._series(e[:, 0].copy(), den)
+            A["S_temp"] = self._series(e[:, 1].copy(), den)
+            A["S_total"] = self._joint(A["S_spat"], A["S_temp"])
+        if self.get_plaquettes_avr:
+            e = g.buffer_map(self.lattice_energies_plq, np.float64).reshape(-1, 2)[: self.ITER]
+            A["Plq_spat"] = self._series(e[:, 0].copy(), den)
+            A["Plq_temp"] = self._series(e[:, 1].copy(), den)
+            A["Plq_total"] = self._joint(A["Plq_spat"], A["Plq_temp"])
+        if self.PL_level > 0:
+            e = g.buffer_map(self.lattice_polyakov_loop, np.float64).reshape(-1, 2)
+            pden = float(self.lattice_full_n1n2n3 * self.lattice_group)
+            A["Polyakov_loop"] = self._series(e[: self.ITER, 0].copy(), pden)
+            A["Polyakov_loop_im"] = self._series(e[: self.ITER, 1].copy(), pden)
+            if self.PL_level > 1:
+                o = self.lattice_polyakov_loop_size
+                A["Polyakov_loop_P2"] = self._series(e[o: o + self.ITER, 0].copy(), float(self.lattice_full_n1n2n3 * self.lattice_group ** 2))
+                A["Polyakov_loop_P4"] = self._series(e[o: o + self.ITER, 1].copy(), float(self.lattice_full_n1n2n3 * self.lattice_group ** 4))
+        return A
+
+    # lattice_write_results (suncl.cpp:1679-1854)
+    def columns(self) -> list[str]:
+        cols = []
+        if self.get_plaquettes_avr: cols += ["Plq_spat", "Plq_temp", "Plq_total"]
+        if self.get_actions_avr: cols += ["S_spat", "S_temp", "S_total"]
+        if self.PL_level > 0: cols += ["Polyakov_loop", "Polyakov_loop_im"]
+        if self.PL_level > 1: cols += ["Polyakov_loop_P2", "Polyakov_loop_P4"]
+        return cols
+
+    def lattice_write_results(self, filename: str | None = None) -> str:
+        A = self.Analysis
+        if filename is None:
+            filename = os.path.join(self.path, self.fprefix + time.strftime("%y-%b-%d-%H-%M-%S") + ".txt")
+        cols = self.columns()
+        with open(filename, "w") as f:
+            f.write(self.header)
+            f.write(f" Elapsed time             : {self.elapsed:.3f} s\n")
+            f.write(" ***************************************************\n")
+            for c in ("S_total", "Plq_total", "Polyakov_loop", "Polyakov_loop_im", "Polyakov_loop_P2", "Polyakov_loop_P4"):
+                if c in A:
+                    f.write(f" Mean {c:20s}: {A[c]['mean_value']: 16.13e}\n")
+                    f.write(f" Variance {c:16s}: {A[c]['variance']: 16.13e}\n")
+            f.write(" ***************************************************\n")
+            f.write(" Data fields:\n")
+            f.write("    #,  " + "".join(f"{c:<21s} " for c in cols) + "\n")
+            f.write(" ***************************************************\n")
+            for i in range(self.ITER):
+                f.write(f"{i:5d}" + "".join(f" {A[c]['data'][i]: 16.13e}" for c in cols) + "\n")
+        return filename
+
+    # ------------------------------------------------------------------ helpers for tests / tools
+    def table_numpy(self) -> np.ndarray:
+        """Link table as (planes, ROWSIZE, 4) in the storage precision (a copy)."""
+        rdt = np.float64 if self.precision == model_precision_double else np.float32
+        t = self.GPU0.buffer_map(self.lattice_table, rdt)
+        planes = self.lattice_group_elements
+        return t[: planes * self.lattice_table_row_size * 4].reshape(planes, self.lattice_table_row_size, 4).copy()
+
+    def set_table(self, table: np.ndarray):
+        rdt = np.float64 if self.precision == model_precision_double else np.float32
+        full = self.GPU0.buffer_map(self.lattice_table, rdt).copy()
+        flat = np.ascontiguousarray(table, dtype=rdt).reshape(-1)
+        full[: flat.size] = flat
+        self.GPU0.buffer_write_from(self.lattice_table, full)
+
+    def close(self):
+        self.GPU0.close()
+
+
+def main(argv=None):
+    """QCDGPU.cpp main(): defaults, optional init.dat, init -> simulate -> analysis -> write."""
+    import sys
+    argv = sys.argv[1:] if argv is None else argv
+    m = Model()
+    if argv:
+        m.lattice_get_init_file(argv[0])
+    t0 = time.time()
+    m.lattice_init()
+    print(m.header)
+    m.lattice_simulate()
+    m.lattice_analysis()
+    out = m.lattice_write_results()
+    cols = m.columns()
+    print(" #     " + " ".join(f"{c:>14s}" for c in cols))
+    for i in range(m.ITER):
+        print(f"[{i:5d}]: " + " ".join(f"{m.Analysis[c]['data'][i]:14.8f}" for c in cols))
+    print(f"\nresults: {out}\nEXECUTION TIME: {time.time() - t0:f} sec\n")
+    m.close()
+
+
+if __name__ == "__main__":
+    main()
