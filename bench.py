@@ -165,6 +165,8 @@ def native_single(args):
     dims = tuple(int(x) for x in args.dims.split("x")) if args.dims else WORKLOAD["dims"]
     m = build_model(dims, fused=not args.buffered)
     g = m.GPU0
+    if args.materialize:
+        g.set_fused_prng(False)      # PRNG_instances == PRNGSTEP, but every produce() writes the PRN buffer
     V = m.lattice_domain_site
     links_per_step = 4 * V
     for _ in range(args.warmup):
@@ -247,6 +249,7 @@ def main():
     ap.add_argument("--dims", default="")
     ap.add_argument("--buffered", action="store_true", help="reference-layout PRN buffer instead of the fused generator")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--materialize", action="store_true", help="one generator per update thread, PRN buffer written (diagnostic)")
     args = ap.parse_args()
     if args.impl == "reference":
         return reference_main(args)

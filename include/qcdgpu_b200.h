@@ -110,6 +110,10 @@ int   qgpu_synchronize(qgpu* h);
  * with its state in registers and the buffer is never written.  Any other access materialises it first.
  * Streams and results are identical either way. */
 void  qgpu_set_fused_prng(qgpu* h, int on);
+/* L2 tiling of the update passes: x-chunk width of the launch order (0 = the reference's order, -1 = automatic:
+ * 8 once three x-slices of links exceed 48 MB; env QCDGPU_TILE_X overrides the automatic choice).  Results do
+ * not depend on it. */
+void  qgpu_set_tile_x(qgpu* h, int tile);
 /* raw device pointer of a buffer (halo exchange, interop) and raw stream handle (cudaStream_t) */
 void* qgpu_buffer_device_ptr(qgpu* h, int buffer_id);
 void* qgpu_stream(qgpu* h);

@@ -89,6 +89,7 @@ struct qgpu {
     qgpu_device_info info;
     bool profiling = false, brief = false, show_stage = false;
     bool return_errors = false, async = false, fused = false;
+    int tile_x = -1;
     std::string last_error;
     std::vector<ProgramCfg> programs;
     std::vector<Kernel> kernels;
@@ -156,7 +157,7 @@ void parse_options(const char* opt, ProgramCfg& c) {
     }
 }
 
-Geom make_geom(const ProgramCfg& c) {
+Geom make_geom(const ProgramCfg& c, int tile_override = -1) {
     Geom g;
     memset(&g, 0, sizeof(g));
     g.n1 = c.n1; g.n2 = c.n2; g.n3 = c.n3; g.n4 = c.n4;
@@ -168,6 +169,19 @@ Geom make_geom(const ProgramCfg& c) {
     g.left_sites = c.left_sites; g.full_sites = c.full_sites;
     g.nhit = (uint32_t)c.nhit; g.nhitpar = (uint32_t)c.nhitpar;
     if (c.biglat && g.n234) { g.tw_lo = c.left_sites / g.n234; g.tw_hi = c.full_sites / g.n234; }
+    // L2 tiling (lattice.cuh remap_gid): worthwhile once three x-slices of all links no longer fit the L2
+    {
+        static int env_tile = -2;
+        if (env_tile == -2) { const char* e = getenv("QCDGPU_TILE_X"); env_tile = e ? atoi(e) : -1; }
+        const uint32_t nx = c.biglat ? c.n1 - 2 : c.n1;
+        const size_t slice_bytes = (size_t)g.n234 * 4 * (c.sun == 3 ? 3 : 1) * (c.precision == 1 ? 32 : 16);
+        uint32_t tile = 0;
+        if (tile_override >= 0) tile = (uint32_t)tile_override;
+        else if (env_tile >= 0) tile = (uint32_t)env_tile;
+        else if (3 * slice_bytes > (size_t)48 << 20) tile = 8;
+        if (tile >= nx || (c.n2 & 1)) tile = 0;
+        g.tile_x = tile;
+    }
     return g;
 }
 int prec_index(const ProgramCfg& c) { return c.precision == 1 ? 1 : 0; }   // mixed == single storage/arithmetic (complex.h:61-91)
@@ -255,7 +269,7 @@ int launch_kernel(qgpu* h, int kid) {
             memset(&a, 0, sizeof(a));
             a.table = buf_ptr(h, k, 0); a.params = buf_ptr(h, k, 1);
             if (!a.table || !a.params) return fail(h, "kernel %s: arguments (lattice_table, lattice_parameters) not set", k.name.c_str());
-            a.geom = make_geom(c); a.odd = k.odd; a.tbc = c.tbc ? 1 : 0;
+            a.geom = make_geom(c, h->tile_x); a.odd = k.odd; a.tbc = c.tbc ? 1 : 0;
             UpdateLaunchFn fn = get_update_launcher(c.sun, prec, k.dir);
             if (!fn) return fail(h, "kernel %s: no CUDA instantiation for SUN=%d PRECISION=%d", k.name.c_str(), c.sun, c.precision);
             if (k.kind == K_OVERRELAX) { a.overrelax = 1; CUDA_OK(h, fn(a, st)); break; }
@@ -400,6 +414,7 @@ void qgpu_set_error_mode(qgpu* h, int r) { h->return_errors = r != 0; }
 const char* qgpu_last_error(qgpu* h) { return h->last_error.c_str(); }
 void qgpu_set_async(qgpu* h, int on) { h->async = on != 0; }
 void qgpu_set_fused_prng(qgpu* h, int on) { h->fused = on != 0; }
+void qgpu_set_tile_x(qgpu* h, int tile) { h->tile_x = tile; }
 uint64_t qgpu_launch_count(qgpu* h) { return h->launches; }
 void* qgpu_stream(qgpu* h) { return (void*)h->stream; }
 

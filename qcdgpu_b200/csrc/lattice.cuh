@@ -31,6 +31,7 @@ struct Geom {
     uint32_t full_sites;          // FULL_SITES
     uint32_t nhit, nhitpar;
     uint32_t tw_lo, tw_hi;        // BIGLAT twist test: x + left_sites/n234 == tw_lo || == tw_hi
+    uint32_t tile_x;              // L2 tiling of the update passes: x-chunk width (0 = reference order)
 };
 
 struct Coord { uint32_t x, y, z, t; };
@@ -58,6 +59,29 @@ __device__ __forceinline__ uint32_t parity_gid(const Geom& g, uint32_t GID, bool
     uint32_t gindex = odd ? gde - (par ^ 1u) : gde + par;
     if (g.biglat) gindex += g.n234;
     return gindex;
+}
+// L2-friendly launch order.  The reference's thread index GID enumerates sites with x slowest
+// (GID = y/2 + N2/2 (z + N3 (t + N4 x))), so the x+-1 neighbours of a site are touched a whole
+// N2 N3 N4 volume later -- at 64^4 that is 100 MB of links in between and they have left the L2 by then
+// (measured: 1.75x the compulsory DRAM reads).  Thread k of the launch instead works on logical index
+// GID = remap(k): x is cut into chunks of `tile_x` slices and inside a chunk t is the slow loop and x the
+// next one, so the window that must stay cached is (tile_x + 2) x 3 (y,z)-planes.  Which thread updates a site
+// changes, the site's GID (hence its PRNG instance / PRN slots) does not.
+__device__ __forceinline__ uint32_t remap_gid(const Geom& g, uint32_t k) {
+    if (g.tile_x == 0) return k;
+    const uint32_t P = (g.n2 >> 1) * g.n3;                 // threads per (x,t) plane
+    const uint32_t nx = g.biglat ? g.n1 - 2 : g.n1;        // updated x-slices
+    const uint32_t chunk = g.tile_x * g.n4 * P;
+    const uint32_t xc = k / chunk;
+    uint32_t r = k - xc * chunk;
+    const uint32_t x0 = xc * g.tile_x;
+    const uint32_t w = min(g.tile_x, nx - x0);
+    const uint32_t wp = w * P;
+    const uint32_t t = r / wp;
+    r -= t * wp;
+    const uint32_t xi = r / P;
+    const uint32_t yz = r - xi * P;
+    return yz + P * (t + g.n4 * (x0 + xi));
 }
 template <int DIR> __device__ __forceinline__ Coord nb_plus(const Geom& g, Coord c) {
     // sun_common.cl:455-483

@@ -10,8 +10,8 @@
 //
 // New design: the reference keeps the 24 RANLUX seeds as fp32 multiples of 2^-24
 // and steps them with float compares; here they are 24-bit integers, one
-// subtract-with-borrow is an IADD3 + a mask, and numbers are converted to float
-// only when a consumer actually asks for them.  The float results are identical:
+// subtract-with-borrow is a carry-flag subtract + a mask, and numbers are converted
+// to float only when a consumer can actually use them.  The float results are identical:
 // every reference operation on those values is exact in fp32 except the
 // "uni < 2^-12" fix-up, which is reproduced with round-to-nearest float adds.
 //
@@ -26,40 +26,54 @@ namespace qcd {
 struct F4 { float x, y, z, w; };
 
 // ---------------------------------------------------------------- RANLUX
-// Register state: s[0..23] hold the ring buffer ROTATED so that the next number to be
-// produced always uses i24 = 23, j24 = 9: all indices are compile-time constants and the
-// 24 words stay in registers.  `left` = numbers left before the next luxury skip (0..24).
+// Register state: s[0..23] hold the ring buffer ROTATED so that the next number to be produced
+// always uses i24 = 23, j24 = 9: all indices are compile-time constants and the 24 words stay in
+// registers.  Each word holds the 24-bit seed in its TOP 24 bits (x << 8, low byte zero): a
+// subtract-with-borrow step is then one `subc.cc.u32` whose borrow travels in the hardware carry flag
+// (the only serial dependency: ~1 ALU latency per step) plus one `and` that clears the low byte off the
+// critical path.  `left` = numbers left before the next luxury skip (0..24), as RL_in24 of the host replica.
+#define QCD_SWB(I, J) "subc.cc.u32 %" #I ", %" #J ", %" #I ";\n\tand.b32 %" #I ", %" #I ", 0xFFFFFF00;\n\t"
+#define QCD_SWB_OPERANDS(s, c)                                                                              \
+    "+r"(s[0]), "+r"(s[1]), "+r"(s[2]), "+r"(s[3]), "+r"(s[4]), "+r"(s[5]), "+r"(s[6]), "+r"(s[7]),         \
+    "+r"(s[8]), "+r"(s[9]), "+r"(s[10]), "+r"(s[11]), "+r"(s[12]), "+r"(s[13]), "+r"(s[14]), "+r"(s[15]),   \
+    "+r"(s[16]), "+r"(s[17]), "+r"(s[18]), "+r"(s[19]), "+r"(s[20]), "+r"(s[21]), "+r"(s[22]), "+r"(s[23]), \
+    "+r"(c)
+// carry (0/1) -> CF, N steps, CF -> carry
+#define QCD_SWB_PRE  "{\n\t.reg .u32 t;\n\tsub.cc.u32 t, 0, %24;\n\t"
+#define QCD_SWB_POST "subc.u32 t, 0, 0;\n\tand.b32 %24, t, 1;\n\t}"
+#define QCD_SWB_1  QCD_SWB(23, 9)
+#define QCD_SWB_4  QCD_SWB_1 QCD_SWB(22, 8) QCD_SWB(21, 7) QCD_SWB(20, 6)
+#define QCD_SWB_5  QCD_SWB_4 QCD_SWB(19, 5)
+#define QCD_SWB_7  QCD_SWB_5 QCD_SWB(18, 4) QCD_SWB(17, 3)
+#define QCD_SWB_24 QCD_SWB_7 QCD_SWB(16, 2) QCD_SWB(15, 1) QCD_SWB(14, 0) QCD_SWB(13, 23) QCD_SWB(12, 22)  \
+    QCD_SWB(11, 21) QCD_SWB(10, 20) QCD_SWB(9, 19) QCD_SWB(8, 18) QCD_SWB(7, 17) QCD_SWB(6, 16)             \
+    QCD_SWB(5, 15) QCD_SWB(4, 14) QCD_SWB(3, 13) QCD_SWB(2, 12) QCD_SWB(1, 11) QCD_SWB(0, 10)
+
 struct Ranlux {
-    uint32_t s[24];
+    uint32_t s[24];   // seed << 8
     uint32_t carry;   // 0 / 1
     uint32_t left;    // in24 of the host replica
 
     // one block of 24 subtract-with-borrow steps: afterwards the ring is back in canonical rotation
     __device__ __forceinline__ void block24() {
-#pragma unroll
-        for (int k = 0; k < 24; k++) {
-            const int i = 23 - k, j = (9 - k + 24) % 24;
-            int32_t d = int32_t(s[j]) - int32_t(s[i]) - int32_t(carry);
-            carry = uint32_t(d) >> 31;
-            s[i] = uint32_t(d) & 0xFFFFFFu;
-        }
+        asm volatile(QCD_SWB_PRE QCD_SWB_24 QCD_SWB_POST : QCD_SWB_OPERANDS(s, carry));
     }
-    // n (< 24) single steps followed by a rotation that restores the canonical indices
-    template <int N> __device__ __forceinline__ void steps_rot() {
-        if (N == 0) return;
-#pragma unroll
-        for (int k = 0; k < N; k++) {
-            const int i = 23 - k, j = (9 - k + 24) % 24;
-            int32_t d = int32_t(s[j]) - int32_t(s[i]) - int32_t(carry);
-            carry = uint32_t(d) >> 31;
-            s[i] = uint32_t(d) & 0xFFFFFFu;
-        }
-        // after N steps the live indices are i24 = 23-N, j24 = 9-N: rotate up by N
+    template <int N> __device__ __forceinline__ void rotate() {
         uint32_t t[24];
 #pragma unroll
         for (int k = 0; k < 24; k++) t[(k + N) % 24] = s[k];
 #pragma unroll
         for (int k = 0; k < 24; k++) s[k] = t[k];
+    }
+    // N (< 24) single steps followed by the rotation that restores the canonical indices
+    template <int N> __device__ __forceinline__ void steps_rot() {
+        static_assert(N == 0 || N == 1 || N == 4 || N == 5 || N == 7, "RL_skip % 24 must be 0, 1, 5 or 7");
+        if (N == 0) return;
+        if (N == 1) asm volatile(QCD_SWB_PRE QCD_SWB_1 QCD_SWB_POST : QCD_SWB_OPERANDS(s, carry));
+        if (N == 4) asm volatile(QCD_SWB_PRE QCD_SWB_4 QCD_SWB_POST : QCD_SWB_OPERANDS(s, carry));
+        if (N == 5) asm volatile(QCD_SWB_PRE QCD_SWB_5 QCD_SWB_POST : QCD_SWB_OPERANDS(s, carry));
+        if (N == 7) asm volatile(QCD_SWB_PRE QCD_SWB_7 QCD_SWB_POST : QCD_SWB_OPERANDS(s, carry));
+        rotate<N>();
     }
     template <int NSKIP> __device__ __forceinline__ void luxury_skip() {
 #pragma unroll 1
@@ -69,29 +83,101 @@ struct Ranlux {
     // four consecutive numbers (one float4 sample).  24 % 4 == 0, so a sample never straddles a skip.
     template <int NSKIP> __device__ __forceinline__ F4 next4() {
         if (left == 0) { luxury_skip<NSKIP>(); left = 24; }
+        asm volatile(QCD_SWB_PRE QCD_SWB_4 QCD_SWB_POST : QCD_SWB_OPERANDS(s, carry));
         float o[4];
 #pragma unroll
         for (int k = 0; k < 4; k++) {
-            const int i = 23 - k, j = (9 - k + 24) % 24, jn = (8 - k + 24) % 24;
-            int32_t d = int32_t(s[j]) - int32_t(s[i]) - int32_t(carry);
-            carry = uint32_t(d) >> 31;
-            uint32_t u = uint32_t(d) & 0xFFFFFFu;
-            s[i] = u;
-            float f = __uint2float_rn(u) * 5.9604644775390625e-8f;          // exact
-            if (u < 4096u) {                                               // uni < 2^-12
-                f = __fadd_rn(f, __fmul_rn(5.9604644775390625e-8f, __uint2float_rn(s[jn]) * 5.9604644775390625e-8f));
+            const uint32_t x = s[23 - k];                       // new seed << 8
+            float f = __uint2float_rn(x) * 2.3283064365386963e-10f;        // (x >> 8) * 2^-24, exact
+            if (x < (4096u << 8)) {                                        // uni < 2^-12: add 2^-24 * seeds[j24 after the step]
+                f = __fadd_rn(f, __fmul_rn(5.9604644775390625e-8f, __uint2float_rn(s[8 - k]) * 2.3283064365386963e-10f));
                 if (f == 0.0f) f = 5.9604644775390625e-8f * 5.9604644775390625e-8f;
             }
             o[k] = f;
         }
-        // rotate by 4
-        uint32_t t[24];
-#pragma unroll
-        for (int k = 0; k < 24; k++) t[(k + 4) % 24] = s[k];
-#pragma unroll
-        for (int k = 0; k < 24; k++) s[k] = t[k];
+        rotate<4>();
         left -= 4;
         return { o[0], o[1], o[2], o[3] };
+    }
+    // A whole block of 24 numbers = 6 float4 samples, written to out[q * stride], q = 0..5.  Requires left == 0 or 24
+    // on entry (block boundary).  No register rotation: after 24 steps the ring is canonical again.
+    template <int NSKIP> __device__ __forceinline__ void next24(float4* out, uint32_t stride) {
+        if (left == 0) luxury_skip<NSKIP>();
+        // the "uni < 2^-12" fix-up of number k reads seeds[8-k]: for k <= 8 that word is overwritten later in this
+        // block (step 15+k), so keep the nine old values; for k >= 9 it is s[32-k], already final when step k runs
+        uint32_t old[9];
+#pragma unroll
+        for (int k = 0; k < 9; k++) old[k] = s[k];
+        block24();
+        float o[24];
+#pragma unroll
+        for (int k = 0; k < 24; k++) {
+            const uint32_t x = s[23 - k];
+            const uint32_t nx = (k <= 8) ? old[8 - k] : s[32 - k];
+            float f = __uint2float_rn(x) * 2.3283064365386963e-10f;
+            if (x < (4096u << 8)) {
+                f = __fadd_rn(f, __fmul_rn(5.9604644775390625e-8f, __uint2float_rn(nx) * 2.3283064365386963e-10f));
+                if (f == 0.0f) f = 5.9604644775390625e-8f * 5.9604644775390625e-8f;
+            }
+            o[k] = f;
+        }
+#pragma unroll
+        for (int q = 0; q < 6; q++) out[q * stride] = make_float4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]);
+        left = 0;
+    }
+    // One pass worth of generator work in a single loop (every code piece instantiated once, to stay inside the
+    // instruction cache): advance by `samples` float4, converting and storing the first `keep` of them to
+    // out[k * stride].  Whole 24-number blocks avoid the register rotation.
+    template <int NSKIP> __device__ __forceinline__ void run_pass(float4* out, uint32_t stride, uint32_t keep, uint32_t samples) {
+        uint32_t k = 0;
+#pragma unroll 1
+        while (k < samples) {
+            if (left == 0) { luxury_skip<NSKIP>(); left = 24; }
+            if (left == 24 && k + 6 <= samples) {
+                uint32_t old[9];
+#pragma unroll
+                for (int i = 0; i < 9; i++) old[i] = s[i];
+                block24();
+                if (k < keep) {
+#pragma unroll
+                    for (int q = 0; q < 6; q++) {
+                        float o[4];
+#pragma unroll
+                        for (int e = 0; e < 4; e++) {
+                            const int n = 4 * q + e;
+                            const uint32_t x = s[23 - n];
+                            const uint32_t nx = (n <= 8) ? old[8 - n] : s[32 - n];
+                            float f = __uint2float_rn(x) * 2.3283064365386963e-10f;
+                            if (x < (4096u << 8)) {
+                                f = __fadd_rn(f, __fmul_rn(5.9604644775390625e-8f, __uint2float_rn(nx) * 2.3283064365386963e-10f));
+                                if (f == 0.0f) f = 5.9604644775390625e-8f * 5.9604644775390625e-8f;
+                            }
+                            o[e] = f;
+                        }
+                        if (k + q < keep) out[(k + q) * stride] = make_float4(o[0], o[1], o[2], o[3]);
+                    }
+                }
+                k += 6; left = 0;
+            } else {
+                asm volatile(QCD_SWB_PRE QCD_SWB_4 QCD_SWB_POST : QCD_SWB_OPERANDS(s, carry));
+                if (k < keep) {
+                    float o[4];
+#pragma unroll
+                    for (int e = 0; e < 4; e++) {
+                        const uint32_t x = s[23 - e];
+                        float f = __uint2float_rn(x) * 2.3283064365386963e-10f;
+                        if (x < (4096u << 8)) {
+                            f = __fadd_rn(f, __fmul_rn(5.9604644775390625e-8f, __uint2float_rn(s[8 - e]) * 2.3283064365386963e-10f));
+                            if (f == 0.0f) f = 5.9604644775390625e-8f * 5.9604644775390625e-8f;
+                        }
+                        o[e] = f;
+                    }
+                    out[k * stride] = make_float4(o[0], o[1], o[2], o[3]);
+                }
+                rotate<4>();
+                left -= 4; k++;
+            }
+        }
     }
     // advance by one float4 sample without converting
     template <int NSKIP> __device__ __forceinline__ void skip4() {
@@ -101,8 +187,9 @@ struct Ranlux {
     }
     // advance by n float4 samples
     template <int NSKIP> __device__ __forceinline__ void skip_samples(uint32_t n) {
-        // bring to a 24-boundary, then whole periods of (24 outputs + NSKIP) in block form
+        // bring to a 24-boundary, then whole periods of (NSKIP + 24 outputs) in block form
         while (n > 0 && left != 0) { steps_rot<4>(); left -= 4; n--; }
+#pragma unroll 1
         while (n >= 6) {
             luxury_skip<NSKIP>();
             block24();
@@ -114,7 +201,7 @@ struct Ranlux {
 
 // state table layout in global memory (this backend's own; the reference's float4 x 7 table is
 // never read by the host except through PRNG::check_seeds):
-//   word w (0..25) of instance i at  table[w * instances + i]; w 0..23 seeds, 24 carry, 25 left
+//   word w (0..25) of instance i at  table[w * instances + i]; w 0..23 seeds << 8, 24 carry, 25 left
 __device__ __forceinline__ void ranlux_load(Ranlux& r, const uint32_t* table, uint32_t instances, uint32_t i) {
 #pragma unroll
     for (int w = 0; w < 24; w++) r.s[w] = table[size_t(w) * instances + i];
@@ -134,7 +221,7 @@ __device__ __forceinline__ void ranlux_seed(Ranlux& r, int32_t jseed) {
         int32_t k = jseed / 53668;
         jseed = 40014 * (jseed - k * 53668) - k * 12211;
         if (jseed < 0) jseed += 2147483563;
-        r.s[i] = uint32_t(jseed % 16777216);
+        r.s[i] = uint32_t(jseed % 16777216) << 8;
     }
     r.carry = (r.s[23] == 0u) ? 1u : 0u;
     r.left = 0u;        // the first request performs the luxury skip first (RL_in24 = 0 / in24 = 6.0f)

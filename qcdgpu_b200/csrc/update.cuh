@@ -32,6 +32,7 @@ struct PrnBuffered {
     __device__ __forceinline__ void burn() { ind += step; }
     __device__ __forceinline__ void finish() {}
     static constexpr bool kGid = false;
+    static constexpr int kMinBlocks = 3;
 };
 // INTS=2 / -D GID_UPD closed-form pseudo-randoms (su3_update_cl.cl:598-637); every trial is accepted
 struct PrnGid {
@@ -59,6 +60,7 @@ struct PrnGid {
     __device__ __forceinline__ void burn() {}
     __device__ __forceinline__ void finish() {}
     static constexpr bool kGid = true;
+    static constexpr int kMinBlocks = 2;
 };
 // Fused generators: instance GID lives in the registers of update thread GID.  Bit-exact with the
 // buffered path when the run is configured with PRNG_instances == PRNGSTEP (hard part 1):
@@ -74,6 +76,22 @@ struct PrnRanlux {
     __device__ __forceinline__ void burn() { used++; r.template skip4<NSKIP>(); }
     __device__ __forceinline__ void finish() { r.template skip_samples<NSKIP>(samples - used); ranlux_store(r, table, instances, id); }
     static constexpr bool kGid = false;
+    static constexpr int kMinBlocks = 2;
+};
+// RANLUX, two-phase: phase 1 of the kernel runs the whole generator work of the pass (all `samples` vec4,
+// luxury skips included) and parks the first `keep` = 3 (NHIT+1) NHITPar vec4 -- the most a link can consume --
+// in shared memory; phase 2 (the fp64/fp32 physics) reads them from there.  The 26 state registers are dead
+// during phase 2, which is what lets three blocks share an SM.
+struct PrnSmem {
+    struct Args { int dummy; };
+    const float4* p; uint32_t k, stride;
+    __device__ __forceinline__ PrnSmem(const float4* base, uint32_t stride_) : p(base), k(0), stride(stride_) {}
+    __device__ __forceinline__ F4 trial() { float4 r = p[k * stride]; k++; return { r.x, r.y, r.z, r.w }; }
+    __device__ __forceinline__ F4 direction() { return trial(); }
+    __device__ __forceinline__ void burn() { k++; }
+    __device__ __forceinline__ void finish() {}
+    static constexpr bool kGid = false;
+    static constexpr int kMinBlocks = 3;
 };
 template <class Gen, int WORDS>
 struct PrnSmallState {   // XOR128 (4 words), PM (4 words), MRG32k3a (2 x uint4 rows)
@@ -92,6 +110,7 @@ struct PrnSmallState {   // XOR128 (4 words), PM (4 words), MRG32k3a (2 x uint4 
         store();
     }
     static constexpr bool kGid = false;
+    static constexpr int kMinBlocks = 3;
 };
 template <> __device__ __forceinline__ void PrnSmallState<Xor128, 4>::load() {
     uint4 s = reinterpret_cast<const uint4*>(table)[id]; gen.x = s.x; gen.y = s.y; gen.z = s.z; gen.w = s.w;
@@ -227,22 +246,46 @@ template <typename R> __device__ __forceinline__ void acc3(M3<R>& S, const M3<R>
         for (int j = 0; j < 3; j++) { S.e[i][j].re += F.e[i][j].re; S.e[i][j].im += F.e[i][j].im; }
 }
 
-// staple contribution of the (MU,NU) plane at site p: forward + backward
-template <typename R, int MU, int NU, bool TBC>
-__device__ __forceinline__ void staple3_plane(const R* table, const Geom& g, const Coord& p, uint32_t gindex,
-                                              const Coord& pmu, const Twist<R>& tw, M3<R>& S, bool first) {
+// The six links of the (MU,NU) plane that enter the staple of U_mu(p): site indices and x coordinates (twist test)
+struct PlaneSites { uint32_t g_pmu, g_pnu, g_pmn, g_pmnmu; uint32_t x_pmu, x_pnu, x_pmn, x_pmnmu; };
+template <int MU, int NU>
+__device__ __forceinline__ PlaneSites plane_sites(const Geom& g, const Coord& p, const Coord& pmu) {
     Coord pnu = nb_plus<NU>(g, p);
     Coord pmn = nb_minus<NU>(g, p);
     Coord pmnmu = nb_plus<MU>(g, pmn);
-    uint32_t g_pmu = coords_to_gid(g, pmu), g_pnu = coords_to_gid(g, pnu);
-    uint32_t g_pmn = coords_to_gid(g, pmn), g_pmnmu = coords_to_gid(g, pmnmu);
+    PlaneSites s;
+    s.g_pmu = coords_to_gid(g, pmu); s.g_pnu = coords_to_gid(g, pnu);
+    s.g_pmn = coords_to_gid(g, pmn); s.g_pmnmu = coords_to_gid(g, pmnmu);
+    s.x_pmu = pmu.x; s.x_pnu = pnu.x; s.x_pmn = pmn.x; s.x_pmnmu = pmnmu.x;
+    return s;
+}
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" :: "l"(p)); }
+template <typename R, int DIR, int NPL>
+__device__ __forceinline__ void prefetch_link(const R* table, const Geom& g, uint32_t gindex) {
+#pragma unroll
+    for (int k = 0; k < NPL; k++) prefetch_l2(table + 4 * (size_t(gindex) + size_t(DIR + 4 * k) * g.rowsize));
+}
+// pull the six links of a plane towards L2 while the previous plane is being multiplied (no registers held)
+template <typename R, int MU, int NU, int NPL>
+__device__ __forceinline__ void plane_prefetch(const R* table, const Geom& g, uint32_t gindex, const PlaneSites& s) {
+    prefetch_link<R, NU, NPL>(table, g, s.g_pmu);
+    prefetch_link<R, MU, NPL>(table, g, s.g_pnu);
+    prefetch_link<R, NU, NPL>(table, g, gindex);
+    prefetch_link<R, NU, NPL>(table, g, s.g_pmnmu);
+    prefetch_link<R, MU, NPL>(table, g, s.g_pmn);
+    prefetch_link<R, NU, NPL>(table, g, s.g_pmn);
+}
+// staple contribution of the (MU,NU) plane at site p: forward + backward
+template <typename R, int MU, int NU, bool TBC>
+__device__ __forceinline__ void staple3_plane(const R* table, const Geom& g, uint32_t px, uint32_t gindex,
+                                              const PlaneSites& ps, const Twist<R>& tw, M3<R>& S, bool first) {
     // issue all six link loads of the plane before the arithmetic
-    M3r2<R> A  = load3<R, NU, TBC>(table, g, g_pmu, pmu.x, tw);      // U_nu(p+mu)
-    M3r2<R> B  = load3<R, MU, TBC>(table, g, g_pnu, pnu.x, tw);      // U_mu(p+nu)
-    M3r2<R> C  = load3<R, NU, TBC>(table, g, gindex, p.x, tw);       // U_nu(p)
-    M3r2<R> A2 = load3<R, NU, TBC>(table, g, g_pmnmu, pmnmu.x, tw);  // U_nu(p-nu+mu)
-    M3r2<R> B2 = load3<R, MU, TBC>(table, g, g_pmn, pmn.x, tw);      // U_mu(p-nu)
-    M3r2<R> C2 = load3<R, NU, TBC>(table, g, g_pmn, pmn.x, tw);      // U_nu(p-nu)
+    M3r2<R> A  = load3<R, NU, TBC>(table, g, ps.g_pmu, ps.x_pmu, tw);      // U_nu(p+mu)
+    M3r2<R> B  = load3<R, MU, TBC>(table, g, ps.g_pnu, ps.x_pnu, tw);      // U_mu(p+nu)
+    M3r2<R> C  = load3<R, NU, TBC>(table, g, gindex, px, tw);              // U_nu(p)
+    M3r2<R> A2 = load3<R, NU, TBC>(table, g, ps.g_pmnmu, ps.x_pmnmu, tw);  // U_nu(p-nu+mu)
+    M3r2<R> B2 = load3<R, MU, TBC>(table, g, ps.g_pmn, ps.x_pmn, tw);      // U_mu(p-nu)
+    M3r2<R> C2 = load3<R, NU, TBC>(table, g, ps.g_pmn, ps.x_pmn, tw);      // U_nu(p-nu)
     {   // forward: A B^+ C^+ = A (C B)^+
         M3<R> Bf = complete(B), D, F;
         mul_r2_full(C, Bf, D);
@@ -256,18 +299,36 @@ __device__ __forceinline__ void staple3_plane(const R* table, const Geom& g, con
         acc3(S, G);
     }
 }
+// plane order of the reference: X:{Y,Z,T} Y:{X,Z,T} Z:{Y,X,T} T:{Y,Z,X}  (su3_update_cl.cl:367-559)
+template <int MU> struct PlaneOrder {
+    static constexpr int n0 = (MU == 1) ? 0 : 1;
+    static constexpr int n1 = (MU == 0 || MU == 1 || MU == 3) ? 2 : 0;
+    static constexpr int n2 = (MU == 3) ? 0 : 3;
+};
 template <typename R, int MU, bool TBC>
 __device__ __forceinline__ M3<R> staple3(const R* table, const Geom& g, const Coord& p, uint32_t gindex, const Twist<R>& tw) {
     M3<R> S;
     Coord pmu = nb_plus<MU>(g, p);
-    // plane order of the reference: X:{Y,Z,T} Y:{X,Z,T} Z:{Y,X,T} T:{Y,Z,X}  (su3_update_cl.cl:367-559)
-    constexpr int n0 = (MU == 1) ? 0 : 1;
-    constexpr int n1 = (MU == 0 || MU == 1 || MU == 3) ? 2 : 0;
-    constexpr int n2 = (MU == 3) ? 0 : 3;
-    staple3_plane<R, MU, n0, TBC>(table, g, p, gindex, pmu, tw, S, true);
-    staple3_plane<R, MU, n1, TBC>(table, g, p, gindex, pmu, tw, S, false);
-    staple3_plane<R, MU, n2, TBC>(table, g, p, gindex, pmu, tw, S, false);
+    constexpr int n0 = PlaneOrder<MU>::n0, n1 = PlaneOrder<MU>::n1, n2 = PlaneOrder<MU>::n2;
+    PlaneSites s0 = plane_sites<MU, n0>(g, p, pmu);
+    PlaneSites s1 = plane_sites<MU, n1>(g, p, pmu);
+    PlaneSites s2 = plane_sites<MU, n2>(g, p, pmu);
+    plane_prefetch<R, MU, n1, 3>(table, g, gindex, s1);
+    staple3_plane<R, MU, n0, TBC>(table, g, p.x, gindex, s0, tw, S, true);
+    plane_prefetch<R, MU, n2, 3>(table, g, gindex, s2);
+    staple3_plane<R, MU, n1, TBC>(table, g, p.x, gindex, s1, tw, S, false);
+    staple3_plane<R, MU, n2, TBC>(table, g, p.x, gindex, s2, tw, S, false);
     return S;
+}
+// first things a site update will read: its own link and the first plane (issued before the generator phase)
+template <int SUN, typename R, int MU>
+__device__ __forceinline__ void prefetch_site_head(const R* table, const Geom& g, uint32_t gindex) {
+    constexpr int NPL = (SUN == 3) ? 3 : 1;
+    Coord p = gid_to_coords(g, gindex);
+    Coord pmu = nb_plus<MU>(g, p);
+    PlaneSites s0 = plane_sites<MU, PlaneOrder<MU>::n0>(g, p, pmu);
+    prefetch_link<R, MU, NPL>(table, g, gindex);
+    plane_prefetch<R, MU, PlaneOrder<MU>::n0, NPL>(table, g, gindex, s0);
 }
 
 // left-multiply rows (a,b) of M by the SU(2) element d (4-vector): rows' = [[u1,u2],[-conj u2, conj u1]] rows
@@ -434,10 +495,11 @@ __device__ __forceinline__ Twist<R> make_twist(const R* params) {
 }
 
 template <int SUN, typename R, int MU, bool TBC, class Prn>
-__global__ void __launch_bounds__(kUpdateThreads)
+__global__ void __launch_bounds__(kUpdateThreads, Prn::kMinBlocks)
 update_kernel(R* __restrict__ table, const R* __restrict__ params, const __grid_constant__ Geom g, int odd, typename Prn::Args pargs) {
     uint32_t GID = blockIdx.x * blockDim.x + threadIdx.x;
     if (GID >= g.nthreads) return;
+    GID = remap_gid(g, GID);
     const R beta = params[0];
     const Twist<R> tw = make_twist<SUN, R, TBC>(params);
     uint32_t gindex = parity_gid(g, GID, odd != 0);
@@ -446,11 +508,35 @@ update_kernel(R* __restrict__ table, const R* __restrict__ params, const __grid_
     else          update_site_su2<R, MU, TBC, Prn>(table, g, beta, tw, gindex, prn);
     prn.finish();
 }
+template <int SUN, typename R, int MU, bool TBC, int NSKIP>
+__global__ void __launch_bounds__(kUpdateThreads, 3)
+update_kernel_rlx(R* __restrict__ table, const R* __restrict__ params, const __grid_constant__ Geom g, int odd,
+                  uint32_t* __restrict__ rtable, uint32_t instances, uint32_t samples, uint32_t keep) {
+    extern __shared__ float4 prn_smem[];
+    uint32_t GID = blockIdx.x * blockDim.x + threadIdx.x;
+    if (GID >= g.nthreads) return;
+    GID = remap_gid(g, GID);
+    prefetch_site_head<SUN, R, MU>(table, g, parity_gid(g, GID, odd != 0));
+    {   // phase 1: the pass's whole RANLUX work
+        Ranlux r;
+        ranlux_load(r, rtable, instances, GID);
+        r.template run_pass<NSKIP>(prn_smem + threadIdx.x, kUpdateThreads, keep, samples);
+        ranlux_store(r, rtable, instances, GID);
+    }
+    // phase 2: the link update
+    const R beta = params[0];
+    const Twist<R> tw = make_twist<SUN, R, TBC>(params);
+    uint32_t gindex = parity_gid(g, GID, odd != 0);
+    PrnSmem prn(prn_smem + threadIdx.x, kUpdateThreads);
+    if (SUN == 3) update_site_su3<R, MU, TBC, PrnSmem>(table, g, beta, tw, gindex, prn);
+    else          update_site_su2<R, MU, TBC, PrnSmem>(table, g, beta, tw, gindex, prn);
+}
 template <int SUN, typename R, int MU>
 __global__ void __launch_bounds__(kUpdateThreads)
 overrelax_kernel(R* __restrict__ table, const __grid_constant__ Geom g, int odd) {
     uint32_t GID = blockIdx.x * blockDim.x + threadIdx.x;
     if (GID >= g.nthreads) return;
+    GID = remap_gid(g, GID);
     uint32_t gindex = parity_gid(g, GID, odd != 0);
     if (SUN == 3) overrelax_site_su3<R, MU>(table, g, gindex);
     else          overrelax_site_su2<R, MU>(table, g, gindex);

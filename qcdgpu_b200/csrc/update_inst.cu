@@ -23,12 +23,35 @@ static cudaError_t launch_one(const UpdateArgs& a, typename Prn::Args pa, cudaSt
         static_cast<RealT*>(a.table), static_cast<const RealT*>(a.params), a.geom, a.odd, pa);
     return cudaGetLastError();
 }
+// two-phase RANLUX kernel (generator phase -> shared memory -> physics phase)
+template <bool TBC>
+static cudaError_t launch_rlx(const UpdateArgs& a, cudaStream_t st) {
+    uint32_t keep = 3u * (a.geom.nhit + 1u) * a.geom.nhitpar;
+    if (keep > a.prn_samples) keep = a.prn_samples;
+    size_t smem = size_t(keep) * kUpdateThreads * sizeof(float4);
+    if (smem > 200 * 1024) {   // does not fit: state-in-registers variant
+        PrnRanlux<223>::Args pa = { a.prn_table, a.prn_instances, a.prn_samples };
+        return launch_one<TBC, PrnRanlux<223>>(a, pa, st);
+    }
+    auto kern = update_kernel_rlx<INST_SUN, RealT, INST_MU, TBC, 223>;
+    static size_t configured = 0;
+    if (smem > configured) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        configured = smem;
+    }
+    dim3 block(kUpdateThreads), grid((a.geom.nthreads + kUpdateThreads - 1) / kUpdateThreads);
+    if (grid.x == 0) return cudaSuccess;
+    kern<<<grid, block, smem, st>>>(static_cast<RealT*>(a.table), static_cast<const RealT*>(a.params), a.geom, a.odd,
+                                    a.prn_table, a.prn_instances, a.prn_samples, keep);
+    return cudaGetLastError();
+}
 template <bool TBC>
 static cudaError_t launch_tbc(const UpdateArgs& a, cudaStream_t st) {
     switch (a.prn_kind) {
         case PRN_BUFFERED: { PrnBuffered::Args pa = { static_cast<const float4*>(a.prns) }; return launch_one<TBC, PrnBuffered>(a, pa, st); }
         case PRN_GID:      { PrnGid::Args pa = { 0 }; return launch_one<TBC, PrnGid>(a, pa, st); }
-        case PRN_RANLUX3:  { PrnRanlux<223>::Args pa = { a.prn_table, a.prn_instances, a.prn_samples }; return launch_one<TBC, PrnRanlux<223>>(a, pa, st); }
+        case PRN_RANLUX3:  return launch_rlx<TBC>(a, st);
         case PRN_XOR128:   { PrnXor128::Args pa = { a.prn_table, a.prn_instances, a.prn_samples }; return launch_one<TBC, PrnXor128>(a, pa, st); }
         case PRN_PM:       { PrnPM::Args pa = { a.prn_table, a.prn_instances, a.prn_samples }; return launch_one<TBC, PrnPM>(a, pa, st); }
         case PRN_MRG32K3A: { PrnMrg::Args pa = { a.prn_table, a.prn_instances, a.prn_samples }; return launch_one<TBC, PrnMrg>(a, pa, st); }
@@ -56,11 +79,16 @@ template <bool TBC, class Prn> static int regs_of() {
     if (cudaFuncGetAttributes(&at, update_kernel<INST_SUN, RealT, INST_MU, TBC, Prn>) != cudaSuccess) return -1;
     return at.numRegs;
 }
+template <bool TBC> static int regs_of_rlx() {
+    cudaFuncAttributes at;
+    if (cudaFuncGetAttributes(&at, update_kernel_rlx<INST_SUN, RealT, INST_MU, TBC, 223>) != cudaSuccess) return -1;
+    return at.numRegs;
+}
 int REGS_NAME(int tbc, int prn_kind) {
     switch (prn_kind) {
         case PRN_BUFFERED: return tbc ? regs_of<true, PrnBuffered>() : regs_of<false, PrnBuffered>();
         case PRN_GID:      return tbc ? regs_of<true, PrnGid>() : regs_of<false, PrnGid>();
-        case PRN_RANLUX3:  return tbc ? regs_of<true, PrnRanlux<223>>() : regs_of<false, PrnRanlux<223>>();
+        case PRN_RANLUX3:  return tbc ? regs_of_rlx<true>() : regs_of_rlx<false>();
         case PRN_XOR128:   return tbc ? regs_of<true, PrnXor128>() : regs_of<false, PrnXor128>();
         case PRN_PM:       return tbc ? regs_of<true, PrnPM>() : regs_of<false, PrnPM>();
         case PRN_MRG32K3A: return tbc ? regs_of<true, PrnMrg>() : regs_of<false, PrnMrg>();
