@@ -114,6 +114,13 @@ void  qgpu_set_fused_prng(qgpu* h, int on);
  * 8 once three x-slices of links exceed 48 MB; env QCDGPU_TILE_X overrides the automatic choice).  Results do
  * not depend on it. */
 void  qgpu_set_tile_x(qgpu* h, int tile);
+/* Run on a caller-owned cudaStream_t instead of the handle's own stream (e.g. a torch stream, so that NCCL
+ * send/recv of halo buffers issued through torch.distributed is ordered with the kernels). */
+int   qgpu_set_stream(qgpu* h, void* cuda_stream);
+/* Restrict an update kernel to x-slices [x_first, x_first + x_count) of the updated region (x_count < 0: all).
+ * Used by the BigLattice path to update the two boundary slices first and the interior while halos travel.
+ * A restricted launch always reads the PRN buffer (the generators advance once per pass, for all sites). */
+int   qgpu_kernel_set_x_range(qgpu* h, int kernel_id, int x_first, int x_count);
 /* raw device pointer of a buffer (halo exchange, interop) and raw stream handle (cudaStream_t) */
 void* qgpu_buffer_device_ptr(qgpu* h, int buffer_id);
 void* qgpu_stream(qgpu* h);

@@ -1,0 +1,390 @@
+"""BigLattice: 1-D slab decomposition along x over several GPUs with NVLink halo exchange.
+
+Mirror of the reference's BIGLAT build (SubLattice, model::UpdateEdges, lattice_simulate,
+SU(N)/suncl/suncl.cpp:278-287, 2388-2561, 4005-4062, 4804-5210): the lattice is cut along x = N1, the
+slowest storage index (what north_star calls the "t-split"); every part stores
+Nx real slices plus one halo slice on each side (N1 = Nx + 2, kernels built with -D BIGLAT -D FULL_SITES
+-D LEFT_SITES), parts form a ring, and after each of the 8 (parity, direction) passes the direction-mu
+links of the two boundary slices go to the neighbours' halos.  Each part has its own PRNG and RANDSERIES
+(suncl.cpp:377-386), so a partitioned run agrees with the single-device run statistically, and exactly
+for the PRNG-free INTS=2 start.
+
+What is new here:
+  * one process per GPU (torch.distributed / NCCL over NVLink) or several parts in one process (P2P
+    `qgpu_halo_copy` kernels reading peer memory, also usable with all parts on one device, like the
+    reference's init_2.dat);
+  * the reference stages halos through mapped host memory after the whole pass (clEnqueueMapBuffer +
+    memcpy, fully serialised); here the two boundary slices are updated first, their links start
+    travelling (NCCL send/recv on its own stream, or a P2P copy kernel), and the interior slices are
+    updated meanwhile;
+  * observables are summed over parts with one small all-reduce.
+"""
+from __future__ import annotations
+
+import json
+import os
+import time
+
+import numpy as np
+
+from .capi import GPU, QcdGpuError
+from .model import DIRS, Model, model_start_hot
+
+
+def split_slabs(L1: int, nparts: int) -> list[int]:
+    """Nx per part: as equal as possible, larger parts first (the reference takes N1 = {a, b, ...} from init.dat)."""
+    if nparts < 1 or L1 < nparts:
+        raise ValueError(f"cannot cut {L1} x-slices into {nparts} parts")
+    base, rem = divmod(L1, nparts)
+    nx = [base + (1 if k < rem else 0) for k in range(nparts)]
+    return nx
+
+
+def parity_consistent(nx: list[int]) -> bool:
+    """The kernels classify even/odd sites from the part-local x (sun_common.cl:383-417): the checkerboards of
+    neighbouring parts only line up when every part owns an even number of slices."""
+    return all(n % 2 == 0 for n in nx)
+
+
+def ring_neighbours(k: int, nparts: int) -> tuple[int, int]:
+    """(left, right) part indices; k_next = (k + 1) % Nparts (suncl.cpp:4027)."""
+    return (k - 1) % nparts, (k + 1) % nparts
+
+
+def exchange_packed(dist, send_first, send_last, recv_left, recv_right, left: int, right: int):
+    """Ring exchange of packed boundary slices between processes (model::UpdateEdges across devices):
+    my LAST real slice goes to the right neighbour's left halo, my FIRST real slice to the left neighbour's
+    right halo.  Returns the work handles.  Send/recv order matters when left == right (two parts): messages
+    between one pair of ranks match in posting order, so "to the right" is posted before "to the left" and
+    "from the left" before "from the right"."""
+    ops = [dist.P2POp(dist.isend, send_last, right), dist.P2POp(dist.isend, send_first, left),
+           dist.P2POp(dist.irecv, recv_left, left), dist.P2POp(dist.irecv, recv_right, right)]
+    return dist.batch_isend_irecv(ops)
+
+
+class SubLattice(Model):
+    """One part: a Model built with -D BIGLAT, owning Nx real x-slices (SubLattice, suncl.h:470-700)."""
+
+    def __init__(self, k: int, nparts: int, full_size, Nx_all: list[int], device: int = 0):
+        super().__init__()
+        self.k, self.nparts = k, nparts
+        self.lattice_full_size = list(full_size)
+        self.biglat = True
+        self.Nx = Nx_all[k]
+        self.left_x = sum(Nx_all[:k])
+        self.desired_device = device
+        self.PL_level = 0
+
+    # x index (in the stored part, halos included) of the slices involved in the exchange
+    @property
+    def x_first_real(self): return 1
+    @property
+    def x_last_real(self): return self.Nx
+    @property
+    def x_left_halo(self): return 0
+    @property
+    def x_right_halo(self): return self.Nx + 1
+
+
+class BigLattice:
+    """The driver: parts of this process + transport to the ring neighbours."""
+
+    def __init__(self, full_size, nparts: int, local_parts: list[int] | None = None, devices: list[int] | None = None,
+                 dist=None, configure=None, randseries: list[int] | None = None):
+        """`dist`: a torch.distributed module with an initialised process group when parts live in other
+        processes (then this process owns exactly part `dist.get_rank()`), else None (all parts local)."""
+        self.full_size = list(full_size)
+        self.nparts = nparts
+        self.Nx_all = split_slabs(full_size[0], nparts)
+        if nparts > 1 and not parity_consistent(self.Nx_all):
+            raise QcdGpuError(f"x-slabs {self.Nx_all}: every part needs an even number of x-slices for a consistent checkerboard")
+        self.dist = dist
+        if dist is not None:
+            local_parts = [dist.get_rank()]
+        elif local_parts is None:
+            local_parts = list(range(nparts))
+        self.local = local_parts
+        devices = devices or [0] * len(local_parts)
+        self.parts: dict[int, SubLattice] = {}
+        for k, dev in zip(local_parts, devices):
+            p = SubLattice(k, nparts, full_size, self.Nx_all, dev)
+            p.PRNG0.PRNG_randseries = (randseries[k] if randseries else 54 + 1000 * k)   # per-part series (init_2.dat)
+            if configure:
+                configure(p)
+            self.parts[k] = p
+        self.overlap = True
+        self._torch = None
+        self._stream = None
+        self._pack = {}
+        self.halo_bytes_per_pass = 0
+
+    # ------------------------------------------------------------------ set-up
+    def lattice_init(self):
+        for p in self.parts.values():
+            p.lattice_init()
+        if self.dist is not None:
+            import torch
+            self._torch = torch
+            p = self.parts[self.local[0]]
+            torch.cuda.set_device(p.desired_device)
+            self._stream = torch.cuda.Stream(device=p.desired_device)
+            p.GPU0.set_stream(self._stream.cuda_stream)      # kernels and NCCL ops are ordered through this stream
+
+    def lattice_start(self):
+        for p in self.parts.values():
+            p.lattice_create_buffers()
+            p.lattice_make_programs()
+            if p.ints == model_start_hot:
+                p.PRNG0.produce()
+                for i, k in enumerate(p.sun_init_hot_id):
+                    p.GPU0.kernel_run(k)
+                    if i < 3:
+                        p.PRNG0.produce()
+            else:
+                p.GPU0.kernel_run(p.sun_init_id)
+        self.finish_edges(self.update_edges(-1))          # a hot start fills halos with unrelated links: take the neighbours' real ones
+        self.measure()
+        for p in self.parts.values():
+            p.ITER_counter += 1
+
+    # ------------------------------------------------------------------ halo exchange (model::UpdateEdges)
+    def _packed(self, p: SubLattice, name: str, nbytes: int):
+        t = self._pack.get((p.k, name))
+        if t is None or t.numel() < nbytes:
+            t = self._torch.empty(nbytes, dtype=self._torch.uint8, device=f"cuda:{p.desired_device}")
+            self._pack[(p.k, name)] = t
+        return t
+
+    def update_edges(self, d: int):
+        """Direction-d planes (all planes if d < 0) of every part's two boundary slices -> neighbours' halos."""
+        if self.nparts == 1 and self.dist is None:
+            p = self.parts[0]
+            # periodic in x through the part's own halos
+            p.GPU0.halo_copy(p.program_update, p.lattice_table, p.x_left_halo, p.GPU0, p.program_update, p.lattice_table, p.x_last_real, d)
+            p.GPU0.halo_copy(p.program_update, p.lattice_table, p.x_right_halo, p.GPU0, p.program_update, p.lattice_table, p.x_first_real, d)
+            self.halo_bytes_per_pass = 2 * p.GPU0.halo_bytes(p.program_update, d)
+            return None
+        if self.dist is None:
+            for k, p in self.parts.items():
+                left, right = ring_neighbours(k, self.nparts)
+                L, R = self.parts[left], self.parts[right]
+                # my left halo <- left neighbour's last real slice; my right halo <- right neighbour's first real slice
+                p.GPU0.halo_copy(p.program_update, p.lattice_table, p.x_left_halo, L.GPU0, L.program_update, L.lattice_table, L.x_last_real, d)
+                p.GPU0.halo_copy(p.program_update, p.lattice_table, p.x_right_halo, R.GPU0, R.program_update, R.lattice_table, R.x_first_real, d)
+            self.halo_bytes_per_pass = 2 * p.GPU0.halo_bytes(p.program_update, d)
+            return None
+        # one part per process: pack -> NCCL send/recv -> unpack, everything ordered on self._stream
+        torch, dist = self._torch, self.dist
+        p = self.parts[self.local[0]]
+        left, right = ring_neighbours(p.k, self.nparts)
+        nb = p.GPU0.halo_bytes(p.program_update, d)
+        self.halo_bytes_per_pass = 2 * nb
+        with torch.cuda.stream(self._stream):
+            s_first, s_last = self._packed(p, "s_first", nb), self._packed(p, "s_last", nb)
+            r_left, r_right = self._packed(p, "r_left", nb), self._packed(p, "r_right", nb)
+            p.GPU0.halo_pack(p.program_update, p.lattice_table, p.x_first_real, d, s_first.data_ptr())
+            p.GPU0.halo_pack(p.program_update, p.lattice_table, p.x_last_real, d, s_last.data_ptr())
+            works = exchange_packed(dist, s_first[:nb], s_last[:nb], r_left[:nb], r_right[:nb], left, right)
+        return (works, r_left, r_right, d)
+
+    def finish_edges(self, pending):
+        if pending is None:
+            return
+        works, r_left, r_right, d = pending
+        p = self.parts[self.local[0]]
+        with self._torch.cuda.stream(self._stream):
+            for w in works:
+                w.wait()                 # stream-level wait: the unpack kernels run after the NCCL transfer
+            p.GPU0.halo_unpack(p.program_update, p.lattice_table, p.x_left_halo, d, r_left.data_ptr())
+            p.GPU0.halo_unpack(p.program_update, p.lattice_table, p.x_right_halo, d, r_right.data_ptr())
+
+    # ------------------------------------------------------------------ sweeps (lattice_simulate BIGLAT, suncl.cpp:4804-5210)
+    def _update_pass(self, par: str, d: str):
+        di = DIRS.index(d)
+        split = self.overlap and all(p.Nx >= 3 for p in self.parts.values())
+        for p in self.parts.values():
+            p.PRNG0.produce()
+            kid = p.sun_update_id[(par, d)]
+            if split:
+                # boundary slices first so that their links can travel while the interior is updated
+                p.GPU0.kernel_set_x_range(kid, 0, 1)
+                p.GPU0.kernel_run(kid)
+                p.GPU0.kernel_set_x_range(kid, p.Nx - 1, 1)
+                p.GPU0.kernel_run(kid)
+            else:
+                p.GPU0.kernel_set_x_range(kid, 0, -1)
+                p.GPU0.kernel_run(kid)
+        if self.dist is not None:
+            pending = self.update_edges(di)
+            if split:
+                for p in self.parts.values():
+                    kid = p.sun_update_id[(par, d)]
+                    p.GPU0.kernel_set_x_range(kid, 1, p.Nx - 2)
+                    p.GPU0.kernel_run(kid)
+            self.finish_edges(pending)
+        else:
+            if split:
+                for p in self.parts.values():
+                    kid = p.sun_update_id[(par, d)]
+                    p.GPU0.kernel_set_x_range(kid, 1, p.Nx - 2)
+                    p.GPU0.kernel_run(kid)
+            self.update_edges(di)
+
+    def lattice_sweep(self):
+        for par in ("odd", "even"):
+            for d in DIRS:
+                self._update_pass(par, d)
+        if self.dist is None and len(self.parts) > 1:
+            for p in self.parts.values():      # halo copies read neighbours' tables on the readers' streams
+                p.GPU0.synchronize()
+        for p in self.parts.values():
+            if not p.turnoff_gramschmidt:
+                p.GPU0.kernel_run(p.sun_GramSchmidt_id)
+
+    # ------------------------------------------------------------------ measurements
+    def measure(self):
+        for p in self.parts.values():
+            p._measure()
+
+    def synchronize(self):
+        for p in self.parts.values():
+            p.GPU0.synchronize()
+        if self._stream is not None:
+            self._stream.synchronize()
+
+    def lattice_simulate(self):
+        self.lattice_start()
+        p0 = next(iter(self.parts.values()))
+        for _ in range(p0.NAV):
+            self.lattice_sweep()
+        for _ in range(1, p0.ITER):
+            for _ in range(p0.NITER):
+                self.lattice_sweep()
+            self.measure()
+            for p in self.parts.values():
+                p.ITER_counter += 1
+        self.synchronize()
+
+    def lattice_analysis(self) -> dict:
+        """Per-part sums -> global observables (lattice_analysis_SLtoL, suncl.cpp:909-959): the parts' raw sums
+        add up; denominators are those of the full lattice."""
+        p0 = next(iter(self.parts.values()))
+        ITER = p0.ITER
+        sums = {}
+        for name, buf in (("S", "lattice_energies"), ("Plq", "lattice_energies_plq")):
+            acc = np.zeros((ITER, 2))
+            for p in self.parts.values():
+                acc += p.GPU0.buffer_map(getattr(p, buf), np.float64).reshape(-1, 2)[:ITER]
+            sums[name] = acc
+        if self.dist is not None:
+            torch = self._torch
+            flat = torch.tensor(np.concatenate([sums["S"].ravel(), sums["Plq"].ravel()]), device=f"cuda:{p0.desired_device}")
+            self.dist.all_reduce(flat)
+            flat = flat.cpu().numpy()
+            sums["S"], sums["Plq"] = flat[: 2 * ITER].reshape(ITER, 2), flat[2 * ITER:].reshape(ITER, 2)
+        den = float(np.prod(self.full_size) * 3)
+        A = {}
+        for name in ("S", "Plq"):
+            A[f"{name}_spat"] = Model._series(sums[name][:, 0].copy(), den)
+            A[f"{name}_temp"] = Model._series(sums[name][:, 1].copy(), den)
+            A[f"{name}_total"] = Model._joint(A[f"{name}_spat"], A[f"{name}_temp"])
+        self.Analysis = A
+        return A
+
+    def close(self):
+        for p in self.parts.values():
+            p.close()
+
+
+# ---------------------------------------------------------------------------------------------- bench (N > 1)
+def bench_main(args, workload):
+    """bench.py --gpus N under torchrun: weak scaling, one 64-slice slab of SU(3) fp64 per GPU."""
+    import torch
+    import torch.distributed as dist
+    from bench import ClockSampler, measured_peaks
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", str(rank)))
+    torch.cuda.set_device(local_rank)
+    if not dist.is_initialized():
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
+    dims = tuple(int(x) for x in args.dims.split("x")) if args.dims else workload["dims"]
+    full = (dims[0] * world, dims[1], dims[2], dims[3])
+
+    def configure(p):
+        p.lattice_group, p.precision, p.ints = workload["group"], workload["precision"], workload["ints"]
+        p.BETA, p.NHIT = workload["beta"], workload["nhit"]
+        p.PRNG0.PRNG_generator = workload["prng"]
+        p.fused_prng = not args.buffered
+        p.ITER = 4096
+        p.desired_device = local_rank
+
+    B = BigLattice(full, world, dist=dist, configure=configure, devices=[local_rank])
+    B.lattice_init()
+    B.lattice_start()
+    p = B.parts[rank]
+    g = p.GPU0
+    for _ in range(args.warmup):
+        B.lattice_sweep()
+    B.synchronize()
+    dist.barrier()
+    torch.cuda.synchronize()
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()
+    l0 = g.launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with torch.cuda.stream(B._stream):
+        ev0.record()
+        for _ in range(args.steps):
+            B.lattice_sweep()
+        ev1.record()
+    ev1.synchronize()
+    dist.barrier()
+    torch.cuda.synchronize()
+    ms = torch.tensor([ev0.elapsed_time(ev1)], device=f"cuda:{local_rank}")
+    dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms = float(ms.item())
+    launches = g.launch_count() - l0
+    V_total = int(np.prod(full))
+    links = 4 * V_total
+    value = links * args.steps / (ms * 1e-3)
+    # e2e through the host-facing loop: per step parameter upload, sweep, measurement, all-reduced result read back
+    t0 = time.perf_counter()
+    params = g.buffer_map(p.lattice_parameters, np.uint8)
+    for _ in range(args.steps):
+        g._chk(g.L.qgpu_buffer_unmap(g.h, p.lattice_parameters, params.ctypes.data), "unmap")
+        B.lattice_sweep()
+        g.kernel_run(p.sun_measurement_plq_id)
+        g.kernel_init_constant_reset(p.sun_measurement_plq_reduce_id, 1, p.argument_plq_index)
+        g.kernel_run(p.sun_measurement_plq_reduce_id)
+        e = g.buffer_map(p.lattice_energies_plq, np.float64)[2:4].copy()
+        tt = torch.tensor(e, device=f"cuda:{local_rank}")
+        dist.all_reduce(tt)
+        plq = tt.cpu().numpy()
+    dist.barrier()
+    e2e_s = torch.tensor([time.perf_counter() - t0], device=f"cuda:{local_rank}")
+    dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
+    e2e = links * args.steps / float(e2e_s.item())
+    ck = clocks.stop() if rank == 0 else None
+    peak, peak_kind = measured_peaks()
+    if rank == 0:
+        bytes_per_s = value * 864.0 / 1e9 / world
+        out = {
+            "metric": "SU(3) link updates/sec", "value": value, "unit": "link-updates/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"SU(3) {'x'.join(map(str, full))} fp64 heat-bath sweeps, BigLattice x-slab split over {world} GPUs "
+                                   f"({dims[0]} slices per GPU), halo exchange after each of the 8 passes (NCCL send/recv, overlapped with the "
+                                   f"interior update), beta=6.0, NHIT=10, RANLUX3, cold start",
+                       "l2_policy": "inputs_larger_than_L2", "sweeps_per_s": args.steps / (ms * 1e-3),
+                       "halo_bytes_per_pass_per_gpu": 2 * B.halo_bytes_per_pass, "plaquette_after_run": float(plq.sum() / (6.0 * V_total))},
+            "roofline": {"bound": "hbm", "achieved": bytes_per_s, "peak": peak, "unit": "GB/s", "frac": bytes_per_s / peak,
+                         "traffic": None, "peak_source": peak_kind, "note": "per GPU, whole sweep (update + halo + reunitarisation)"},
+            "e2e": {"value": e2e, "unit": "link-updates/s", "h2d_bytes_per_step": int(params.size) * world, "d2h_bytes_per_step": 16 * world},
+            "gpu_launches": int(launches), "clocks": ck,
+        }
+        print(json.dumps(out))
+    B.close()
+    dist.destroy_process_group()

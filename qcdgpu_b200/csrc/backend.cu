@@ -61,6 +61,7 @@ struct Kernel {
     size_t global[3] = { 1, 1, 1 };
     size_t local0 = 0;
     bool local_given = false;
+    int x_first = 0, x_count = -1;   // update kernels: x-range of the launch inside the updated region (-1 = all)
     std::vector<Arg> args;
     // profiling (GPU_debug.profiling)
     double t_sum = 0, t_sq = 0; int starts = 0;
@@ -74,6 +75,7 @@ struct Buffer {
     void* shadow = nullptr;          // host memory returned by buffer_map
     size_t map_off = 0, map_len = 0;
     int pending_produce = 0;         // kernel id of a deferred PRN producer writing this buffer
+    bool pending_partly_fused = false;   // x-range launches of the current pass already ran that generator in registers
     bool alive = false;
 };
 
@@ -83,6 +85,7 @@ struct qgpu {
     int device = 0;
     bool initialized = false;
     cudaStream_t stream = nullptr;
+    bool own_stream = false;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, evp0 = nullptr, evp1 = nullptr, ev_halo = nullptr;
     unsigned limit_wg = 0;
     size_t max_memory_width = 0;
@@ -168,6 +171,7 @@ Geom make_geom(const ProgramCfg& c, int tile_override = -1) {
     g.prngstep = c.prngstep ? c.prngstep : g.sites / 2;                     // model.cl:126-128
     g.left_sites = c.left_sites; g.full_sites = c.full_sites;
     g.nhit = (uint32_t)c.nhit; g.nhitpar = (uint32_t)c.nhitpar;
+    g.upd_x0 = 0; g.upd_nx = c.biglat ? c.n1 - 2 : c.n1;
     if (c.biglat && g.n234) { g.tw_lo = c.left_sites / g.n234; g.tw_hi = c.full_sites / g.n234; }
     // L2 tiling (lattice.cuh remap_gid): worthwhile once three x-slices of all links no longer fit the L2
     {
@@ -180,6 +184,7 @@ Geom make_geom(const ProgramCfg& c, int tile_override = -1) {
         else if (env_tile >= 0) tile = (uint32_t)env_tile;
         else if (3 * slice_bytes > (size_t)48 << 20) tile = 8;
         if (tile >= nx || (c.n2 & 1)) tile = 0;
+        (void)nx;
         g.tile_x = tile;
     }
     return g;
@@ -229,6 +234,8 @@ int flush_pending(qgpu* h, int bid) {
     if (!valid_buf(h, bid)) return 0;
     int kid = h->buffers[bid].pending_produce;
     if (!kid) return 0;
+    if (h->buffers[bid].pending_partly_fused)
+        return fail(h, "PRN buffer %d is needed in memory, but x-range launches of this pass already consumed its generator in registers", bid);
     h->buffers[bid].pending_produce = 0;
     Kernel& k = h->kernels[kid];
     int samples = 0;
@@ -270,6 +277,14 @@ int launch_kernel(qgpu* h, int kid) {
             a.table = buf_ptr(h, k, 0); a.params = buf_ptr(h, k, 1);
             if (!a.table || !a.params) return fail(h, "kernel %s: arguments (lattice_table, lattice_parameters) not set", k.name.c_str());
             a.geom = make_geom(c, h->tile_x); a.odd = k.odd; a.tbc = c.tbc ? 1 : 0;
+            if (k.x_count >= 0) {
+                if ((uint32_t)(k.x_first + k.x_count) > a.geom.upd_nx) return fail(h, "kernel %s: x-range [%d,+%d) outside the %u updated slices", k.name.c_str(), k.x_first, k.x_count, a.geom.upd_nx);
+                a.geom.upd_x0 = (uint32_t)k.x_first; a.geom.upd_nx = (uint32_t)k.x_count;
+                a.geom.nthreads = a.geom.upd_nx * (a.geom.n234 / 2);
+                if (a.geom.tile_x >= a.geom.upd_nx) a.geom.tile_x = 0;
+                if (a.geom.nthreads == 0) break;
+            }
+            const uint32_t full_threads = (c.biglat ? c.n1 - 2 : c.n1) * (a.geom.n234 / 2);
             UpdateLaunchFn fn = get_update_launcher(c.sun, prec, k.dir);
             if (!fn) return fail(h, "kernel %s: no CUDA instantiation for SUN=%d PRECISION=%d", k.name.c_str(), c.sun, c.precision);
             if (k.kind == K_OVERRELAX) { a.overrelax = 1; CUDA_OK(h, fn(a, st)); break; }
@@ -282,19 +297,20 @@ int launch_kernel(qgpu* h, int kid) {
             if (pbuf.pending_produce) {
                 Kernel& pk = h->kernels[pbuf.pending_produce];
                 int samples = 0; arg_int(pk, 2, &samples);
-                bool fusable = h->fused && (uint32_t)pk.global[0] == a.geom.prngstep && a.geom.nthreads <= a.geom.prngstep &&
+                bool fusable = h->fused && (uint32_t)pk.global[0] == a.geom.prngstep && full_threads <= a.geom.prngstep &&
                                (pk.prn_kind == PRN_RANLUX3 || pk.prn_kind == PRN_XOR128 || pk.prn_kind == PRN_PM || pk.prn_kind == PRN_MRG32K3A) &&
                                (uint32_t)samples >= 3u * (uint32_t)(c.nhit + 1) * (uint32_t)c.nhitpar;
                 if (fusable) {
                     a.prn_kind = pk.prn_kind; a.prn_table = (uint32_t*)buf_ptr(h, pk, 0);
                     a.prn_instances = (uint32_t)pk.global[0]; a.prn_samples = (uint32_t)samples;
-                    pbuf.pending_produce = 0;
+                    if (k.x_count < 0) { pbuf.pending_produce = 0; pbuf.pending_partly_fused = false; }
+                    else pbuf.pending_partly_fused = true;       // the other x-ranges of this pass follow
                     fused = true;
                 } else if (flush_pending(h, pb) < 0) return -1;
             }
             if (!fused) {
                 a.prn_kind = PRN_BUFFERED; a.prns = pbuf.dptr;
-                size_t need = (size_t)a.geom.prngstep * (3u * (c.nhit + 1) * c.nhitpar - 1) + a.geom.nthreads;
+                size_t need = (size_t)a.geom.prngstep * (3u * (c.nhit + 1) * c.nhitpar - 1) + full_threads;
                 if (pbuf.bytes < need * 16) return fail(h, "kernel %s: PRN buffer holds %zu vec4, the pass may read %zu", k.name.c_str(), pbuf.bytes / 16, need);
             }
             CUDA_OK(h, fn(a, st));
@@ -376,6 +392,7 @@ int launch_kernel(qgpu* h, int kid) {
             if (!buf_ptr(h, k, 0) || !valid_buf(h, pb) || !arg_int(k, 2, &samples)) return fail(h, "kernel %s: arguments (seed table, prns, samples) not set", k.name.c_str());
             if (c.prng_precision == 2) return fail(h, "kernel %s: PRNG_PRECISION=2 (double PRNs) is not implemented", k.name.c_str());
             if (h->buffers[pb].bytes < (size_t)k.global[0] * samples * 16) return fail(h, "kernel %s: PRN buffer too small", k.name.c_str());
+            if (h->buffers[pb].pending_partly_fused) { h->buffers[pb].pending_produce = 0; h->buffers[pb].pending_partly_fused = false; }   // previous pass: consumed by its x-range launches
             if (flush_pending(h, pb) < 0) return -1;   // an unconsumed earlier produce() must still advance the streams
             if (h->fused) { h->buffers[pb].pending_produce = kid; return 0; }   // decided at the consumer
             CUDA_OK(h, launch_prn_produce(k.prn_kind, (uint32_t*)buf_ptr(h, k, 0), h->buffers[pb].dptr, (uint32_t)k.global[0], (uint32_t)samples, st));
@@ -415,6 +432,19 @@ const char* qgpu_last_error(qgpu* h) { return h->last_error.c_str(); }
 void qgpu_set_async(qgpu* h, int on) { h->async = on != 0; }
 void qgpu_set_fused_prng(qgpu* h, int on) { h->fused = on != 0; }
 void qgpu_set_tile_x(qgpu* h, int tile) { h->tile_x = tile; }
+int qgpu_set_stream(qgpu* h, void* stream) {
+    if (!h->initialized) return fail(h, "set_stream before device_initialize");
+    if (h->own_stream) { cudaStreamSynchronize(h->stream); cudaStreamDestroy(h->stream); h->own_stream = false; }
+    h->stream = (cudaStream_t)stream;
+    return 0;
+}
+int qgpu_kernel_set_x_range(qgpu* h, int kid, int x_first, int x_count) {
+    if (!valid_kernel(h, kid)) return fail(h, "bad kernel id %d", kid);
+    Kernel& k = h->kernels[kid];
+    if (k.kind != K_UPDATE && k.kind != K_OVERRELAX) return fail(h, "kernel %s has no x-range", k.name.c_str());
+    k.x_first = x_first; k.x_count = x_count;
+    return 0;
+}
 uint64_t qgpu_launch_count(qgpu* h) { return h->launches; }
 void* qgpu_stream(qgpu* h) { return (void*)h->stream; }
 
@@ -436,6 +466,7 @@ int qgpu_device_initialize(qgpu* h) {
     CUDA_OK(h, cudaGetDeviceProperties(&p, h->device));
     if (p.major < 10) return fail(h, "device %s is sm_%d%d; this library contains only sm_100a code", p.name, p.major, p.minor);
     CUDA_OK(h, cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    h->own_stream = true;
     CUDA_OK(h, cudaEventCreate(&h->ev0)); CUDA_OK(h, cudaEventCreate(&h->ev1));
     CUDA_OK(h, cudaEventCreate(&h->evp0)); CUDA_OK(h, cudaEventCreate(&h->evp1));
     CUDA_OK(h, cudaEventCreateWithFlags(&h->ev_halo, cudaEventDisableTiming));
@@ -466,8 +497,8 @@ int qgpu_device_finalize(qgpu* h, int error_code) {
         h->buffers[i] = Buffer();
     }
     cudaEventDestroy(h->ev0); cudaEventDestroy(h->ev1); cudaEventDestroy(h->evp0); cudaEventDestroy(h->evp1); cudaEventDestroy(h->ev_halo);
-    cudaStreamDestroy(h->stream);
-    h->stream = nullptr; h->initialized = false;
+    if (h->own_stream) cudaStreamDestroy(h->stream);
+    h->stream = nullptr; h->own_stream = false; h->initialized = false;
     return error_code;
 }
 int qgpu_get_device_info(qgpu* h, qgpu_device_info* out) {

@@ -32,6 +32,7 @@ struct Geom {
     uint32_t nhit, nhitpar;
     uint32_t tw_lo, tw_hi;        // BIGLAT twist test: x + left_sites/n234 == tw_lo || == tw_hi
     uint32_t tile_x;              // L2 tiling of the update passes: x-chunk width (0 = reference order)
+    uint32_t upd_x0, upd_nx;      // x-range of this launch inside the updated region (halo/interior split); nthreads = upd_nx*N4*N2/2*N3
 };
 
 struct Coord { uint32_t x, y, z, t; };
@@ -68,20 +69,19 @@ __device__ __forceinline__ uint32_t parity_gid(const Geom& g, uint32_t GID, bool
 // next one, so the window that must stay cached is (tile_x + 2) x 3 (y,z)-planes.  Which thread updates a site
 // changes, the site's GID (hence its PRNG instance / PRN slots) does not.
 __device__ __forceinline__ uint32_t remap_gid(const Geom& g, uint32_t k) {
-    if (g.tile_x == 0) return k;
     const uint32_t P = (g.n2 >> 1) * g.n3;                 // threads per (x,t) plane
-    const uint32_t nx = g.biglat ? g.n1 - 2 : g.n1;        // updated x-slices
+    if (g.tile_x == 0) return k + g.upd_x0 * g.n4 * P;     // reference order, shifted to the launch's x-range
     const uint32_t chunk = g.tile_x * g.n4 * P;
     const uint32_t xc = k / chunk;
     uint32_t r = k - xc * chunk;
     const uint32_t x0 = xc * g.tile_x;
-    const uint32_t w = min(g.tile_x, nx - x0);
+    const uint32_t w = min(g.tile_x, g.upd_nx - x0);
     const uint32_t wp = w * P;
     const uint32_t t = r / wp;
     r -= t * wp;
     const uint32_t xi = r / P;
     const uint32_t yz = r - xi * P;
-    return yz + P * (t + g.n4 * (x0 + xi));
+    return yz + P * (t + g.n4 * (g.upd_x0 + x0 + xi));
 }
 template <int DIR> __device__ __forceinline__ Coord nb_plus(const Geom& g, Coord c) {
     // sun_common.cl:455-483

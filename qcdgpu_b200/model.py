@@ -87,6 +87,10 @@ class Model:
         self.get_plaquettes_avr = True
         self.path = "./"
         self.fprefix = "su3-"
+        # BIGLAT part description (biglattice.py): this Model then owns Nx real x-slices plus one halo slice each side
+        self.biglat = False
+        self.Nx = 0                 # real x-slices of the part (SubLat[k].Nx, QCDGPU.cpp:117-118)
+        self.left_x = 0             # x-slices owned by the parts to the left
         # extensions
         self.fused_prng = False
         self.async_run = True
@@ -144,16 +148,23 @@ class Model:
             raise QcdGpuError("GROUP must be 2 or 3")
         if self.PL_level > 2:
             raise QcdGpuError("PL_LEVEL 3 (Polyakov-loop *_diff_* kernels) is outside the implemented hot path")
-        n = self.lattice_full_size
+        full = self.lattice_full_size
+        if self.biglat:
+            # suncl.cpp:2388-2446: the part is stored with N1 = Nx + 2 (one halo slice on each side)
+            n = [self.Nx + 2, full[1], full[2], full[3]]
+            real_n1 = self.Nx
+        else:
+            n = list(full)
+            real_n1 = full[0]
         self.lattice_domain_size = list(n)
         self.lattice_domain_n1 = n[0]
         self.lattice_domain_n2n3 = n[1] * n[2]
-        self.lattice_domain_exact_n1n2n3 = n[0] * n[1] * n[2]
+        self.lattice_domain_exact_n1n2n3 = real_n1 * n[1] * n[2]
         self.lattice_domain_n2n3n4 = n[1] * n[2] * n[3]
         self.lattice_domain_site = n[0] * n[1] * n[2] * n[3]
-        self.lattice_domain_exact_site = self.lattice_domain_site
-        self.lattice_full_site = self.lattice_domain_site
-        self.lattice_full_n1n2n3 = n[0] * n[1] * n[2]
+        self.lattice_domain_exact_site = real_n1 * n[1] * n[2] * n[3]
+        self.lattice_full_site = full[0] * full[1] * full[2] * full[3]
+        self.lattice_full_n1n2n3 = full[0] * full[1] * full[2]
         self.lattice_domain_link = self.lattice_nd * self.lattice_domain_site
         local_size_intel = g.GPU_limit_max_workgroup_size or 0
         workgroup_factor = local_size_intel if local_size_intel else 32
@@ -164,7 +175,7 @@ class Model:
         self.lattice_energies_size = al(self.ITER)
         self.lattice_energies_offset = self.lattice_energies_size
         self.lattice_table_row_size = al(self.lattice_domain_site)
-        self.lattice_table_row_size_half = al(self.lattice_domain_site // 2)
+        self.lattice_table_row_size_half = al(self.lattice_domain_exact_site // 2)
         self.lattice_table_exact_row_size = al(self.lattice_domain_exact_site)
         self.lattice_table_exact_row_size_half = al(self.lattice_domain_exact_site // 2)
         self.lattice_table_size = al(self.lattice_table_row_size * self.lattice_nd * ge // 4)
@@ -253,6 +264,9 @@ class Model:
         if not (self.PHI == 0.0 and self.OMEGA == 0.0):
             o += " -D TBC"
         o += f" -D ROWSIZE={self.lattice_table_row_size} -D PRECISION={self.precision}"
+        if self.biglat:   # suncl.cpp:2427-2441
+            n234 = n[1] * n[2] * n[3]
+            o += f" -D BIGLAT -D FULL_SITES={self.lattice_full_site} -D LEFT_SITES={self.left_x * n234}"
         return o
 
     def lattice_make_programs(self):

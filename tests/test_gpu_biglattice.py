@@ -1,0 +1,136 @@
+"""BigLattice (x-slab split + halo exchange) on a B200.  With the PRNG-free INTS=2 start a partitioned run must
+reproduce the unpartitioned one exactly (the reference only promises statistical agreement once PRNGs are
+involved, suncl.cpp:377-386); parts can share one device, as in the reference's init_2.dat."""
+import json
+import os
+import socket
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLD = os.path.join(ROOT, "tests", "golden")
+
+
+def _configure(sun, beta, ints, iters, prec=1, fused=False, prng="RANLUX3"):
+    def f(p):
+        p.lattice_group, p.precision, p.ints, p.BETA, p.ITER = sun, prec, ints, beta, iters
+        p.fused_prng = fused
+        p.PRNG0.PRNG_generator = prng
+        if not fused:
+            p.GPU0.L.qgpu_set_max_memory_width(p.GPU0.h, 64)
+    return f
+
+
+@pytest.mark.parametrize("sun,dims,nparts", [(3, (4, 6, 2, 8), 1), (3, (4, 6, 2, 8), 2), (3, (12, 4, 2, 4), 3), (2, (8, 4, 8, 2), 2)])
+def test_gid_start_partitioned_equals_single(sun, dims, nparts):
+    from qcdgpu_b200 import Model
+    from qcdgpu_b200.biglattice import BigLattice
+    beta = 5.7 if sun == 3 else 2.3
+    m = Model()
+    m.lattice_group, m.lattice_full_size, m.precision, m.ints, m.BETA, m.ITER, m.PL_level = sun, list(dims), 1, 2, beta, 4, 0
+    m.lattice_init()
+    m.lattice_simulate()
+    m.lattice_analysis()
+    want = np.array([[m.Analysis[c]["data"][i] for c in ("Plq_spat", "Plq_temp", "S_spat", "S_temp")] for i in range(4)])
+    m.close()
+    for overlap in (False, True):
+        B = BigLattice(dims, nparts, configure=_configure(sun, beta, 2, 4))
+        B.overlap = overlap
+        B.lattice_init()
+        B.lattice_simulate()
+        A = B.lattice_analysis()
+        got = np.array([[A[c]["data"][i] for c in ("Plq_spat", "Plq_temp", "S_spat", "S_temp")] for i in range(4)])
+        np.testing.assert_allclose(got, want, rtol=1e-12)
+        B.close()
+
+
+def test_gid_biglattice_matches_reference_golden():
+    gold = json.load(open(os.path.join(GOLD, "ref_cpurun_su3_4x6x2x8_gid.json")))
+    p = gold["params"]
+    from qcdgpu_b200.biglattice import BigLattice
+
+    def conf(q):
+        _configure(3, p["BETA"], 2, p["ITER"])(q)
+        q.turnoff_gramschmidt = True
+    B = BigLattice((p["L1"], p["L2"], p["L3"], p["L4"]), 2, configure=conf)
+    B.lattice_init()
+    B.lattice_simulate()
+    A = B.lattice_analysis()
+    got = np.array([[A[c]["data"][i] for c in gold["columns"]] for i in range(p["ITER"])])
+    np.testing.assert_allclose(got, np.array(gold["rows"]), rtol=5e-6)
+    B.close()
+
+
+@pytest.mark.parametrize("fused", [False, True])
+def test_overlap_schedule_is_bit_identical(fused):
+    """Boundary-slices-first + interior (3 launches per pass) vs one launch per pass: same links, hot start, PRNGs on."""
+    from qcdgpu_b200.biglattice import BigLattice
+    tables = []
+    for overlap in (False, True):
+        B = BigLattice((12, 4, 4, 4), 2, configure=_configure(3, 6.0, 0, 3, fused=fused))
+        B.overlap = overlap
+        B.lattice_init()
+        B.lattice_simulate()
+        tables.append([p.table_numpy() for p in B.parts.values()])
+        B.close()
+    for a, b in zip(*tables):
+        np.testing.assert_array_equal(a.view(np.uint8), b.view(np.uint8))
+
+
+def test_partitioned_ensemble_agrees():
+    """With PRNGs the parts use their own series: plaquette after thermalisation agrees statistically with the
+    reference's CPU_RUN series (8^4, beta = 6)."""
+    gold = json.load(open(os.path.join(GOLD, "ref_cpurun_su3_8x8x8x8_cold_ens.json")))
+    ref = np.array(gold["rows"])[15:, 2]
+    from qcdgpu_b200.biglattice import BigLattice
+
+    def conf(q):
+        _configure(3, 6.0, 1, 61, fused=True)(q)
+        q.NAV = 40
+    B = BigLattice((8, 8, 8, 8), 2, configure=conf)
+    B.lattice_init()
+    B.lattice_simulate()
+    A = B.lattice_analysis()
+    mine = A["Plq_total"]["data"][1:]
+    se = 3 * np.sqrt(ref.var() / len(ref) + mine.var() / len(mine))
+    assert abs(mine.mean() - ref.mean()) < 5 * se, (mine.mean(), ref.mean(), se)
+    B.close()
+
+
+NCCL_WORKER = r'''
+import os, sys, json
+import numpy as np, torch, torch.distributed as dist
+sys.path.insert(0, os.environ["QCD_ROOT"])
+from qcdgpu_b200.biglattice import BigLattice
+rank = int(os.environ["RANK"]); world = int(os.environ["WORLD_SIZE"])
+torch.cuda.set_device(rank)
+dist.init_process_group("nccl", device_id=torch.device(f"cuda:{rank}"))
+def conf(p):
+    p.lattice_group, p.precision, p.ints, p.BETA, p.ITER = 3, 1, 2, 5.7, 3
+    p.turnoff_gramschmidt = True
+    p.desired_device = rank
+B = BigLattice((4, 6, 2, 8), world, dist=dist, configure=conf, devices=[rank])
+B.lattice_init(); B.lattice_simulate(); A = B.lattice_analysis()
+if rank == 0:
+    print("ROWS " + json.dumps([[float(A[c]["data"][i]) for c in ("Plq_spat", "Plq_temp", "Plq_total", "S_spat", "S_temp", "S_total")] for i in range(3)]))
+B.close(); dist.destroy_process_group()
+'''
+
+
+def test_nccl_two_gpus_gid(tmp_path):
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
+    gold = json.load(open(os.path.join(GOLD, "ref_cpurun_su3_4x6x2x8_gid.json")))
+    script = tmp_path / "w.py"
+    script.write_text(NCCL_WORKER)
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+                        "--master-port", str(port), str(script)], capture_output=True, text=True, env=dict(os.environ, QCD_ROOT=ROOT), timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
+    rows = json.loads([l for l in r.stdout.splitlines() if l.startswith("ROWS ")][0][5:])
+    np.testing.assert_allclose(np.array(rows), np.array(gold["rows"]), rtol=5e-6)
