@@ -70,6 +70,7 @@ struct Kernel {
 struct Buffer {
     int type = 0;
     size_t size = 0, size_of = 0, bytes = 0;
+    size_t capacity = 0;             // allocated bytes (>= bytes): see qgpu_buffer_init
     void* dptr = nullptr;
     const void* host_ptr = nullptr;
     void* shadow = nullptr;          // host memory returned by buffer_map
@@ -337,7 +338,7 @@ int launch_kernel(qgpu* h, int kid) {
             a.nsites = c.biglat ? (c.n1 - 2) * a.geom.n234 : a.geom.sites;
             a.block = (uint32_t)k.local0;
             size_t blocks = (a.nsites + a.block - 1) / a.block;
-            if (h->buffers[buf_id(k, 1)].bytes < blocks * 16) return fail(h, "kernel %s: measurement buffer too small (%zu partials needed)", k.name.c_str(), blocks);
+            if (h->buffers[buf_id(k, 1)].capacity < blocks * 16) return fail(h, "kernel %s: measurement buffer too small (%zu partials needed)", k.name.c_str(), blocks);
             CUDA_OK(h, launch_measure(c.sun, prec, a, st));
             break;
         }
@@ -365,7 +366,7 @@ int launch_kernel(qgpu* h, int kid) {
             a.x_first = c.biglat ? 1 : 0; a.x_count = c.biglat ? c.n1 - 2 : c.n1;
             a.block = (uint32_t)k.local0;
             size_t blocks = ((size_t)a.x_count * a.geom.n23 + a.block - 1) / a.block;
-            if (h->buffers[buf_id(k, 1)].bytes < ((c.pl > 1 ? (size_t)offset : 0) + blocks) * 16) return fail(h, "kernel %s: measurement buffer too small", k.name.c_str());
+            if (h->buffers[buf_id(k, 1)].capacity < ((c.pl > 1 ? (size_t)offset : 0) + blocks) * 16) return fail(h, "kernel %s: measurement buffer too small", k.name.c_str());
             CUDA_OK(h, launch_polyakov(c.sun, prec, a, st));
             break;
         }
@@ -603,10 +604,14 @@ int qgpu_buffer_init(qgpu* h, int type, size_t size, const void* host_ptr, size_
     Buffer b;
     b.type = type; b.size = size; b.size_of = size_of; b.bytes = size * size_of; b.host_ptr = host_ptr; b.alive = true;
     if (type != QGPU_BUFFER_LDS && b.bytes) {
-        CUDA_OK(h, cudaMalloc(&b.dptr, b.bytes));
+        // 64 KiB of zeroed slack behind every buffer: with small lattices the reference's own sizing lets
+        // lattice_polyakov write its second partial block at measurement[BID + offset] past the end of
+        // lattice_measurement (suncl.cpp:2272-2285 vs polyakov.cl:135-139); OpenCL runtimes tolerate it silently.
+        b.capacity = b.bytes + (64u << 10);
+        CUDA_OK(h, cudaMalloc(&b.dptr, b.capacity));
+        CUDA_OK(h, cudaMemsetAsync(b.dptr, 0, b.capacity, h->stream));
         bool copy = host_ptr && (type == QGPU_BUFFER_INPUT || type == QGPU_BUFFER_CONSTANT || type == QGPU_BUFFER_IO);
         if (copy) CUDA_OK(h, cudaMemcpyAsync(b.dptr, host_ptr, b.bytes, cudaMemcpyHostToDevice, h->stream));
-        else CUDA_OK(h, cudaMemsetAsync(b.dptr, 0, b.bytes, h->stream));
         CUDA_OK(h, cudaStreamSynchronize(h->stream));   // host_ptr may be freed by the caller right after (blocking write, clinterface.cpp:1393-1410)
     }
     h->buffers.push_back(b);

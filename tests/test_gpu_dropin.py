@@ -1,0 +1,80 @@
+"""Drop-in check: the UNMODIFIED reference host program (QCDGPU.cpp main, suncl.cpp run loop, random.cpp,
+su{2,3}cpu.cpp LatticeCheckCPU, data_analysis.cpp) linked against integration/clinterface_cuda.cpp +
+libqcdgpu_b200.so (integration/Makefile; built where the reference tree exists, the binary travels).
+The reference verifies itself: it re-measures the last configuration on the CPU and compares with the
+device values at 1e-11 (double) / 5e-5 (single) -- data_analysis.cpp:40-101."""
+import glob
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+BIN = os.path.join(ROOT, "integration", "_build", "QCDGPU_b200")
+
+INIT = """\tPLATFORM = 0
+\tDEVICE= 0
+\tFINISHPATH=./
+\tOUTPUTPATH=./
+\tGROUP = {group}
+\tND = 4
+\tLS = {ls}
+\tLT = {lt}
+\tITER = {iter}
+\tNITER = 1
+\tNHIT = 10
+\tBETA = {beta:.13e}
+\tNAV = {nav}
+\tINTS = {ints}
+\tPRNG = {prng}
+\tRANDSERIES = 54
+\tPL_LEVEL = 2
+\tPHI = {phi:.13e}
+"""
+
+
+def run_reference_host(tmp_path, **kw):
+    if not os.path.exists(BIN):
+        pytest.skip("integration/_build/QCDGPU_b200 not built (needs the reference tree: make -C integration)")
+    cfg = dict(group=3, ls=8, lt=8, iter=4, beta=6.0, nav=2, ints=1, prng="RANLUX3", phi=0.0)
+    cfg.update(kw)
+    (tmp_path / "init.dat").write_text(INIT.format(**cfg))
+    r = subprocess.run([BIN, "init.dat"], cwd=tmp_path, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    out = glob.glob(str(tmp_path / "su*-*.txt"))
+    assert len(out) == 1, (out, r.stdout[-2000:])
+    return open(out[0]).read(), r.stdout
+
+
+def last_values(text):
+    vals = {}
+    for kind, name, v in re.findall(r"^ (CPU|GPU) last (\S+)\s*:\s*(\S+)", text, flags=re.M):
+        vals.setdefault(name, {})[kind] = float(v)
+    return vals
+
+
+@pytest.mark.parametrize("group,ints,beta", [(3, 1, 6.0), (3, 0, 5.7), (2, 0, 2.5)])
+def test_reference_host_runs_on_cuda_backend_and_verifies_itself(tmp_path, group, ints, beta):
+    text, stdout = run_reference_host(tmp_path, group=group, ints=ints, beta=beta)
+    assert "Verification successfully passed" in text, text[-3000:]
+    vals = last_values(text)
+    for name in ("S_total", "Plq_total", "Polyakov_loop"):
+        assert name in vals, (name, sorted(vals))
+        c, g = vals[name]["CPU"], vals[name]["GPU"]
+        assert abs(c) > 1e-3
+        assert abs(1.0 - g / c) < 1e-11, (name, c, g)
+    # the per-iteration table is there and physical
+    rows = [l.split() for l in text.splitlines() if re.match(r"^\s+\d+\s+[-\d]", l)]
+    assert len(rows) == 4
+    plq_total = [float(r[3]) for r in rows]
+    if ints == 1:
+        assert plq_total[0] == float(group)
+
+
+def test_reference_host_twisted_run_verifies(tmp_path):
+    """PHI != 0 (init.dat sample value 3.0): twisted loads in staples, measurements and the CPU check."""
+    text, _ = run_reference_host(tmp_path, group=3, ints=0, beta=6.0, phi=3.0, ls=6, lt=4)
+    assert "Verification successfully passed" in text, text[-3000:]
