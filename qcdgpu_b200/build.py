@@ -21,6 +21,8 @@ LIB = os.path.join(LIBDIR, "libqcdgpu_b200.so")
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-O2"]
+# experiment knobs: QCD_NVCC_EXTRA="-DQCD_BUF_MINBLOCKS=4 ..." (part of the build digest)
+NVCC_FLAGS += os.environ.get("QCD_NVCC_EXTRA", "").split()
 
 
 def _nvcc() -> str:

@@ -174,6 +174,7 @@ Geom make_geom(const ProgramCfg& c, int tile_override = -1) {
     g.nhit = (uint32_t)c.nhit; g.nhitpar = (uint32_t)c.nhitpar;
     g.upd_x0 = 0; g.upd_nx = c.biglat ? c.n1 - 2 : c.n1;
     if (c.biglat && g.n234) { g.tw_lo = c.left_sites / g.n234; g.tw_hi = c.full_sites / g.n234; }
+    { static int dbg = -1; if (dbg < 0) { const char* e = getenv("QCDGPU_DEBUG_SKIP"); dbg = e ? atoi(e) : 0; } g.debug_skip = (uint32_t)dbg; }
     // L2 tiling (lattice.cuh remap_gid): worthwhile once three x-slices of all links no longer fit the L2
     {
         static int env_tile = -2;

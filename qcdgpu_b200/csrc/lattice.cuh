@@ -32,6 +32,7 @@ struct Geom {
     uint32_t nhit, nhitpar;
     uint32_t tw_lo, tw_hi;        // BIGLAT twist test: x + left_sites/n234 == tw_lo || == tw_hi
     uint32_t tile_x;              // L2 tiling of the update passes: x-chunk width (0 = reference order)
+    uint32_t debug_skip;          // diagnostics (env QCDGPU_DEBUG_SKIP): 1 = skip the generator phase, 2 = skip the physics phase
     uint32_t upd_x0, upd_nx;      // x-range of this launch inside the updated region (halo/interior split); nthreads = upd_nx*N4*N2/2*N3
 };
 
@@ -98,6 +99,13 @@ template <int DIR> __device__ __forceinline__ Coord nb_minus(const Geom& g, Coor
     if (DIR == 2) { if (c.z == 0) c.z = g.n3; c.z--; }
     if (DIR == 3) { if (c.t == 0) c.t = g.n4; c.t--; }
     return c;
+}
+// run-time direction variants (used where a loop over planes keeps the code size down)
+__device__ __forceinline__ Coord nb_plus_rt(const Geom& g, const Coord& c, int dir) {
+    switch (dir) { case 0: return nb_plus<0>(g, c); case 1: return nb_plus<1>(g, c); case 2: return nb_plus<2>(g, c); default: return nb_plus<3>(g, c); }
+}
+__device__ __forceinline__ Coord nb_minus_rt(const Geom& g, const Coord& c, int dir) {
+    switch (dir) { case 0: return nb_minus<0>(g, c); case 1: return nb_minus<1>(g, c); case 2: return nb_minus<2>(g, c); default: return nb_minus<3>(g, c); }
 }
 __device__ __forceinline__ bool twisted_x(const Geom& g, uint32_t x) {
     // su3_matrix_memory.cl:57-63
@@ -247,6 +255,21 @@ __device__ __forceinline__ V4<R> load2(const R* table, const Geom& g, uint32_t g
         if (twisted_x(g, x)) {
             V4<R> om = { tw.c1, R(0), tw.s1, R(0) };
             m = su2_mul(om, m);
+        }
+    }
+    return m;
+}
+template <typename R, bool TBC>
+__device__ __forceinline__ M3r2<R> load3_rt(const R* table, const Geom& g, uint32_t gindex, uint32_t x, int dir, const Twist<R>& tw) {
+    V4<R> a = ld_plane(table, g, gindex, dir + 0);
+    V4<R> b = ld_plane(table, g, gindex, dir + 4);
+    V4<R> c = ld_plane(table, g, gindex, dir + 8);
+    M3r2<R> m = unpack3(a, b, c);
+    if (TBC) {
+        if (dir == 1 && twisted_x(g, x)) {
+            const Cx<R> p1 = { tw.c1, tw.s1 }, p2 = { tw.c2, tw.s2 };
+#pragma unroll
+            for (int j = 0; j < 3; j++) { m.e[0][j] = cmul(m.e[0][j], p1); m.e[1][j] = cmul(m.e[1][j], p2); }
         }
     }
     return m;

@@ -19,6 +19,10 @@
 #include "lattice.cuh"
 #include "prng.cuh"
 
+#ifndef QCD_BUF_MINBLOCKS
+#define QCD_BUF_MINBLOCKS 3
+#endif
+
 namespace qcd {
 
 // ---------------------------------------------------------------- PRN sources
@@ -29,10 +33,12 @@ struct PrnBuffered {
     __device__ __forceinline__ PrnBuffered(const Args& a, const Geom& g, uint32_t GID, uint32_t) : p(a.prns), ind(GID), step(g.prngstep) {}
     __device__ __forceinline__ F4 trial() { float4 r = __ldg(p + ind); ind += step; return { r.x, r.y, r.z, r.w }; }
     __device__ __forceinline__ F4 direction() { return trial(); }
+    __device__ __forceinline__ F4 peek() { float4 r = __ldg(p + ind); return { r.x, r.y, r.z, r.w }; }     // next slot, not consumed
     __device__ __forceinline__ void burn() { ind += step; }
     __device__ __forceinline__ void finish() {}
     static constexpr bool kGid = false;
-    static constexpr int kMinBlocks = 3;
+    static constexpr bool kCanPeek = true;
+    static constexpr int kMinBlocks = QCD_BUF_MINBLOCKS;
 };
 // INTS=2 / -D GID_UPD closed-form pseudo-randoms (su3_update_cl.cl:598-637); every trial is accepted
 struct PrnGid {
@@ -60,6 +66,7 @@ struct PrnGid {
     __device__ __forceinline__ void burn() {}
     __device__ __forceinline__ void finish() {}
     static constexpr bool kGid = true;
+    static constexpr bool kCanPeek = false;
     static constexpr int kMinBlocks = 2;
 };
 // Fused generators: instance GID lives in the registers of update thread GID.  Bit-exact with the
@@ -76,6 +83,7 @@ struct PrnRanlux {
     __device__ __forceinline__ void burn() { used++; r.template skip4<NSKIP>(); }
     __device__ __forceinline__ void finish() { r.template skip_samples<NSKIP>(samples - used); ranlux_store(r, table, instances, id); }
     static constexpr bool kGid = false;
+    static constexpr bool kCanPeek = false;
     static constexpr int kMinBlocks = 2;
 };
 // RANLUX, two-phase: phase 1 of the kernel runs the whole generator work of the pass (all `samples` vec4,
@@ -88,28 +96,37 @@ struct PrnSmem {
     __device__ __forceinline__ PrnSmem(const float4* base, uint32_t stride_) : p(base), k(0), stride(stride_) {}
     __device__ __forceinline__ F4 trial() { float4 r = p[k * stride]; k++; return { r.x, r.y, r.z, r.w }; }
     __device__ __forceinline__ F4 direction() { return trial(); }
+    __device__ __forceinline__ F4 peek() { float4 r = p[k * stride]; return { r.x, r.y, r.z, r.w }; }
     __device__ __forceinline__ void burn() { k++; }
     __device__ __forceinline__ void finish() {}
     static constexpr bool kGid = false;
+    static constexpr bool kCanPeek = true;
     static constexpr int kMinBlocks = 3;
 };
 template <class Gen, int WORDS>
 struct PrnSmallState {   // XOR128 (4 words), PM (4 words), MRG32k3a (2 x uint4 rows)
     struct Args { uint32_t* table; uint32_t instances; uint32_t samples; };
     Gen gen; uint32_t used; uint32_t* table; uint32_t instances, samples, id;
+    F4 ahead; bool have_ahead;     // peek(): the next sample, generated but not yet consumed
     __device__ __forceinline__ PrnSmallState(const Args& a, const Geom&, uint32_t GID, uint32_t)
-        : used(0), table(a.table), instances(a.instances), samples(a.samples), id(GID) { load(); }
+        : used(0), table(a.table), instances(a.instances), samples(a.samples), id(GID), have_ahead(false) { load(); }
     __device__ __forceinline__ void load();
     __device__ __forceinline__ void store();
-    __device__ __forceinline__ F4 trial() { used++; return gen.next4(); }
-    __device__ __forceinline__ F4 direction() { used++; return gen.next4(); }
-    __device__ __forceinline__ void burn() { used++; gen.skip4(); }
+    __device__ __forceinline__ F4 trial() {
+        used++;
+        if (have_ahead) { have_ahead = false; return ahead; }
+        return gen.next4();
+    }
+    __device__ __forceinline__ F4 direction() { return trial(); }
+    __device__ __forceinline__ F4 peek() { if (!have_ahead) { ahead = gen.next4(); have_ahead = true; } return ahead; }
+    __device__ __forceinline__ void burn() { used++; if (have_ahead) have_ahead = false; else gen.skip4(); }
     __device__ __forceinline__ void finish() {
 #pragma unroll 1
-        for (uint32_t k = used; k < samples; k++) gen.skip4();
+        for (uint32_t k = used + (have_ahead ? 1u : 0u); k < samples; k++) gen.skip4();
         store();
     }
     static constexpr bool kGid = false;
+    static constexpr bool kCanPeek = true;
     static constexpr int kMinBlocks = 3;
 };
 template <> __device__ __forceinline__ void PrnSmallState<Xor128, 4>::load() {
@@ -156,46 +173,68 @@ template <> struct Mth<float> {
 
 // Kennedy-Pendleton sampling of the new SU(2) element (reference: lattice_heatbath2).
 // aH = (r/sqrt(det r))^+ as a 4-vector, bdet = beta*sqrt(det).  Returns false after NHIT rejections.
+// direction part of the new element: uniform point on S^2 from (r.x, r.y)
+template <typename R> struct KpDir { R costh, sinth, sinphi, cosphi; };
+template <typename R> __device__ __forceinline__ KpDir<R> kp_direction(R rx, R ry) {
+    KpDir<R> d;
+    d.costh = R(2) * rx - R(1);
+    d.sinth = Mth<R>::sqrt_(R(1) - d.costh * d.costh);
+    Mth<R>::sincos2pi(ry, &d.sinphi, &d.cosphi);
+    return d;
+}
+template <typename R> __device__ __forceinline__ V4<R> kp_compose(R delta, const KpDir<R>& d, const V4<R>& aH) {
+    R cosal = R(1) - delta;
+    R sinal = Mth<R>::sqrt_(R(1) - cosal * cosal);
+    V4<R> c;
+    c.x = cosal;
+    c.z = sinal * d.costh;
+    c.y = sinal * d.sinth * d.sinphi;
+    c.w = sinal * d.sinth * d.cosphi;
+    return su2_mul(c, aH);
+}
 template <typename R, class Prn>
 __device__ __forceinline__ bool kp_heatbath(Prn& prn, const Geom& g, const V4<R>& aH, R bdet, V4<R>& out) {
-    bool flag = false;
-    R delta = R(0);
     R ibdet = R(1) / bdet;
-    uint32_t i = 0;
-    R rx, ry;
     if constexpr (Prn::kGid) {
         double r[4];
         prn.trial_d(r);
         R c = Mth<R>::cos2pi(R(r[1]));
-        delta = c * c * ibdet;
-        flag = true;
+        R delta = c * c * ibdet;
         prn.direction_d(r);
-        rx = R(r[0]); ry = R(r[1]);
+        out = kp_compose(delta, kp_direction<R>(R(r[0]), R(r[1])), aH);
+        return true;
+    } else if constexpr (Prn::kCanPeek) {
+        // The slot after a trial is the direction sample if the trial is accepted and the next trial if not:
+        // evaluate both roles together (five independent transcendental chains instead of one after the other).
+        F4 r = prn.trial();
+        for (uint32_t i = 0; i < g.nhit; i++) {
+            F4 r2 = prn.peek();
+            R c = Mth<R>::cos2pi(R(r.y));
+            R l1 = Mth<R>::log_(R(1) - R(r.x)), l2 = Mth<R>::log_(R(1) - R(r.z));
+            KpDir<R> d = kp_direction<R>(R(r2.x), R(r2.y));
+            R delta = -(l1 + c * c * l2) * ibdet;
+            if (R(r.w) * R(r.w) <= R(1) - R(0.5) * delta) {
+                prn.burn();                        // the peeked slot is consumed as the direction sample
+                out = kp_compose(delta, d, aH);
+                return true;
+            }
+            if (i + 1 < g.nhit) r = prn.trial();   // the peeked slot becomes the next trial
+        }
+        return false;
     } else {
-        while (i < g.nhit && !flag) {
+        bool flag = false;
+        R delta = R(0);
+        for (uint32_t i = 0; i < g.nhit && !flag; i++) {
             F4 r = prn.trial();
             R c = Mth<R>::cos2pi(R(r.y));
             delta = -(Mth<R>::log_(R(1) - R(r.x)) + c * c * Mth<R>::log_(R(1) - R(r.z))) * ibdet;
             if (R(r.w) * R(r.w) <= R(1) - R(0.5) * delta) flag = true;
-            i++;
         }
         if (!flag) return false;
         F4 r = prn.direction();
-        rx = R(r.x); ry = R(r.y);
+        out = kp_compose(delta, kp_direction<R>(R(r.x), R(r.y)), aH);
+        return true;
     }
-    R cosal = R(1) - delta;
-    R costh = R(2) * rx - R(1);
-    R sinth = Mth<R>::sqrt_(R(1) - costh * costh);
-    R sinal = Mth<R>::sqrt_(R(1) - cosal * cosal);
-    R sinphi, cosphi;
-    Mth<R>::sincos2pi(ry, &sinphi, &cosphi);
-    V4<R> c;
-    c.x = cosal;
-    c.z = sinal * costh;
-    c.y = sinal * sinth * sinphi;
-    c.w = sinal * sinth * cosphi;
-    out = su2_mul(c, aH);
-    return true;
 }
 
 // ---------------------------------------------------------------- SU(3) products on 2-row operands
@@ -239,6 +278,32 @@ template <typename R> __device__ __forceinline__ void mul_dag_full(const M3<R>& 
         }
     third_row(G.e[0], G.e[1], G.e[2]);
 }
+#ifdef QCD_S_SMEM
+// staple accumulator parked in shared memory: element e of thread t at sm[e * kThreads + t] (conflict-free)
+template <typename R> struct SmemAcc {
+    R* p;
+    __device__ __forceinline__ void set(const M3<R>& F) {
+#pragma unroll
+        for (int i = 0; i < 3; i++)
+#pragma unroll
+            for (int j = 0; j < 3; j++) { p[(6 * i + 2 * j) * 128] = F.e[i][j].re; p[(6 * i + 2 * j + 1) * 128] = F.e[i][j].im; }
+    }
+    __device__ __forceinline__ void add(const M3<R>& F) {
+#pragma unroll
+        for (int i = 0; i < 3; i++)
+#pragma unroll
+            for (int j = 0; j < 3; j++) { p[(6 * i + 2 * j) * 128] += F.e[i][j].re; p[(6 * i + 2 * j + 1) * 128] += F.e[i][j].im; }
+    }
+    __device__ __forceinline__ M3<R> get() const {
+        M3<R> S;
+#pragma unroll
+        for (int i = 0; i < 3; i++)
+#pragma unroll
+            for (int j = 0; j < 3; j++) { S.e[i][j].re = p[(6 * i + 2 * j) * 128]; S.e[i][j].im = p[(6 * i + 2 * j + 1) * 128]; }
+        return S;
+    }
+};
+#endif
 template <typename R> __device__ __forceinline__ void acc3(M3<R>& S, const M3<R>& F) {
 #pragma unroll
     for (int i = 0; i < 3; i++)
@@ -276,9 +341,9 @@ __device__ __forceinline__ void plane_prefetch(const R* table, const Geom& g, ui
     prefetch_link<R, NU, NPL>(table, g, s.g_pmn);
 }
 // staple contribution of the (MU,NU) plane at site p: forward + backward
-template <typename R, int MU, int NU, bool TBC>
+template <typename R, int MU, int NU, bool TBC, class Acc>
 __device__ __forceinline__ void staple3_plane(const R* table, const Geom& g, uint32_t px, uint32_t gindex,
-                                              const PlaneSites& ps, const Twist<R>& tw, M3<R>& S, bool first) {
+                                              const PlaneSites& ps, const Twist<R>& tw, Acc& S, bool first) {
     // issue all six link loads of the plane before the arithmetic
     M3r2<R> A  = load3<R, NU, TBC>(table, g, ps.g_pmu, ps.x_pmu, tw);      // U_nu(p+mu)
     M3r2<R> B  = load3<R, MU, TBC>(table, g, ps.g_pnu, ps.x_pnu, tw);      // U_mu(p+nu)
@@ -290,24 +355,37 @@ __device__ __forceinline__ void staple3_plane(const R* table, const Geom& g, uin
         M3<R> Bf = complete(B), D, F;
         mul_r2_full(C, Bf, D);
         mul_r2_dag(A, D, F);
-        if (first) S = F; else acc3(S, F);
+        if (first) S.set(F); else S.add(F);
     }
     {   // backward: A2^+ B2^+ C2 = (B2 A2)^+ C2
         M3<R> Af = complete(A2), Cf = complete(C2), E, G;
         mul_r2_full(B2, Af, E);
         mul_dag_full(E, Cf, G);
-        acc3(S, G);
+        S.add(G);
     }
 }
+template <typename R> struct RegAcc {
+    M3<R> S;
+    __device__ __forceinline__ void set(const M3<R>& F) { S = F; }
+    __device__ __forceinline__ void add(const M3<R>& F) { acc3(S, F); }
+    __device__ __forceinline__ M3<R> get() const { return S; }
+};
 // plane order of the reference: X:{Y,Z,T} Y:{X,Z,T} Z:{Y,X,T} T:{Y,Z,X}  (su3_update_cl.cl:367-559)
 template <int MU> struct PlaneOrder {
     static constexpr int n0 = (MU == 1) ? 0 : 1;
     static constexpr int n1 = (MU == 0 || MU == 1 || MU == 3) ? 2 : 0;
     static constexpr int n2 = (MU == 3) ? 0 : 3;
 };
+// Sum of the six staples, planes unrolled (a run-time loop over the planes was measured 4 % slower: spills
+// and run-time plane indexing cost more than the smaller code saves in instruction fetch).
 template <typename R, int MU, bool TBC>
 __device__ __forceinline__ M3<R> staple3(const R* table, const Geom& g, const Coord& p, uint32_t gindex, const Twist<R>& tw) {
-    M3<R> S;
+#ifdef QCD_S_SMEM
+    __shared__ R s_acc[18 * 128];
+    SmemAcc<R> S = { s_acc + threadIdx.x };
+#else
+    RegAcc<R> S;
+#endif
     Coord pmu = nb_plus<MU>(g, p);
     constexpr int n0 = PlaneOrder<MU>::n0, n1 = PlaneOrder<MU>::n1, n2 = PlaneOrder<MU>::n2;
     PlaneSites s0 = plane_sites<MU, n0>(g, p, pmu);
@@ -318,7 +396,7 @@ __device__ __forceinline__ M3<R> staple3(const R* table, const Geom& g, const Co
     plane_prefetch<R, MU, n2, 3>(table, g, gindex, s2);
     staple3_plane<R, MU, n1, TBC>(table, g, p.x, gindex, s1, tw, S, false);
     staple3_plane<R, MU, n2, TBC>(table, g, p.x, gindex, s2, tw, S, false);
-    return S;
+    return S.get();
 }
 // first things a site update will read: its own link and the first plane (issued before the generator phase)
 template <int SUN, typename R, int MU>
@@ -358,16 +436,30 @@ __device__ __forceinline__ V4<R> block_dagger(const M3<R>& W, R& det) {
     aH.x *= id; aH.y *= id; aH.z *= id; aH.w *= id;
     return aH;
 }
-template <typename R, int A, int B, class Prn>
-__device__ __forceinline__ void cm_subgroup(M3<R>& U, M3<R>& W, const Geom& g, R beta, Prn& prn) {
-    R det;
-    V4<R> aH = block_dagger<R, A, B>(W, det);
-    V4<R> d;
-    if (kp_heatbath<R, Prn>(prn, g, aH, beta * det, d)) {
-        rotate_rows<R, A, B>(U, d);
-        rotate_rows<R, A, B>(W, d);
-    } else {
-        prn.burn();    // su3_update_cl.cl:665-668
+// One Cabibbo-Marinari round over the subgroups (0,1), (0,2), (1,2) in the reference's order.  The loop is NOT unrolled:
+// the Kennedy-Pendleton code (log, cospi, sincospi, sqrt) is instantiated once; only the small block-extraction and
+// row-rotation pieces are per-subgroup (uniform switch, no divergence).
+template <typename R, class Prn>
+__device__ __forceinline__ void cm_round(M3<R>& U, M3<R>& W, const Geom& g, R beta, Prn& prn) {
+#pragma unroll 1
+    for (int sub = 0; sub < 3; sub++) {
+        R det;
+        V4<R> aH;
+        switch (sub) {
+            case 0: aH = block_dagger<R, 0, 1>(W, det); break;
+            case 1: aH = block_dagger<R, 0, 2>(W, det); break;
+            default: aH = block_dagger<R, 1, 2>(W, det); break;
+        }
+        V4<R> d;
+        if (kp_heatbath<R, Prn>(prn, g, aH, beta * det, d)) {
+            switch (sub) {
+                case 0: rotate_rows<R, 0, 1>(U, d); rotate_rows<R, 0, 1>(W, d); break;
+                case 1: rotate_rows<R, 0, 2>(U, d); rotate_rows<R, 0, 2>(W, d); break;
+                default: rotate_rows<R, 1, 2>(U, d); rotate_rows<R, 1, 2>(W, d); break;
+            }
+        } else {
+            prn.burn();    // su3_update_cl.cl:665-668
+        }
     }
 }
 template <typename R, int A, int B>
@@ -423,9 +515,7 @@ __device__ __forceinline__ void update_site_su3(R* table, const Geom& g, R beta,
     for (uint32_t h = 0; h < g.nhitpar; h++) {
         third_row(U.e[0], U.e[1], U.e[2]);
         M3<R> W = mul_full(U, S);
-        cm_subgroup<R, 0, 1, Prn>(U, W, g, beta, prn);
-        cm_subgroup<R, 0, 2, Prn>(U, W, g, beta, prn);
-        cm_subgroup<R, 1, 2, Prn>(U, W, g, beta, prn);
+        cm_round<R, Prn>(U, W, g, beta, prn);
         gram_schmidt3(U.e[0], U.e[1]);
     }
     store3<R, MU>(table, g, gindex, U.e[0], U.e[1]);
@@ -517,12 +607,13 @@ update_kernel_rlx(R* __restrict__ table, const R* __restrict__ params, const __g
     if (GID >= g.nthreads) return;
     GID = remap_gid(g, GID);
     prefetch_site_head<SUN, R, MU>(table, g, parity_gid(g, GID, odd != 0));
-    {   // phase 1: the pass's whole RANLUX work
+    if (g.debug_skip != 1u) {   // phase 1: the pass's whole RANLUX work
         Ranlux r;
         ranlux_load(r, rtable, instances, GID);
         r.template run_pass<NSKIP>(prn_smem + threadIdx.x, kUpdateThreads, keep, samples);
         ranlux_store(r, rtable, instances, GID);
     }
+    if (g.debug_skip == 2u) return;
     // phase 2: the link update
     const R beta = params[0];
     const Twist<R> tw = make_twist<SUN, R, TBC>(params);

@@ -2,6 +2,7 @@
 // (INST_SUN, INST_PREC, INST_MU) by build.py so that the 16 units compile in parallel.
 #include "launch.h"
 #include "update.cuh"
+#include <cstdlib>
 
 #ifndef INST_SUN
 #error "compile with -DINST_SUN=2|3 -DINST_PREC=0|1 -DINST_MU=0..3"
