@@ -125,11 +125,25 @@ struct Ranlux {
         for (int q = 0; q < 6; q++) out[q * stride] = make_float4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]);
         left = 0;
     }
+    // float of the k-th number just produced (x = new seed << 8, nx = seeds[j24 after the step] << 8), reference
+    // semantics incl. the "uni < 2^-12" fix-up (random.cpp:565-569)
+    static __device__ __forceinline__ float to_float(uint32_t x, uint32_t nx) {
+        float f = __uint2float_rn(x) * 2.3283064365386963e-10f;            // (x >> 8) * 2^-24, exact
+        if (x < (4096u << 8)) {
+            f = __fadd_rn(f, __fmul_rn(5.9604644775390625e-8f, __uint2float_rn(nx) * 2.3283064365386963e-10f));
+            if (f == 0.0f) f = 5.9604644775390625e-8f * 5.9604644775390625e-8f;
+        }
+        return f;
+    }
     // One pass worth of generator work in a single loop (every code piece instantiated once, to stay inside the
-    // instruction cache): advance by `samples` float4, converting and storing the first `keep` of them to
-    // out[k * stride].  Whole 24-number blocks avoid the register rotation.
-    template <int NSKIP> __device__ __forceinline__ void run_pass(float4* out, uint32_t stride, uint32_t keep, uint32_t samples) {
+    // instruction cache): advance by `samples` float4 and park the first `keep` of them at out[k * stride].
+    // Parked samples stay RAW (four seeds << 8): only the ~7 of 33 that a link really consumes get converted, by the
+    // consumer.  The exception is a sample containing a number below 2^-12, whose fix-up needs a seed that is gone
+    // later: it is converted here and flagged in `*converted` (bit k).  Whole 24-number blocks avoid the register rotation.
+    template <int NSKIP> __device__ __forceinline__ void run_pass(uint4* out, uint32_t stride, uint32_t keep, uint32_t samples,
+                                                                  unsigned long long* converted) {
         uint32_t k = 0;
+        unsigned long long conv = 0ull;
 #pragma unroll 1
         while (k < samples) {
             if (left == 0) { luxury_skip<NSKIP>(); left = 24; }
@@ -141,43 +155,38 @@ struct Ranlux {
                 if (k < keep) {
 #pragma unroll
                     for (int q = 0; q < 6; q++) {
-                        float o[4];
+                        uint32_t w[4], nx[4];
 #pragma unroll
                         for (int e = 0; e < 4; e++) {
                             const int n = 4 * q + e;
-                            const uint32_t x = s[23 - n];
-                            const uint32_t nx = (n <= 8) ? old[8 - n] : s[32 - n];
-                            float f = __uint2float_rn(x) * 2.3283064365386963e-10f;
-                            if (x < (4096u << 8)) {
-                                f = __fadd_rn(f, __fmul_rn(5.9604644775390625e-8f, __uint2float_rn(nx) * 2.3283064365386963e-10f));
-                                if (f == 0.0f) f = 5.9604644775390625e-8f * 5.9604644775390625e-8f;
-                            }
-                            o[e] = f;
+                            w[e] = s[23 - n];
+                            nx[e] = (n <= 8) ? old[8 - n] : s[32 - n];
                         }
-                        if (k + q < keep) out[(k + q) * stride] = make_float4(o[0], o[1], o[2], o[3]);
+                        if (min(min(w[0], w[1]), min(w[2], w[3])) < (4096u << 8)) {
+#pragma unroll
+                            for (int e = 0; e < 4; e++) w[e] = __float_as_uint(to_float(w[e], nx[e]));
+                            conv |= 1ull << (k + q);
+                        }
+                        if (k + q < keep) out[(k + q) * stride] = make_uint4(w[0], w[1], w[2], w[3]);
                     }
                 }
                 k += 6; left = 0;
             } else {
                 asm volatile(QCD_SWB_PRE QCD_SWB_4 QCD_SWB_POST : QCD_SWB_OPERANDS(s, carry));
                 if (k < keep) {
-                    float o[4];
+                    uint32_t w[4] = { s[23], s[22], s[21], s[20] };
+                    if (min(min(w[0], w[1]), min(w[2], w[3])) < (4096u << 8)) {
 #pragma unroll
-                    for (int e = 0; e < 4; e++) {
-                        const uint32_t x = s[23 - e];
-                        float f = __uint2float_rn(x) * 2.3283064365386963e-10f;
-                        if (x < (4096u << 8)) {
-                            f = __fadd_rn(f, __fmul_rn(5.9604644775390625e-8f, __uint2float_rn(s[8 - e]) * 2.3283064365386963e-10f));
-                            if (f == 0.0f) f = 5.9604644775390625e-8f * 5.9604644775390625e-8f;
-                        }
-                        o[e] = f;
+                        for (int e = 0; e < 4; e++) w[e] = __float_as_uint(to_float(w[e], s[8 - e]));
+                        conv |= 1ull << k;
                     }
-                    out[k * stride] = make_float4(o[0], o[1], o[2], o[3]);
+                    out[k * stride] = make_uint4(w[0], w[1], w[2], w[3]);
                 }
                 rotate<4>();
                 left -= 4; k++;
             }
         }
+        *converted = conv;
     }
     // advance by one float4 sample without converting
     template <int NSKIP> __device__ __forceinline__ void skip4() {

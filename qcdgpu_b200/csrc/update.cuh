@@ -92,11 +92,18 @@ struct PrnRanlux {
 // during phase 2, which is what lets three blocks share an SM.
 struct PrnSmem {
     struct Args { int dummy; };
-    const float4* p; uint32_t k, stride;
-    __device__ __forceinline__ PrnSmem(const float4* base, uint32_t stride_) : p(base), k(0), stride(stride_) {}
-    __device__ __forceinline__ F4 trial() { float4 r = p[k * stride]; k++; return { r.x, r.y, r.z, r.w }; }
-    __device__ __forceinline__ F4 direction() { return trial(); }
-    __device__ __forceinline__ F4 peek() { float4 r = p[k * stride]; return { r.x, r.y, r.z, r.w }; }
+    const uint4* p; uint32_t k, stride; unsigned long long converted;
+    __device__ __forceinline__ PrnSmem(const uint4* base, uint32_t stride_, unsigned long long conv) : p(base), k(0), stride(stride_), converted(conv) {}
+    // parked samples are raw seeds << 8 unless flagged as already converted (run_pass, prng.cuh)
+    __device__ __forceinline__ F4 get(uint32_t i) const {
+        uint4 r = p[i * stride];
+        if ((converted >> i) & 1ull) return { __uint_as_float(r.x), __uint_as_float(r.y), __uint_as_float(r.z), __uint_as_float(r.w) };
+        const float c = 2.3283064365386963e-10f;      // (seed << 8) * 2^-32 = seed * 2^-24, exact
+        return { __uint2float_rn(r.x) * c, __uint2float_rn(r.y) * c, __uint2float_rn(r.z) * c, __uint2float_rn(r.w) * c };
+    }
+    __device__ __forceinline__ F4 trial() { return get(k++); }
+    __device__ __forceinline__ F4 direction() { return get(k++); }
+    __device__ __forceinline__ F4 peek() const { return get(k); }
     __device__ __forceinline__ void burn() { k++; }
     __device__ __forceinline__ void finish() {}
     static constexpr bool kGid = false;
@@ -602,15 +609,16 @@ template <int SUN, typename R, int MU, bool TBC, int NSKIP>
 __global__ void __launch_bounds__(kUpdateThreads, 3)
 update_kernel_rlx(R* __restrict__ table, const R* __restrict__ params, const __grid_constant__ Geom g, int odd,
                   uint32_t* __restrict__ rtable, uint32_t instances, uint32_t samples, uint32_t keep) {
-    extern __shared__ float4 prn_smem[];
+    extern __shared__ uint4 prn_smem[];
     uint32_t GID = blockIdx.x * blockDim.x + threadIdx.x;
     if (GID >= g.nthreads) return;
     GID = remap_gid(g, GID);
     prefetch_site_head<SUN, R, MU>(table, g, parity_gid(g, GID, odd != 0));
+    unsigned long long converted = 0ull;
     if (g.debug_skip != 1u) {   // phase 1: the pass's whole RANLUX work
         Ranlux r;
         ranlux_load(r, rtable, instances, GID);
-        r.template run_pass<NSKIP>(prn_smem + threadIdx.x, kUpdateThreads, keep, samples);
+        r.template run_pass<NSKIP>(prn_smem + threadIdx.x, kUpdateThreads, keep, samples, &converted);
         ranlux_store(r, rtable, instances, GID);
     }
     if (g.debug_skip == 2u) return;
@@ -618,7 +626,7 @@ update_kernel_rlx(R* __restrict__ table, const R* __restrict__ params, const __g
     const R beta = params[0];
     const Twist<R> tw = make_twist<SUN, R, TBC>(params);
     uint32_t gindex = parity_gid(g, GID, odd != 0);
-    PrnSmem prn(prn_smem + threadIdx.x, kUpdateThreads);
+    PrnSmem prn(prn_smem + threadIdx.x, kUpdateThreads, converted);
     if (SUN == 3) update_site_su3<R, MU, TBC, PrnSmem>(table, g, beta, tw, gindex, prn);
     else          update_site_su2<R, MU, TBC, PrnSmem>(table, g, beta, tw, gindex, prn);
 }

@@ -30,7 +30,7 @@ static cudaError_t launch_rlx(const UpdateArgs& a, cudaStream_t st) {
     uint32_t keep = 3u * (a.geom.nhit + 1u) * a.geom.nhitpar;
     if (keep > a.prn_samples) keep = a.prn_samples;
     size_t smem = size_t(keep) * kUpdateThreads * sizeof(float4);
-    if (smem > 200 * 1024) {   // does not fit: state-in-registers variant
+    if (smem > 200 * 1024 || keep > 64) {   // does not fit (smem, or the 64-bit "already converted" mask): state-in-registers variant
         PrnRanlux<223>::Args pa = { a.prn_table, a.prn_instances, a.prn_samples };
         return launch_one<TBC, PrnRanlux<223>>(a, pa, st);
     }
