@@ -29,6 +29,7 @@ sys.path.insert(0, ROOT)
 
 WORKLOAD = dict(group=3, dims=(64, 64, 64, 64), precision=1, beta=6.0, nhit=10, prng="RANLUX3", randseries=54, ints=1)
 BYTES_PER_LINK_UPDATE = 9 * 96      # SU(3) 2-row fp64: 4 V link reads + V/2 link writes per pass, 8 passes / 4 V links
+NCU_DRAM_BYTES_PER_LAUNCH = 8.168836e9 + 1.779877e9   # profiles/r01_ncu_update_v3_lazy_conversion.json
 FLOPS_PER_LINK_UPDATE = 4700
 
 
@@ -211,6 +212,10 @@ def native_single(args):
     peak, peak_kind = measured_peaks()
     bytes_per_launch = 4.5 * V * 96.0
     achieved = bytes_per_launch / (upd_ns * 1e-9) / 1e9
+    # DRAM bytes of one launch of that kernel from the committed ncu --set full capture (same command, 64^4 fused only)
+    traffic, traffic_src = None, None
+    if tuple(dims) == (64, 64, 64, 64) and not args.buffered and not args.materialize:
+        traffic, traffic_src = NCU_DRAM_BYTES_PER_LAUNCH, "profiles/r01_ncu_update_v3_lazy_conversion.json (dram__bytes_read.sum + dram__bytes_write.sum)"
     regs = g.update_kernel_registers(m.program_update, 0, 2 if not args.buffered else 0)
     plq_total = float(plq.sum() / (6.0 * V)) if plq is not None else None
     # ---- CPU baseline: the reference itself, 1 core, bounded sample
@@ -224,7 +229,8 @@ def native_single(args):
                    "l2_policy": "inputs_larger_than_L2 (link table 6.44 GB vs 126 MB L2)", "sweeps_per_s": args.steps / (ms * 1e-3),
                    "plaquette_after_run": plq_total, "update_kernel_registers": regs},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": None, "peak_source": peak_kind, "kernel": "update_kernel<3,double,MU,false,PrnRanlux<223>>",
+                     "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_kind,
+                     "kernel": ("update_kernel_rlx<3,double,MU,false,223>" if not args.buffered else "update_kernel<3,double,MU,false,PrnBuffered>"),
                      "avg_launch_us": upd_ns / 1e3, "algorithmic_bytes_per_launch": bytes_per_launch,
                      "fp64_gflops": FLOPS_PER_LINK_UPDATE * (V / 2) / (upd_ns * 1e-9) / 1e9,
                      "reunitarisation_launch_us": gs_ns / 1e3},

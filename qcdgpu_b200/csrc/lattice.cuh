@@ -229,6 +229,16 @@ template <typename R> __device__ __forceinline__ V4<R> su2_dag(const V4<R>& u) {
 // ---------------------------------------------------------------- twisted loads
 template <typename R> struct Twist { R c1, s1, c2, s2; };   // cos/sin((phi+omega)/2), cos/sin((omega-phi)/2); SU(2): c1,s1 of phi/2
 
+// twist of a Y-link at the x boundary: the reference multiplies (uv1,uv2) lanes xyz by e^{i(phi+omega)/2} and lane w (= v3)
+// by e^{i(omega-phi)/2}, uv3 (= v1,v2) by e^{i(omega-phi)/2}  (su3_matrix_memory.cl:64-97)
+template <typename R>
+__device__ __forceinline__ void twist3(M3r2<R>& m, const Geom& g, uint32_t x, const Twist<R>& tw) {
+    if (twisted_x(g, x)) {
+        const Cx<R> p1 = { tw.c1, tw.s1 }, p2 = { tw.c2, tw.s2 };
+#pragma unroll
+        for (int j = 0; j < 3; j++) { m.e[0][j] = cmul(m.e[0][j], p1); m.e[1][j] = cmul(m.e[1][j], p2); }
+    }
+}
 // lattice_table_3 (su3_matrix_memory.cl:43-115): rows of diag(e^{i(phi+omega)/2}, e^{i(omega-phi)/2}, e^{-i omega}) * U
 template <typename R, int DIR, bool TBC>
 __device__ __forceinline__ M3r2<R> load3(const R* table, const Geom& g, uint32_t gindex, uint32_t x, const Twist<R>& tw) {
@@ -236,15 +246,7 @@ __device__ __forceinline__ M3r2<R> load3(const R* table, const Geom& g, uint32_t
     V4<R> b = ld_plane(table, g, gindex, DIR + 4);
     V4<R> c = ld_plane(table, g, gindex, DIR + 8);
     M3r2<R> m = unpack3(a, b, c);
-    if (TBC && DIR == 1) {
-        if (twisted_x(g, x)) {
-            // the reference multiplies (uv1,uv2) lanes xyz by e^{i(phi+omega)/2} and lane w (= v3) by e^{i(omega-phi)/2},
-            // uv3 (= v1,v2) by e^{i(omega-phi)/2}  (su3_matrix_memory.cl:64-97)
-            const Cx<R> p1 = { tw.c1, tw.s1 }, p2 = { tw.c2, tw.s2 };
-#pragma unroll
-            for (int j = 0; j < 3; j++) { m.e[0][j] = cmul(m.e[0][j], p1); m.e[1][j] = cmul(m.e[1][j], p2); }
-        }
-    }
+    if (TBC && DIR == 1) twist3(m, g, x, tw);
     return m;
 }
 // lattice_table_2 (su2_matrix_memory.cl:55-96): Omega * U with Omega = (cos phi/2, 0, sin phi/2, 0)

@@ -6,7 +6,7 @@
 namespace qcd {
 
 cudaError_t launch_reduce_double2(const double2* table, uint32_t off, uint32_t size, double2* dst, uint32_t index, cudaStream_t st) {
-    reduce_double2_kernel<<<1, 256, 0, st>>>(table, off, size, dst, index);
+    reduce_double2_kernel<<<1, 1024, 0, st>>>(table, off, size, dst, index);
     return cudaGetLastError();
 }
 cudaError_t launch_clear_double2(double2* p, uint32_t n, cudaStream_t st) {

@@ -29,6 +29,7 @@ namespace qcd {
 // Reference-layout buffer: thread GID reads prns[GID + k*PRNGSTEP]  (su3_update_cl.cl:613-617, 679)
 struct PrnBuffered {
     struct Args { const float4* prns; };
+    // (keeping the next two slots in flight in registers was measured slower: 3.10 vs 2.97 ms per 64^4 fp64 pass)
     const float4* p; uint32_t ind, step;
     __device__ __forceinline__ PrnBuffered(const Args& a, const Geom& g, uint32_t GID, uint32_t) : p(a.prns), ind(GID), step(g.prngstep) {}
     __device__ __forceinline__ F4 trial() { float4 r = __ldg(p + ind); ind += step; return { r.x, r.y, r.z, r.w }; }
@@ -405,6 +406,130 @@ __device__ __forceinline__ M3<R> staple3(const R* table, const Geom& g, const Co
     staple3_plane<R, MU, n2, TBC>(table, g, p.x, gindex, s2, tw, S, false);
     return S.get();
 }
+// ---------------------------------------------------------------- SU(3) link staging through shared memory
+// Each thread owns a ring of QCD_STAGE_K link slots (3 vec4 each) in shared memory.  The 19 links a site update reads
+// (18 staple links + its own) are copied global -> shared by cp.async (LDGSTS) QCD_STAGE_K links ahead of their use, so
+// their memory latency is covered by the products of the preceding links without holding any register.
+// Layout: 16-byte unit u of thread t at (u * kUpdateThreads + t) * 16: conflict-free LDS.128 / LDGSTS.128.
+// Measured (64^4 fp64, PRNs from memory): K=3 3.12 ms, K=6 3.12 ms per pass against 2.97 ms for plain LDG.256 loads --
+// each LDGSTS.128 of a warp touches 32 half-used sectors, L1 throughput goes 36 % -> 75 % and eats the latency gain
+// (cp.async.cg: 3.73 ms).  Kept as a build-time experiment (QCD_NVCC_EXTRA=-DQCD_STAGE_K=3), off by default.
+#ifndef QCD_STAGE_K
+#define QCD_STAGE_K 0
+#endif
+constexpr int kUpdateThreads = 128;
+constexpr int kStageK = QCD_STAGE_K;
+template <typename R> constexpr size_t stage_bytes() { return size_t(kStageK) * 3 * (sizeof(V4<R>) / 16) * 16 * kUpdateThreads; }
+
+template <int MU> __host__ __device__ constexpr int plane_nu(int pl) {
+    return pl == 0 ? PlaneOrder<MU>::n0 : pl == 1 ? PlaneOrder<MU>::n1 : PlaneOrder<MU>::n2;
+}
+template <typename R, int MU, bool TBC> struct Su3Stage {
+    static constexpr int H = sizeof(V4<R>) / 16;
+    static constexpr int NLINKS = 19;
+    const char* sm;         // this thread's first unit (generic pointer into shared memory)
+    const R* table;
+    uint32_t rowsize, gindex, px;
+    PlaneSites s0, s1, s2;
+
+    template <int SLOT> __device__ __forceinline__ void copy_link(uint32_t gidx, int dir) const {
+        const uint32_t sa = (uint32_t)__cvta_generic_to_shared(sm);
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            const char* src = reinterpret_cast<const char*>(table + 4 * (size_t(gidx) + size_t(dir + 4 * k) * rowsize));
+#pragma unroll
+            for (int h = 0; h < H; h++)
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::
+                             "r"(sa + uint32_t(((SLOT * 3 + k) * H + h) * 16 * kUpdateThreads)), "l"(src + 16 * h) : "memory");
+        }
+    }
+    // link L of the site's read sequence: plane L/6, {U_mu(p+nu), U_nu(p), U_nu(p+mu), U_nu(p-nu+mu), U_mu(p-nu), U_nu(p-nu)}; 18 = U_mu(p)
+    template <int L> __device__ __forceinline__ void issue() const {
+        if constexpr (L < 18) {
+            constexpr int pl = L / 6, i = L % 6, NU = plane_nu<MU>(pl);
+            const PlaneSites& s = (pl == 0) ? s0 : (pl == 1) ? s1 : s2;
+            if constexpr (i == 0) copy_link<L % kStageK>(s.g_pnu, MU);
+            if constexpr (i == 1) copy_link<L % kStageK>(gindex, NU);
+            if constexpr (i == 2) copy_link<L % kStageK>(s.g_pmu, NU);
+            if constexpr (i == 3) copy_link<L % kStageK>(s.g_pmnmu, NU);
+            if constexpr (i == 4) copy_link<L % kStageK>(s.g_pmn, MU);
+            if constexpr (i == 5) copy_link<L % kStageK>(s.g_pmn, NU);
+        } else if constexpr (L == 18) {
+            copy_link<L % kStageK>(gindex, MU);
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");   // also for L > 18: one (empty) group per link keeps the wait count fixed
+    }
+    template <int L> __device__ __forceinline__ M3r2<R> take(const Geom& g, const Twist<R>& tw) const {
+        asm volatile("cp.async.wait_group %0;" :: "n"(kStageK - 1) : "memory");
+        constexpr int SLOT = L % kStageK;
+        V4<R> v[3];
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            if constexpr (H == 2) {
+                const double2 lo = *reinterpret_cast<const double2*>(sm + ((SLOT * 3 + k) * 2 + 0) * 16 * kUpdateThreads);
+                const double2 hi = *reinterpret_cast<const double2*>(sm + ((SLOT * 3 + k) * 2 + 1) * 16 * kUpdateThreads);
+                v[k].x = lo.x; v[k].y = lo.y; v[k].z = hi.x; v[k].w = hi.y;
+            } else {
+                const float4 q = *reinterpret_cast<const float4*>(sm + (SLOT * 3 + k) * 16 * kUpdateThreads);
+                v[k].x = q.x; v[k].y = q.y; v[k].z = q.z; v[k].w = q.w;
+            }
+        }
+        M3r2<R> m = unpack3(v[0], v[1], v[2]);
+        // which links are Y-links (the only twisted ones) and at which x they sit
+        constexpr int pl = (L < 18) ? L / 6 : 0, i = L % 6;
+        constexpr int DIR = (L == 18) ? MU : ((i == 0 || i == 4) ? MU : plane_nu<MU>(pl));
+        if constexpr (TBC && DIR == 1) {
+            const PlaneSites& s = (pl == 0) ? s0 : (pl == 1) ? s1 : s2;
+            const uint32_t x = (L == 18 || i == 1) ? px : (i == 0) ? s.x_pnu : (i == 2) ? s.x_pmu : (i == 3) ? s.x_pmnmu : s.x_pmn;
+            twist3(m, g, x, tw);
+        }
+        asm volatile("" ::: "memory");
+        issue<L + kStageK>();
+        return m;
+    }
+    __device__ __forceinline__ void begin(const void* smem_thread, const R* tab, const Geom& g, uint32_t gi) {
+        sm = reinterpret_cast<const char*>(smem_thread); table = tab; rowsize = g.rowsize; gindex = gi;
+        Coord p = gid_to_coords(g, gi);
+        px = p.x;
+        Coord pmu = nb_plus<MU>(g, p);
+        s0 = plane_sites<MU, PlaneOrder<MU>::n0>(g, p, pmu);
+        s1 = plane_sites<MU, PlaneOrder<MU>::n1>(g, p, pmu);
+        s2 = plane_sites<MU, PlaneOrder<MU>::n2>(g, p, pmu);
+        prologue<0>();
+    }
+    template <int L> __device__ __forceinline__ void prologue() const {
+        if constexpr (L < kStageK) { issue<L>(); prologue<L + 1>(); }
+    }
+    template <int PL> __device__ __forceinline__ void plane(const Geom& g, const Twist<R>& tw, M3<R>& S) const {
+        {   // forward: A B^+ C^+ = A (C B)^+
+            M3r2<R> B = take<6 * PL + 0>(g, tw);
+            M3<R> Bf = complete(B), D, F;
+            M3r2<R> C = take<6 * PL + 1>(g, tw);
+            mul_r2_full(C, Bf, D);
+            M3r2<R> A = take<6 * PL + 2>(g, tw);
+            mul_r2_dag(A, D, F);
+            if (PL == 0) S = F; else acc3(S, F);
+        }
+        {   // backward: A2^+ B2^+ C2 = (B2 A2)^+ C2
+            M3r2<R> A2 = take<6 * PL + 3>(g, tw);
+            M3<R> Af = complete(A2), E, G;
+            M3r2<R> B2 = take<6 * PL + 4>(g, tw);
+            mul_r2_full(B2, Af, E);
+            M3r2<R> C2 = take<6 * PL + 5>(g, tw);
+            M3<R> Cf = complete(C2);
+            mul_dag_full(E, Cf, G);
+            acc3(S, G);
+        }
+    }
+    // staple sum, then the site's own link
+    __device__ __forceinline__ void staple_and_link(const Geom& g, const Twist<R>& tw, M3<R>& S, M3r2<R>& m0) const {
+        plane<0>(g, tw, S);
+        plane<1>(g, tw, S);
+        plane<2>(g, tw, S);
+        m0 = take<18>(g, tw);
+    }
+};
+
 // first things a site update will read: its own link and the first plane (issued before the generator phase)
 template <int SUN, typename R, int MU>
 __device__ __forceinline__ void prefetch_site_head(const R* table, const Geom& g, uint32_t gindex) {
@@ -510,11 +635,26 @@ __device__ __forceinline__ V4<R> staple2(const R* table, const Geom& g, const Co
 }
 
 // ---------------------------------------------------------------- site updates
+template <typename R, int MU, class Prn>
+__device__ __forceinline__ void heatbath_su3(R* table, const Geom& g, R beta, uint32_t gindex, const M3r2<R>& m0, const M3<R>& S, Prn& prn);
 template <typename R, int MU, bool TBC, class Prn>
 __device__ __forceinline__ void update_site_su3(R* table, const Geom& g, R beta, const Twist<R>& tw, uint32_t gindex, Prn& prn) {
     Coord p = gid_to_coords(g, gindex);
     M3r2<R> m0 = load3<R, MU, TBC>(table, g, gindex, p.x, tw);
     M3<R> S = staple3<R, MU, TBC>(table, g, p, gindex, tw);
+    heatbath_su3<R, MU, Prn>(table, g, beta, gindex, m0, S, prn);
+}
+// same with the links arriving through the shared-memory ring (begin() was called earlier)
+template <typename R, int MU, bool TBC, class Prn>
+__device__ __forceinline__ void update_site_su3_staged(R* table, const Geom& g, R beta, const Twist<R>& tw,
+                                                       const Su3Stage<R, MU, TBC>& stage, Prn& prn) {
+    M3<R> S;
+    M3r2<R> m0;
+    stage.staple_and_link(g, tw, S, m0);
+    heatbath_su3<R, MU, Prn>(table, g, beta, stage.gindex, m0, S, prn);
+}
+template <typename R, int MU, class Prn>
+__device__ __forceinline__ void heatbath_su3(R* table, const Geom& g, R beta, uint32_t gindex, const M3r2<R>& m0, const M3<R>& S, Prn& prn) {
     M3<R> U;
 #pragma unroll
     for (int j = 0; j < 3; j++) { U.e[0][j] = m0.e[0][j]; U.e[1][j] = m0.e[1][j]; }
@@ -571,7 +711,6 @@ __device__ __forceinline__ void overrelax_site_su2(R* table, const Geom& g, uint
     st_plane(table, g, gindex, MU, r);
 }
 
-constexpr int kUpdateThreads = 128;
 
 // twist phases from lattice_parameters[1..2] (su3_matrix_memory.cl:64-66, su2_matrix_memory.cl:73-75)
 template <int SUN, typename R, bool TBC>
@@ -601,7 +740,12 @@ update_kernel(R* __restrict__ table, const R* __restrict__ params, const __grid_
     const Twist<R> tw = make_twist<SUN, R, TBC>(params);
     uint32_t gindex = parity_gid(g, GID, odd != 0);
     Prn prn(pargs, g, GID, gindex);
-    if (SUN == 3) update_site_su3<R, MU, TBC, Prn>(table, g, beta, tw, gindex, prn);
+    if constexpr (SUN == 3 && kStageK > 0) {
+        extern __shared__ uint4 dyn_smem[];
+        Su3Stage<R, MU, TBC> stage;
+        stage.begin(dyn_smem + threadIdx.x, table, g, gindex);
+        update_site_su3_staged<R, MU, TBC, Prn>(table, g, beta, tw, stage, prn);
+    } else if constexpr (SUN == 3) update_site_su3<R, MU, TBC, Prn>(table, g, beta, tw, gindex, prn);
     else          update_site_su2<R, MU, TBC, Prn>(table, g, beta, tw, gindex, prn);
     prn.finish();
 }

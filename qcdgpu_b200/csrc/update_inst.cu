@@ -20,7 +20,14 @@ template <bool TBC, class Prn>
 static cudaError_t launch_one(const UpdateArgs& a, typename Prn::Args pa, cudaStream_t st) {
     dim3 block(kUpdateThreads), grid((a.geom.nthreads + kUpdateThreads - 1) / kUpdateThreads);
     if (grid.x == 0) return cudaSuccess;
-    update_kernel<INST_SUN, RealT, INST_MU, TBC, Prn><<<grid, block, 0, st>>>(
+    const size_t smem = (INST_SUN == 3 && kStageK > 0) ? stage_bytes<RealT>() : 0;   // link ring (update.cuh, Su3Stage)
+    static bool configured = false;
+    if (smem > 48 * 1024 && !configured) {
+        cudaError_t e = cudaFuncSetAttribute(update_kernel<INST_SUN, RealT, INST_MU, TBC, Prn>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        configured = true;
+    }
+    update_kernel<INST_SUN, RealT, INST_MU, TBC, Prn><<<grid, block, smem, st>>>(
         static_cast<RealT*>(a.table), static_cast<const RealT*>(a.params), a.geom, a.odd, pa);
     return cudaGetLastError();
 }
