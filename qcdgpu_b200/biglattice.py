@@ -379,7 +379,7 @@ def bench_main(args, workload):
                                    f"({dims[0]} slices per GPU), halo exchange after each of the 8 passes (NCCL send/recv, overlapped with the "
                                    f"interior update), beta=6.0, NHIT=10, RANLUX3, cold start",
                        "l2_policy": "inputs_larger_than_L2", "sweeps_per_s": args.steps / (ms * 1e-3),
-                       "halo_bytes_per_pass_per_gpu": 2 * B.halo_bytes_per_pass, "plaquette_after_run": float(plq.sum() / (6.0 * V_total))},
+                       "halo_bytes_per_pass_per_gpu": B.halo_bytes_per_pass, "plaquette_after_run": float(plq.sum() / (6.0 * V_total))},
             "roofline": {"bound": "hbm", "achieved": bytes_per_s, "peak": peak, "unit": "GB/s", "frac": bytes_per_s / peak,
                          "traffic": None, "peak_source": peak_kind, "note": "per GPU, whole sweep (update + halo + reunitarisation)"},
             "e2e": {"value": e2e, "unit": "link-updates/s", "h2d_bytes_per_step": int(params.size) * world, "d2h_bytes_per_step": 16 * world},
