@@ -35,12 +35,15 @@ struct ProgramCfg {
     int rl_skip = 223;
     int prng_precision = 0;
     bool fmunu = false, f0mu = false;
+    int fmunu_gen1 = 0, fmunu_gen2 = 0;      // -D FMUNU1/2/4 and FMUNU5/6/7 (0: lambda_3 resp. lambda_8)
+    uint32_t plk = 0, plk_axis[3] = { 0, 0, 0 };   // -D PLK, PLKx, PLKy, PLKz (slice-resolved kernels)
     bool has_lattice = false;
 };
 
 enum KernelKind {
     K_NONE = 0, K_INIT_COLD, K_INIT_GID, K_INIT_HOT, K_GRAMSCHMIDT, K_UPDATE, K_OVERRELAX, K_CLEAR,
     K_MEASURE, K_REDUCE_MEAS, K_MEASURE_PLQ, K_REDUCE_PLQ, K_POLYAKOV, K_REDUCE_POLYAKOV,
+    K_POLYAKOV_DIFF, K_REDUCE_POLYAKOV_DIFF, K_WILSON, K_REDUCE_WILSON,
     K_RANLUX_INIT, K_PRODUCE
 };
 
@@ -158,6 +161,16 @@ void parse_options(const char* opt, ProgramCfg& c) {
         else if (name == "PRNG_PRECISION") c.prng_precision = (int)v;
         else if (name == "FMUNU") c.fmunu = true;
         else if (name == "F0MU") c.f0mu = true;
+        else if (name == "FMUNU1") c.fmunu_gen1 = 1;
+        else if (name == "FMUNU2") c.fmunu_gen1 = 2;
+        else if (name == "FMUNU4") c.fmunu_gen1 = 4;
+        else if (name == "FMUNU5") c.fmunu_gen2 = 5;
+        else if (name == "FMUNU6") c.fmunu_gen2 = 6;
+        else if (name == "FMUNU7") c.fmunu_gen2 = 7;
+        else if (name == "PLK") c.plk = (uint32_t)v;
+        else if (name == "PLKx") c.plk_axis[0] = (uint32_t)v;
+        else if (name == "PLKy") c.plk_axis[1] = (uint32_t)v;
+        else if (name == "PLKz") c.plk_axis[2] = (uint32_t)v;
     }
 }
 
@@ -208,6 +221,10 @@ const NameMap kNames[] = {
     { "lattice_measurement", K_MEASURE, 0, 0, 0 }, { "reduce_measurement_double2", K_REDUCE_MEAS, 0, 0, 0 },
     { "lattice_measurement_plq", K_MEASURE_PLQ, 0, 0, 0 }, { "reduce_measurement_plq_double2", K_REDUCE_PLQ, 0, 0, 0 },
     { "lattice_polyakov", K_POLYAKOV, 0, 0, 0 }, { "reduce_polyakov_double2", K_REDUCE_POLYAKOV, 0, 0, 0 },
+    { "lattice_polyakov_diff_x", K_POLYAKOV_DIFF, 0, 0, 0 }, { "lattice_polyakov_diff_y", K_POLYAKOV_DIFF, 1, 0, 0 }, { "lattice_polyakov_diff_z", K_POLYAKOV_DIFF, 2, 0, 0 },
+    { "reduce_polyakov_diff_x_double2", K_REDUCE_POLYAKOV_DIFF, 0, 0, 0 }, { "reduce_polyakov_diff_y_double2", K_REDUCE_POLYAKOV_DIFF, 1, 0, 0 },
+    { "reduce_polyakov_diff_z_double2", K_REDUCE_POLYAKOV_DIFF, 2, 0, 0 },
+    { "lattice_measurement_wilson", K_WILSON, 0, 0, 0 }, { "reduce_wilson_double2", K_REDUCE_WILSON, 0, 0, 0 },
     { "ranlux_init", K_RANLUX_INIT, 0, 0, 0 },
     { "ranlux", K_PRODUCE, 0, 0, -1 }, { "xor128", K_PRODUCE, 0, 0, PRN_XOR128 }, { "pm", K_PRODUCE, 0, 0, PRN_PM }, { "mrg32k3a", K_PRODUCE, 0, 0, PRN_MRG32K3A },
 };
@@ -332,14 +349,23 @@ int launch_kernel(qgpu* h, int kid) {
             a.table = buf_ptr(h, k, 0); a.params = buf_ptr(h, k, 2);
             double2* out = (double2*)buf_ptr(h, k, 1);
             if (!a.table || !a.params || !out) return fail(h, "kernel %s: arguments (table, measurement, parameters) not set", k.name.c_str());
-            if (c.fmunu || c.f0mu) return fail(h, "kernel %s: the FMUNU/F0MU variants are not implemented in qcdgpu_b200", k.name.c_str());
             a.geom = make_geom(c); a.tbc = c.tbc ? 1 : 0;
             if (k.kind == K_MEASURE) a.out_action = out; else a.out_plq = out;
             a.first_site = c.biglat ? a.geom.n234 : 0;
             a.nsites = c.biglat ? (c.n1 - 2) * a.geom.n234 : a.geom.sites;
             a.block = (uint32_t)k.local0;
             size_t blocks = (a.nsites + a.block - 1) / a.block;
-            if (h->buffers[buf_id(k, 1)].capacity < blocks * 16) return fail(h, "kernel %s: measurement buffer too small (%zu partials needed)", k.name.c_str(), blocks);
+            size_t slots = blocks;
+            if (k.kind == K_MEASURE_PLQ && (c.fmunu || c.f0mu)) {      // only the plaquette kernel has Fmunu variants (sun_measurements_cl.cl:710-1175)
+                int offset = 0;
+                if (c.biglat) return fail(h, "kernel %s: FMUNU/F0MU with BIGLAT is not implemented in qcdgpu_b200", k.name.c_str());
+                if (!arg_int(k, 4, &offset) || offset < (int)blocks) return fail(h, "kernel %s: argument 4 (offset) not set or smaller than the partial count", k.name.c_str());
+                a.fmode = c.fmunu ? 1 : 2; a.offset = (uint32_t)offset;
+                if (c.sun == 3) { a.gen1 = c.fmunu_gen1 ? c.fmunu_gen1 : 3; a.gen2 = c.fmunu_gen2 ? c.fmunu_gen2 : 8; }
+                else            { a.gen1 = (c.fmunu_gen1 == 1) ? 1 : 3; a.gen2 = 2; }
+                slots = 6 * (size_t)offset + blocks;
+            }
+            if (h->buffers[buf_id(k, 1)].capacity < slots * 16) return fail(h, "kernel %s: measurement buffer too small (%zu partials needed)", k.name.c_str(), slots);
             CUDA_OK(h, launch_measure(c.sun, prec, a, st));
             break;
         }
@@ -355,6 +381,73 @@ int launch_kernel(qgpu* h, int kid) {
             if (k.args.size() < 5 || k.args[3].type != Arg::U32X4 || !arg_int(k, 4, &index)) return fail(h, "kernel %s: arguments (param, index) not set", k.name.c_str());
             if (!buf_ptr(h, k, 0) || !buf_ptr(h, k, 1)) return fail(h, "kernel %s: buffers not set", k.name.c_str());
             CUDA_OK(h, launch_reduce_double2((const double2*)buf_ptr(h, k, 0), 0, k.args[3].u4[0], (double2*)buf_ptr(h, k, 1), (uint32_t)index, st));
+            if (c.fmunu || c.f0mu) {   // six projected sums: partials at q*offset, results at index + q*offset2  (sun_measurements_cl.cl:1322-1357)
+                const uint32_t size = k.args[3].u4[0], offset = k.args[3].u4[1], offset2 = k.args[3].u4[2];
+                if (h->buffers[buf_id(k, 1)].capacity < ((size_t)index + 6 * (size_t)offset2 + 1) * 16) return fail(h, "kernel %s: result buffer too small for the Fmunu sums", k.name.c_str());
+                for (uint32_t q = 1; q <= 6; q++) {
+                    CUDA_OK(h, launch_reduce_double2((const double2*)buf_ptr(h, k, 0), q * offset, size, (double2*)buf_ptr(h, k, 1), (uint32_t)index + q * offset2, st));
+                    h->launches++;
+                }
+            }
+            break;
+        }
+        case K_WILSON: {
+            MeasureArgs a;
+            memset(&a, 0, sizeof(a));
+            a.table = buf_ptr(h, k, 0); a.params = buf_ptr(h, k, 2);
+            a.out_plq = (double2*)buf_ptr(h, k, 1);
+            if (!a.table || !a.params || !a.out_plq) return fail(h, "kernel %s: arguments (table, measurement, parameters) not set", k.name.c_str());
+            if (c.biglat) return fail(h, "kernel %s: the BIGLAT Wilson-loop kernels are not implemented in qcdgpu_b200", k.name.c_str());
+            if (h->buffers[buf_id(k, 2)].bytes < 5 * (size_t)(prec ? 8 : 4)) return fail(h, "kernel %s: lattice_parameters must hold wilson_R, wilson_T at [3], [4]", k.name.c_str());
+            a.geom = make_geom(c); a.tbc = c.tbc ? 1 : 0; a.wilson = 1;
+            a.first_site = 0; a.nsites = a.geom.sites; a.block = (uint32_t)k.local0;
+            size_t blocks = (a.nsites + a.block - 1) / a.block;
+            if (h->buffers[buf_id(k, 1)].capacity < blocks * 16) return fail(h, "kernel %s: measurement buffer too small (%zu partials needed)", k.name.c_str(), blocks);
+            CUDA_OK(h, launch_measure(c.sun, prec, a, st));
+            break;
+        }
+        case K_REDUCE_WILSON: {
+            int size = 0, index = 0;
+            if (!arg_int(k, 3, &size) || !arg_int(k, 4, &index)) return fail(h, "kernel %s: arguments (size, index) not set", k.name.c_str());
+            if (!buf_ptr(h, k, 0) || !buf_ptr(h, k, 1)) return fail(h, "kernel %s: buffers not set", k.name.c_str());
+            if (h->buffers[buf_id(k, 1)].capacity < ((size_t)index + 1) * 8) return fail(h, "kernel %s: result buffer too small", k.name.c_str());
+            CUDA_OK(h, launch_reduce_double_x((const double2*)buf_ptr(h, k, 0), (uint32_t)size, (double*)buf_ptr(h, k, 1), (uint32_t)index, st));
+            break;
+        }
+        case K_POLYAKOV_DIFF: {
+            PolyakovArgs a;
+            memset(&a, 0, sizeof(a));
+            a.table = buf_ptr(h, k, 0); a.out = (double2*)buf_ptr(h, k, 1); a.params = buf_ptr(h, k, 2);
+            if (!a.table || !a.out || !a.params) return fail(h, "kernel %s: arguments not set", k.name.c_str());
+            if (c.biglat) return fail(h, "kernel %s: the BIGLAT slice-resolved Polyakov kernels are not implemented in qcdgpu_b200", k.name.c_str());
+            a.geom = make_geom(c); a.tbc = c.tbc ? 1 : 0; a.axis = k.dir;
+            a.plk = c.plk_axis[k.dir] ? c.plk_axis[k.dir] : c.plk;
+            if (!a.plk) return fail(h, "kernel %s: the program was created without -D PLK", k.name.c_str());
+            a.block = (uint32_t)k.local0;
+            if (a.block == 0 || a.block > 256) return fail(h, "kernel %s: work-group size %u not supported (1..256)", k.name.c_str(), a.block);
+            a.min_blocks = (uint32_t)((k.global[0] + a.block - 1) / a.block);
+            // (getK() on the host arranges that a work-group lies inside one slice when N1 == N2, suncl.cpp:2081-2091; other
+            //  shapes mix neighbouring slices in a partial exactly as the reference does)
+            if (h->buffers[buf_id(k, 1)].capacity < (size_t)a.min_blocks * 16) return fail(h, "kernel %s: measurement buffer too small", k.name.c_str());
+            CUDA_OK(h, launch_polyakov(c.sun, prec, a, st));
+            break;
+        }
+        case K_REDUCE_POLYAKOV_DIFF: {
+            int index = 0;
+            if (k.args.size() < 5 || k.args[3].type != Arg::U32X4 || !arg_int(k, 4, &index)) return fail(h, "kernel %s: arguments (param, index) not set", k.name.c_str());
+            if (!buf_ptr(h, k, 0) || !buf_ptr(h, k, 1)) return fail(h, "kernel %s: buffers not set", k.name.c_str());
+            if (c.pl < 3) break;                                           // #if (PL > 2) in polyakov.cl:439
+            const uint32_t* p = k.args[3].u4;                              // total partials, offset of the (P^2,P^4) partials, result stride
+            const uint32_t n = (k.dir == 0) ? c.n1 : (k.dir == 1) ? c.n2 : c.n3;
+            const uint32_t size = p[0] / n;
+            if (h->buffers[buf_id(k, 1)].capacity < ((size_t)index + (size_t)p[2] * n + 1) * 16) return fail(h, "kernel %s: result buffer too small", k.name.c_str());
+            const size_t have = h->buffers[buf_id(k, 0)].capacity / 16;
+            if (have < (size_t)size * n) return fail(h, "kernel %s: measurement buffer too small", k.name.c_str());
+            // the extra sum over [offset, offset + size_total) re-reads the (P^2, P^4) partial region; the reference host sizes
+            // lattice_measurement without it, so the range is clipped to the allocation instead of read out of bounds
+            uint32_t extra = p[0];
+            if ((size_t)p[1] >= have) extra = 0; else if ((size_t)p[1] + extra > have) extra = (uint32_t)(have - p[1]);
+            CUDA_OK(h, launch_reduce_slices((const double2*)buf_ptr(h, k, 0), size, n, (double2*)buf_ptr(h, k, 1), (uint32_t)index, p[2], p[1], extra, !c.biglat, st));
             break;
         }
         case K_POLYAKOV: {
@@ -366,7 +459,11 @@ int launch_kernel(qgpu* h, int kid) {
             a.geom = make_geom(c); a.tbc = c.tbc ? 1 : 0; a.offset = (uint32_t)offset; a.pl_level = c.pl;
             a.x_first = c.biglat ? 1 : 0; a.x_count = c.biglat ? c.n1 - 2 : c.n1;
             a.block = (uint32_t)k.local0;
+            a.axis = -1;
+            // PL_LEVEL = 3 enlarges the host's grid (suncl.cpp:2284-2285): all partial slots it will sum must be written
+            a.min_blocks = (uint32_t)((k.global[0] + a.block - 1) / a.block);
             size_t blocks = ((size_t)a.x_count * a.geom.n23 + a.block - 1) / a.block;
+            if (blocks < a.min_blocks) blocks = a.min_blocks;
             if (h->buffers[buf_id(k, 1)].capacity < ((c.pl > 1 ? (size_t)offset : 0) + blocks) * 16) return fail(h, "kernel %s: measurement buffer too small", k.name.c_str());
             CUDA_OK(h, launch_polyakov(c.sun, prec, a, st));
             break;
@@ -543,7 +640,7 @@ int qgpu_kernel_init(qgpu* h, const char* name, unsigned dims, const size_t* glo
     // clinterface.cpp:1158-1169: explicit local size wins, else the (limited) kernel work-group size
     if (local && local[0]) { k.local0 = local[0]; k.local_given = true; }
     else k.local0 = (k.kind == K_UPDATE || k.kind == K_OVERRELAX) ? 128 : (h->limit_wg ? h->limit_wg : 128);
-    if (k.local0 > 128 && (k.kind == K_MEASURE || k.kind == K_MEASURE_PLQ || k.kind == K_POLYAKOV)) k.local0 = 128;
+    if (k.local0 > 128 && (k.kind == K_MEASURE || k.kind == K_MEASURE_PLQ || k.kind == K_POLYAKOV || k.kind == K_WILSON)) k.local0 = 128;
     h->kernels.push_back(k);
     return (int)h->kernels.size() - 1;
 }

@@ -276,6 +276,17 @@ __device__ __forceinline__ M3r2<R> load3_rt(const R* table, const Geom& g, uint3
     }
     return m;
 }
+template <typename R, bool TBC>
+__device__ __forceinline__ V4<R> load2_rt(const R* table, const Geom& g, uint32_t gindex, uint32_t x, int dir, const Twist<R>& tw) {
+    V4<R> m = ld_plane(table, g, gindex, dir);
+    if (TBC) {
+        if (dir == 1 && twisted_x(g, x)) {
+            V4<R> om = { tw.c1, R(0), tw.s1, R(0) };
+            m = su2_mul(om, m);
+        }
+    }
+    return m;
+}
 template <typename R, int DIR>
 __device__ __forceinline__ void store3(R* table, const Geom& g, uint32_t gindex, const Cx<R> u[3], const Cx<R> v[3]) {
     V4<R> a, b, c;

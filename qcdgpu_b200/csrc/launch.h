@@ -39,16 +39,24 @@ struct MeasureArgs {
     const void* table; const void* params; Geom geom; int tbc;
     double2* out_action; double2* out_plq;      // either may be null
     uint32_t first_site, nsites; uint32_t block;
+    // -D FMUNU (fmode 1) / -D F0MU (fmode 2): out_plq also receives six projected partial arrays, `offset` apart
+    int fmode, gen1, gen2; uint32_t offset;
+    int wilson;                                 // 1: Wilson loop W(R,T) into out_plq[BID].x instead of the plaquettes
 };
 cudaError_t launch_measure(int sun, int prec, const MeasureArgs&, cudaStream_t);   // dispatch.cu
 
 struct PolyakovArgs {
     const void* table; const void* params; Geom geom; int tbc;
     double2* out; uint32_t offset; int pl_level; uint32_t x_first, x_count; uint32_t block;
+    uint32_t min_blocks;                        // the host's grid: every partial slot it will sum must be written
+    int axis; uint32_t plk;                     // axis >= 0: slice-resolved variant lattice_polyakov_diff_{x,y,z}
 };
 cudaError_t launch_polyakov(int sun, int prec, const PolyakovArgs&, cudaStream_t);
 cudaError_t launch_reduce_double2(const double2* table, uint32_t off, uint32_t size, double2* dst, uint32_t index, cudaStream_t);
 cudaError_t launch_clear_double2(double2* p, uint32_t n, cudaStream_t);
+cudaError_t launch_reduce_slices(const double2* table, uint32_t size, uint32_t nslices, double2* dst, uint32_t index, uint32_t stride,
+                                 uint32_t extra_off, uint32_t extra_size, bool with_extra, cudaStream_t);
+cudaError_t launch_reduce_double_x(const double2* table, uint32_t size, double* dst, uint32_t index, cudaStream_t);
 
 cudaError_t launch_init_cold(int sun, int prec, void* table, const Geom&, cudaStream_t);
 cudaError_t launch_init_gid(int sun, int prec, void* table, const Geom&, cudaStream_t);

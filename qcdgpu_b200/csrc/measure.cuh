@@ -126,6 +126,226 @@ measure_kernel(const R* __restrict__ table, const R* __restrict__ params, const 
     }
 }
 
+// ---------------------------------------------------------------- Fmunu projections  (-D FMUNU / -D F0MU)
+// lattice_measurement_plq variants (sun_measurements_cl.cl:710-1175): next to the plaquette sums the spatial (FMUNU, H field) or
+// temporal (F0MU, E field) plaquette matrices W = U1 U2 U3^+ U4^+ are projected on two generators, -i Tr(W lambda_a / 2)
+// (su3_measurements_cl.cl:357-458, 550-589; SU(2): sigma_3 or sigma_1, and sigma_2, su2_measurements_cl.cl:89-122, 234-262).
+__device__ __forceinline__ M3<double> plaquette_matrix3(const M3<double>& U1, const M3<double>& U2, const M3<double>& U3, const M3<double>& U4) {
+    M3<double> A = mul_full(U1, U2), B = mul_full(U4, U3), W;     // W = (U1 U2)(U4 U3)^+
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+#pragma unroll
+        for (int j = 0; j < 3; j++) {
+            Cx<double> a = cmulc(A.e[i][0], B.e[j][0]); cfmac(a, A.e[i][1], B.e[j][1]); cfmac(a, A.e[i][2], B.e[j][2]);
+            W.e[i][j] = a;
+        }
+    return W;
+}
+// -i Tr(W lambda_a / 2), a = 1..8
+__device__ __forceinline__ Cx<double> trace_lambda(const M3<double>& W, int a) {
+    Cx<double> t = { 0.0, 0.0 };
+    switch (a) {
+        case 1: t.re =  W.e[0][1].im + W.e[1][0].im; t.im = -W.e[0][1].re - W.e[1][0].re; break;
+        case 2: t.re =  W.e[0][1].re - W.e[1][0].re; t.im =  W.e[0][1].im - W.e[1][0].im; break;
+        case 3: t.re =  W.e[0][0].im - W.e[1][1].im; t.im = -W.e[0][0].re + W.e[1][1].re; break;
+        case 4: t.re =  W.e[0][2].im + W.e[2][0].im; t.im = -W.e[0][2].re - W.e[2][0].re; break;
+        case 5: t.re =  W.e[0][2].re - W.e[2][0].re; t.im =  W.e[0][2].im - W.e[2][0].im; break;
+        case 6: t.re =  W.e[1][2].im + W.e[2][1].im; t.im = -W.e[1][2].re - W.e[2][1].re; break;
+        case 7: t.re =  W.e[1][2].re - W.e[2][1].re; t.im =  W.e[1][2].im - W.e[2][1].im; break;
+        default:
+            t.re = ( W.e[0][0].im + W.e[1][1].im - 2.0 * W.e[2][2].im) * 0.57735026918962576450914878050196;
+            t.im = (-W.e[0][0].re - W.e[1][1].re + 2.0 * W.e[2][2].re) * 0.57735026918962576450914878050196;
+            break;
+    }
+    t.re /= 2; t.im /= 2;
+    return t;
+}
+// SU(2): W as 4-vector (x = Re u1, y = Re u2, z = Im u1, w = Im u2); sigma_1 -> Im u2, sigma_2 -> Re u2, sigma_3 -> Im u1
+__device__ __forceinline__ double trace_sigma(const V4<double>& W, int a) { return a == 1 ? W.w : a == 2 ? W.y : W.z; }
+
+// fmode 1: F on the (x,y), (x,z), (y,z) plaquettes; fmode 2: on (x,t), (y,t), (z,t).
+// out[BID] = (Plq_spat, Plq_temp) partial, out[BID + (1..3)*offset] = first generator, out[BID + (4..6)*offset] = second generator
+template <int SUN, typename R, bool TBC>
+__global__ void __launch_bounds__(kMeasThreads)
+measure_f_kernel(const R* __restrict__ table, const R* __restrict__ params, const __grid_constant__ Geom g,
+                 double2* __restrict__ out, uint32_t offset, int fmode, int gen1, int gen2, uint32_t first_site, uint32_t nsites) {
+    const Twist<R> tw = make_twist<SUN, R, TBC>(params);
+    uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    double v[14];
+#pragma unroll
+    for (int i = 0; i < 14; i++) v[i] = 0.0;
+    if (k < nsites) {
+        uint32_t gid = first_site + k;
+        Coord p = gid_to_coords(g, gid);
+        Coord pn[4] = { nb_plus<0>(g, p), nb_plus<1>(g, p), nb_plus<2>(g, p), nb_plus<3>(g, p) };
+        uint32_t gn[4] = { coords_to_gid(g, pn[0]), coords_to_gid(g, pn[1]), coords_to_gid(g, pn[2]), coords_to_gid(g, pn[3]) };
+        int fslot = 0;
+        // plane order of the reference: xy, xz, xt, yz, yt, zt
+#pragma unroll 1
+        for (int pl = 0; pl < 6; pl++) {
+            const int a = (pl < 3) ? 0 : (pl < 5) ? 1 : 2;
+            const int b = (pl == 0) ? 1 : (pl == 1 || pl == 3) ? 2 : 3;
+            const bool temporal = (b == 3);
+            const bool want_f = (fmode == 1 && !temporal) || (fmode == 2 && temporal);
+            double tr;
+            Cx<double> f1 = { 0.0, 0.0 }, f2 = { 0.0, 0.0 };
+            if (SUN == 3) {
+                M3<double> U1 = promote3(load3_rt<R, TBC>(table, g, gid, p.x, a, tw));
+                M3<double> U2 = promote3(load3_rt<R, TBC>(table, g, gn[a], pn[a].x, b, tw));
+                M3<double> U3 = promote3(load3_rt<R, TBC>(table, g, gn[b], pn[b].x, a, tw));
+                M3<double> U4 = promote3(load3_rt<R, TBC>(table, g, gid, p.x, b, tw));
+                M3<double> W = plaquette_matrix3(U1, U2, U3, U4);
+                tr = W.e[0][0].re + W.e[1][1].re + W.e[2][2].re;
+                if (want_f) { f1 = trace_lambda(W, gen1); f2 = trace_lambda(W, gen2); }
+            } else {
+                V4<double> U1 = promote2(load2_rt<R, TBC>(table, g, gid, p.x, a, tw));
+                V4<double> U2 = promote2(load2_rt<R, TBC>(table, g, gn[a], pn[a].x, b, tw));
+                V4<double> U3 = promote2(load2_rt<R, TBC>(table, g, gn[b], pn[b].x, a, tw));
+                V4<double> U4 = promote2(load2_rt<R, TBC>(table, g, gid, p.x, b, tw));
+                V4<double> W = su2_mul(su2_mul(su2_mul(U1, U2), su2_dag(U3)), su2_dag(U4));
+                tr = 2.0 * W.x;
+                if (want_f) { f1.re = trace_sigma(W, gen1); f2.re = trace_sigma(W, gen2); }
+            }
+            if (temporal) v[1] += tr; else v[0] += tr;
+            if (want_f) {
+                v[2 + 2 * fslot] = f1.re; v[3 + 2 * fslot] = f1.im;
+                v[8 + 2 * fslot] = f2.re; v[9 + 2 * fslot] = f2.im;
+                fslot++;
+            }
+        }
+    }
+    block_sum<14>(v);
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int q = 0; q < 7; q++) out[blockIdx.x + q * offset] = make_double2(v[2 * q], v[2 * q + 1]);
+    }
+}
+
+// ---------------------------------------------------------------- Wilson loop W(R,T)  (wilson_loop.cl:54-452)
+// per site: sum over the three spatial directions d of Re Tr( Tline(p) . Rline_d(p+T t) . Tline(p+R d)^+ . Rline_d(p)^+ ),
+// lines = ordered products of T resp. R links; R, T = lattice_parameters[3], [4].  Accumulated in fp64.
+template <int SUN> struct WMat;
+template <> struct WMat<3> { typedef M3<double> type; };
+template <> struct WMat<2> { typedef V4<double> type; };
+template <int SUN, typename R, bool TBC>
+__device__ __forceinline__ typename WMat<SUN>::type wl_link(const R* table, const Geom& g, const Coord& c, int dir, const Twist<R>& tw) {
+    if constexpr (SUN == 3) return promote3(load3_rt<R, TBC>(table, g, coords_to_gid(g, c), c.x, dir, tw));
+    else return promote2(load2_rt<R, TBC>(table, g, coords_to_gid(g, c), c.x, dir, tw));
+}
+__device__ __forceinline__ M3<double> wl_mul(const M3<double>& a, const M3<double>& b) { return mul_full(a, b); }
+__device__ __forceinline__ V4<double> wl_mul(const V4<double>& a, const V4<double>& b) { return su2_mul(a, b); }
+// ordered product of n links in direction dir starting at c; c is left at the last site used (the reference's convention)
+template <int SUN, typename R, bool TBC>
+__device__ __forceinline__ typename WMat<SUN>::type wl_line(const R* table, const Geom& g, Coord& c, int dir, int n, const Twist<R>& tw) {
+    typename WMat<SUN>::type m = wl_link<SUN, R, TBC>(table, g, c, dir, tw);
+    for (int i = 1; i < n; i++) {
+        c = nb_plus_rt(g, c, dir);
+        m = wl_mul(m, wl_link<SUN, R, TBC>(table, g, c, dir, tw));
+    }
+    return m;
+}
+__device__ __forceinline__ double wl_retrace(const M3<double>& m1, const M3<double>& m2, const M3<double>& m3, const M3<double>& m4) { return retrace_plq3(m1, m2, m3, m4); }
+__device__ __forceinline__ double wl_retrace(const V4<double>& m1, const V4<double>& m2, const V4<double>& m3, const V4<double>& m4) { return retrace_plq2(m1, m2, m3, m4); }
+template <int SUN, typename R, bool TBC>
+__global__ void __launch_bounds__(kMeasThreads)
+wilson_kernel(const R* __restrict__ table, const R* __restrict__ params, const __grid_constant__ Geom g,
+              double2* __restrict__ out, uint32_t first_site, uint32_t nsites) {
+    const Twist<R> tw = make_twist<SUN, R, TBC>(params);
+    // the reference counts with floats: tmp = 1.1; while (tmp < wilson_X) {...; tmp += 1.0}
+    int wr = 1, wt = 1;
+    { float r = float(params[3]), t = float(params[4]); for (float x = 1.1f; x < r; x += 1.0f) wr++; for (float x = 1.1f; x < t; x += 1.0f) wt++; }
+    uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    double v[1] = { 0.0 };
+    if (k < nsites) {
+        const Coord p = gid_to_coords(g, first_site + k);
+        Coord c = p;
+        typename WMat<SUN>::type m1 = wl_line<SUN, R, TBC>(table, g, c, 3, wt, tw);     // bottom: T links from p
+        const Coord pT = nb_plus<3>(g, c);                                               // p + T t
+        double w = 0.0;
+#pragma unroll 1
+        for (int d = 0; d < 3; d++) {
+            Coord c1 = p, c2 = pT;
+            typename WMat<SUN>::type m4 = wl_line<SUN, R, TBC>(table, g, c1, d, wr, tw);  // R links from p
+            typename WMat<SUN>::type m2 = wl_line<SUN, R, TBC>(table, g, c2, d, wr, tw);  // R links from p + T t
+            Coord c4 = nb_plus_rt(g, c1, d);                                              // p + R d
+            typename WMat<SUN>::type m3 = wl_line<SUN, R, TBC>(table, g, c4, 3, wt, tw);  // T links from p + R d
+            w += wl_retrace(m1, m2, m3, m4);
+        }
+        v[0] = w;
+    }
+    block_sum<1>(v);
+    if (threadIdx.x == 0) out[blockIdx.x] = make_double2(v[0], 0.0);
+}
+
+// ---------------------------------------------------------------- slice-resolved Polyakov loop (PL_LEVEL = 3)
+// lattice_polyakov_diff_{x,y,z} (polyakov.cl:143-403): the thread index runs over an enlarged lattice in which one of the
+// transverse extents is padded to PLK so that every work-group lies inside one slice of the resolved axis
+// (lattice_gidK_{x,y,z}_to_gid_xyz, sun_common.cl:93-220); partials at out[BID].
+template <int SUN, typename R, bool TBC>
+__device__ __forceinline__ void polyakov_line(const R* table, const Geom& g, Coord p, const Twist<R>& tw, double& re, double& im) {
+    if (SUN == 3) {
+        M3<R> v0 = complete(load3<R, 3, TBC>(table, g, coords_to_gid(g, p), p.x, tw));
+        for (uint32_t i = 1; i < g.n4; i++) {
+            p = nb_plus<3>(g, p);
+            M3<R> v1 = complete(load3<R, 3, TBC>(table, g, coords_to_gid(g, p), p.x, tw));
+            v0 = mul_full(v0, v1);
+        }
+        re = double(v0.e[0][0].re) + double(v0.e[1][1].re) + double(v0.e[2][2].re);
+        im = double(v0.e[0][0].im) + double(v0.e[1][1].im) + double(v0.e[2][2].im);
+    } else {
+        V4<R> v0 = load2<R, 3, TBC>(table, g, coords_to_gid(g, p), p.x, tw);
+        for (uint32_t i = 1; i < g.n4; i++) {
+            p = nb_plus<3>(g, p);
+            v0 = su2_mul(v0, load2<R, 3, TBC>(table, g, coords_to_gid(g, p), p.x, tw));
+        }
+        re = 2.0 * double(v0.x); im = 0.0;
+    }
+}
+template <int SUN, typename R, bool TBC>
+__global__ void __launch_bounds__(256)
+polyakov_diff_kernel(const R* __restrict__ table, const R* __restrict__ params, const __grid_constant__ Geom g,
+                     double2* __restrict__ out, int axis, uint32_t plk) {
+    const Twist<R> tw = make_twist<SUN, R, TBC>(params);
+    const uint32_t gdi = blockIdx.x * blockDim.x + threadIdx.x;
+    double v[2] = { 0.0, 0.0 };
+    // fast extent A, padded extent (PLK), slice extent
+    const uint32_t A = (axis == 0) ? g.n2 : g.n1;
+    const uint32_t per4 = ((axis == 2) ? g.n1 * g.n3 : g.n1 * g.n2) * plk;
+    const uint32_t z4 = gdi / per4;
+    uint32_t z1 = gdi - z4 * per4;
+    const uint32_t z3 = z1 / (A * plk);
+    z1 -= z3 * A * plk;
+    const uint32_t z2 = z1 / A;
+    z1 -= z2 * A;
+    bool ok; Coord p;
+    if (axis == 0)      { ok = z1 < g.n2 && z2 < g.n3 && z3 < g.n1 && z4 == 0; p = { z3, z1, z2, 0u }; }
+    else if (axis == 1) { ok = z1 < g.n1 && z2 < g.n3 && z3 < g.n2 && z4 == 0; p = { z1, z3, z2, 0u }; }
+    else                { ok = z1 < g.n1 && z2 < g.n2 && z3 < g.n3 && z4 == 0; p = { z1, z2, z3, 0u }; }
+    if (ok) polyakov_line<SUN, R, TBC>(table, g, p, tw, v[0], v[1]);
+    block_sum<2>(v);
+    if (threadIdx.x == 0) out[blockIdx.x] = make_double2(v[0], v[1]);
+}
+// reduce_polyakov_diff_{x,y,z}_double2 (polyakov.cl:432-569): block i < nslices sums partials [i*size, (i+1)*size) into
+// dst[index + i*stride]; block nslices (single lattice only) sums [extra_off, extra_off + extra_size) into dst[index + nslices*stride]
+static __global__ void __launch_bounds__(256)
+reduce_slices_kernel(const double2* __restrict__ table, uint32_t size, uint32_t nslices, double2* __restrict__ dst,
+                     uint32_t index, uint32_t stride, uint32_t extra_off, uint32_t extra_size) {
+    const uint32_t b = blockIdx.x;
+    const uint32_t off = (b < nslices) ? b * size : extra_off, n = (b < nslices) ? size : extra_size;
+    double v[2] = { 0.0, 0.0 };
+    for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) { double2 t = table[off + i]; v[0] += t.x; v[1] += t.y; }
+    block_sum<2>(v);
+    if (threadIdx.x == 0) dst[index + b * stride] = make_double2(v[0], v[1]);
+}
+// reduce_wilson_double2 (wilson_loop.cl:456-465): the result buffer holds plain doubles
+static __global__ void __launch_bounds__(1024)
+reduce_double_x_kernel(const double2* __restrict__ table, uint32_t size, double* __restrict__ dst, uint32_t index) {
+    double v[1] = { 0.0 };
+    for (uint32_t i = threadIdx.x; i < size; i += blockDim.x) v[0] += table[i].x;
+    block_sum<1>(v);
+    if (threadIdx.x == 0) dst[index] = v[0];
+}
+
 // lattice_polyakov: thread per spatial site (x,y,z), ordered product along t in working precision
 template <int SUN, typename R, bool TBC>
 __global__ void __launch_bounds__(kMeasThreads)

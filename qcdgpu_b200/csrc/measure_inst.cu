@@ -26,6 +26,16 @@ cudaError_t NAME(launch_measure)(const MeasureArgs& a, cudaStream_t st) {
     if (grid.x == 0) return cudaSuccess;
     const RealT* t = static_cast<const RealT*>(a.table);
     const RealT* p = static_cast<const RealT*>(a.params);
+    if (a.wilson) {
+        if (a.tbc) wilson_kernel<INST_SUN, RealT, true><<<grid, block, 0, st>>>(t, p, a.geom, a.out_plq, a.first_site, a.nsites);
+        else       wilson_kernel<INST_SUN, RealT, false><<<grid, block, 0, st>>>(t, p, a.geom, a.out_plq, a.first_site, a.nsites);
+        return cudaGetLastError();
+    }
+    if (a.fmode) {
+        if (a.tbc) measure_f_kernel<INST_SUN, RealT, true><<<grid, block, 0, st>>>(t, p, a.geom, a.out_plq, a.offset, a.fmode, a.gen1, a.gen2, a.first_site, a.nsites);
+        else       measure_f_kernel<INST_SUN, RealT, false><<<grid, block, 0, st>>>(t, p, a.geom, a.out_plq, a.offset, a.fmode, a.gen1, a.gen2, a.first_site, a.nsites);
+        return cudaGetLastError();
+    }
     if (a.tbc) measure_kernel<INST_SUN, RealT, true><<<grid, block, 0, st>>>(t, p, a.geom, a.out_action, a.out_plq, a.first_site, a.nsites);
     else       measure_kernel<INST_SUN, RealT, false><<<grid, block, 0, st>>>(t, p, a.geom, a.out_action, a.out_plq, a.first_site, a.nsites);
     return cudaGetLastError();
@@ -33,11 +43,18 @@ cudaError_t NAME(launch_measure)(const MeasureArgs& a, cudaStream_t st) {
 cudaError_t NAME(launch_polyakov)(const PolyakovArgs& a, cudaStream_t st) {
     uint32_t block = a.block ? a.block : kMeasThreads;
     if (block > kMeasThreads) block = kMeasThreads;
-    uint32_t n = a.x_count * a.geom.n23;
-    dim3 grid((n + block - 1) / block);
-    if (grid.x == 0) return cudaSuccess;
     const RealT* t = static_cast<const RealT*>(a.table);
     const RealT* p = static_cast<const RealT*>(a.params);
+    if (a.axis >= 0) {     // slice-resolved: the host's grid and work-group size define the partial layout
+        if (a.min_blocks == 0 || a.block == 0 || a.block > 256) return cudaErrorInvalidValue;
+        if (a.tbc) polyakov_diff_kernel<INST_SUN, RealT, true><<<a.min_blocks, a.block, 0, st>>>(t, p, a.geom, a.out, a.axis, a.plk);
+        else       polyakov_diff_kernel<INST_SUN, RealT, false><<<a.min_blocks, a.block, 0, st>>>(t, p, a.geom, a.out, a.axis, a.plk);
+        return cudaGetLastError();
+    }
+    uint32_t n = a.x_count * a.geom.n23;
+    dim3 grid((n + block - 1) / block);
+    if (grid.x < a.min_blocks) grid.x = a.min_blocks;
+    if (grid.x == 0) return cudaSuccess;
     if (a.tbc) polyakov_kernel<INST_SUN, RealT, true><<<grid, block, 0, st>>>(t, p, a.geom, a.out, a.offset, a.pl_level, a.x_first, a.x_count);
     else       polyakov_kernel<INST_SUN, RealT, false><<<grid, block, 0, st>>>(t, p, a.geom, a.out, a.offset, a.pl_level, a.x_first, a.x_count);
     return cudaGetLastError();

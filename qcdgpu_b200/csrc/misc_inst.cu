@@ -9,6 +9,15 @@ cudaError_t launch_reduce_double2(const double2* table, uint32_t off, uint32_t s
     reduce_double2_kernel<<<1, 1024, 0, st>>>(table, off, size, dst, index);
     return cudaGetLastError();
 }
+cudaError_t launch_reduce_slices(const double2* table, uint32_t size, uint32_t nslices, double2* dst, uint32_t index, uint32_t stride,
+                                 uint32_t extra_off, uint32_t extra_size, bool with_extra, cudaStream_t st) {
+    reduce_slices_kernel<<<nslices + (with_extra ? 1u : 0u), 256, 0, st>>>(table, size, nslices, dst, index, stride, extra_off, extra_size);
+    return cudaGetLastError();
+}
+cudaError_t launch_reduce_double_x(const double2* table, uint32_t size, double* dst, uint32_t index, cudaStream_t st) {
+    reduce_double_x_kernel<<<1, 1024, 0, st>>>(table, size, dst, index);
+    return cudaGetLastError();
+}
 cudaError_t launch_clear_double2(double2* p, uint32_t n, cudaStream_t st) {
     if (n == 0) return cudaSuccess;
     clear_double2_kernel<<<(n + 255) / 256, 256, 0, st>>>(p, n);

@@ -53,6 +53,19 @@ def get_init_file(path: str) -> list[tuple[str, int, float, str]]:
     return out
 
 
+MODEL_energies_size = 7     # suncl.h:222: plaquette sums + 6 Fmunu projections
+
+
+def getK(n1: int, n2: int, ws: int) -> int:
+    """suncl.cpp:2081-2091: smallest i >= n2 with n1 * i a multiple of the work-group size."""
+    i = n2
+    while i < n2 * ws:
+        if n1 * i % ws == 0:
+            break
+        i += 1
+    return i
+
+
 class Model:
     """model_CL::model for one device (the non-BIGLAT build)."""
 
@@ -79,7 +92,14 @@ class Model:
         self.PHI = 0.0
         self.OMEGA = 0.0
         self.ints = model_start_cold
-        self.PL_level = 2           # the reference default 3 adds the *_diff_* kernels (out of scope)
+        self.PL_level = 2           # 3 adds the slice-resolved lattice_polyakov_diff_{x,y,z} (the reference program's default)
+        self.get_wilson_loop = False      # GETWILSON, WILSONR, WILSONT (QCDGPU.cpp:197-209)
+        self.wilson_R = 7
+        self.wilson_T = 2
+        self.get_Fmunu = False            # FMUNU: chromomagnetic projections of the spatial plaquettes
+        self.get_F0mu = False             # F0MU: chromoelectric projections of the temporal plaquettes
+        self.Fmunu_gen1 = 0               # FMUNU1/2/4 (0 = lambda_3 / sigma_3)
+        self.Fmunu_gen2 = 0               # FMUNU5/6/7 (0 = lambda_8; SU(2): always sigma_2)
         self.turnoff_updates = False
         self.turnoff_prns = False
         self.turnoff_gramschmidt = False
@@ -125,6 +145,14 @@ class Model:
             elif key == "OUTPUTPATH": self.path = text
             elif key == "GETRETRACE": self.get_plaquettes_avr = True
             elif key == "PL_LEVEL": self.PL_level = ival
+            elif key == "GETWILSON": self.get_wilson_loop = True
+            elif key == "WILSONR": self.wilson_R = ival
+            elif key == "WILSONT": self.wilson_T = ival
+            elif key == "TURNOFFFMUNU": self.get_Fmunu = self.get_F0mu = False
+            elif key == "FMUNU": self.get_Fmunu, self.get_F0mu = True, False
+            elif key == "F0MU": self.get_Fmunu, self.get_F0mu = False, True
+            elif key in ("FMUNU1", "FMUNU2", "FMUNU4"): self.Fmunu_gen1 = int(key[-1])
+            elif key in ("FMUNU5", "FMUNU6", "FMUNU7"): self.Fmunu_gen2 = int(key[-1])
             # extensions (not reference keys): PRECISION 0/1/2, NHITPAR, FUSEDPRNG, ORSTEPS
             elif key == "PRECISION": self.precision = ival
             elif key == "NHITPAR": self.NHITPar = ival
@@ -146,8 +174,8 @@ class Model:
         g = self.GPU0
         if self.lattice_group not in (2, 3):
             raise QcdGpuError("GROUP must be 2 or 3")
-        if self.PL_level > 2:
-            raise QcdGpuError("PL_LEVEL 3 (Polyakov-loop *_diff_* kernels) is outside the implemented hot path")
+        if self.biglat and (self.PL_level > 2 or self.get_wilson_loop or self.get_Fmunu or self.get_F0mu):
+            raise QcdGpuError("PL_LEVEL 3, Wilson loops and Fmunu are implemented for the single-lattice build only")
         full = self.lattice_full_size
         if self.biglat:
             # suncl.cpp:2388-2446: the part is stored with N1 = Nx + 2 (one halo slice on each side)
@@ -180,8 +208,14 @@ class Model:
         self.lattice_table_exact_row_size_half = al(self.lattice_domain_exact_site // 2)
         self.lattice_table_size = al(self.lattice_table_row_size * self.lattice_nd * ge // 4)
         self.lattice_measurement_size = al(int(math.ceil(self.lattice_table_exact_row_size / workgroup_factor)))
-        self.lattice_measurement_size_F = self.lattice_measurement_size
-        self.lattice_polyakov_size = al(self.lattice_domain_exact_n1n2n3)
+        fm = self.get_Fmunu or self.get_F0mu
+        self.lattice_measurement_size_F = self.lattice_measurement_size * (MODEL_energies_size if fm else 1)   # suncl.cpp:2281, 2296-2299
+        if self.PL_level > 2:      # suncl.cpp:2284-2285: one transverse extent padded so that a work-group stays inside a slice
+            self.PLK = getK(n[0], n[1], local_size_intel)
+            self.lattice_polyakov_size = al(self.lattice_domain_n2n3 * self.PLK)
+        else:
+            self.PLK = 0
+            self.lattice_polyakov_size = al(self.lattice_domain_exact_n1n2n3)
         self.lattice_polyakov_loop_size = al(self.ITER)
         self.lattice_polyakov_loop_offset = al(int(math.ceil(self.lattice_polyakov_size / workgroup_factor)))
         self.lattice_action_size = self.lattice_table_exact_row_size
@@ -238,12 +272,17 @@ class Model:
         self.size_lattice_measurement = max(self.lattice_measurement_size_F,
                                             2 * self.lattice_polyakov_loop_offset if self.PL_level > 1 else 0)
         self.size_lattice_energies = self.lattice_energies_size
-        self.size_lattice_energies_plq = self.lattice_energies_offset
-        self.size_lattice_polyakov_loop = 2 * self.lattice_polyakov_loop_size * max(self.PL_level, 1)
+        self.size_lattice_energies_plq = self.lattice_energies_offset * MODEL_energies_size      # suncl.cpp:3890
+        if self.PL_level > 2:      # suncl.cpp:3898-3901
+            self.size_lattice_polyakov_loop = (self.lattice_domain_n1 + 1) * self.lattice_polyakov_loop_size * max(self.PLK, 1)
+        else:
+            self.size_lattice_polyakov_loop = 2 * self.lattice_polyakov_loop_size * max(self.PL_level, 1)
         params = np.zeros(self.lattice_parameters_size, dtype=rdt)
         params[0] = self.BETA / self.lattice_group
         params[1] = self.PHI
         params[2] = self.OMEGA
+        params[3] = self.wilson_R          # suncl.cpp:3942-3953
+        params[4] = self.wilson_T
         self.lattice_table = g.buffer_init(GPU.buffer_type_IO, self.size_lattice_table, None, vec)
         self.lattice_parameters = g.buffer_init(GPU.buffer_type_Constant, self.lattice_parameters_size, params, params.itemsize)
         self.lattice_measurement = g.buffer_init(GPU.buffer_type_IO, self.size_lattice_measurement, None, 16)
@@ -253,6 +292,10 @@ class Model:
         self.lattice_energies_plq = g.buffer_init(GPU.buffer_type_IO, self.size_lattice_energies_plq, None, 16)
         if self.PL_level > 0:
             self.lattice_polyakov_loop = g.buffer_init(GPU.buffer_type_IO, self.size_lattice_polyakov_loop, None, 16)
+        if self.PL_level > 2:
+            self.lattice_polyakov_loop_diff = {a: g.buffer_init(GPU.buffer_type_IO, self.size_lattice_polyakov_loop, None, 16) for a in "xyz"}
+        if self.get_wilson_loop:
+            self.lattice_wilson_loop = g.buffer_init(GPU.buffer_type_IO, self.lattice_energies_size, None, 8)
 
     # ------------------------------------------------------------------ lattice_make_programs (suncl.cpp:3265-3648)
     def options_common(self) -> str:
@@ -264,6 +307,8 @@ class Model:
         if not (self.PHI == 0.0 and self.OMEGA == 0.0):
             o += " -D TBC"
         o += f" -D ROWSIZE={self.lattice_table_row_size} -D PRECISION={self.precision}"
+        if not self.biglat:     # suncl.cpp:3292
+            o += f" -D PLK={getK(n[0], n[1], self.GPU0.GPU_limit_max_workgroup_size or 0)}"
         if self.biglat:   # suncl.cpp:2427-2441
             n234 = n[1] * n[2] * n[3]
             o += f" -D BIGLAT -D FULL_SITES={self.lattice_full_site} -D LEFT_SITES={self.left_x * n234}"
@@ -309,7 +354,13 @@ class Model:
                     g.kernel_init_buffer(k, self.lattice_parameters)
                     self.sun_overrelax_id[(par, d)] = k
         # measurements
-        self.program_measurements = g.program_create(None, oc)
+        om = oc                                                    # suncl.cpp:3398-3408
+        if self.get_Fmunu: om += " -D FMUNU"
+        if self.get_F0mu: om += " -D F0MU"
+        if self.get_Fmunu or self.get_F0mu:
+            if self.Fmunu_gen1: om += f" -D FMUNU{self.Fmunu_gen1}"
+            if self.Fmunu_gen2: om += f" -D FMUNU{self.Fmunu_gen2}"
+        self.program_measurements = g.program_create(None, om)
         meas_gs = [self.lattice_action_size]
         self.sun_clear_measurement_id = g.kernel_init("clear_measurement", 1, [self.size_lattice_measurement], None)
         g.kernel_init_buffer(self.sun_clear_measurement_id, self.lattice_measurement)
@@ -333,6 +384,17 @@ class Model:
             g.kernel_init_buffer(self.sun_measurement_plq_reduce_id, b)
         self.argument_plq_index = g.kernel_init_constant(self.sun_measurement_plq_reduce_id,
                                                          [size_plq, offset_plq, self.lattice_energies_offset, 0])
+        # Wilson loop (suncl.cpp:3518-3546)
+        if self.get_wilson_loop:
+            self.program_wilson = g.program_create(None, oc)
+            self.sun_measurement_wilson_id = g.kernel_init("lattice_measurement_wilson", 1, meas_gs, [wg])
+            for b in (self.lattice_table, self.lattice_measurement, self.lattice_parameters, self.lattice_lds):
+                g.kernel_init_buffer(self.sun_measurement_wilson_id, b)
+            size_w = int(math.ceil(self.lattice_domain_exact_site / g.kernel_get_worksize(self.sun_measurement_wilson_id)))
+            self.sun_wilson_loop_reduce_id = g.kernel_init("reduce_wilson_double2", 1, [wg], [wg])
+            for b in (self.lattice_measurement, self.lattice_wilson_loop, self.lattice_lds):
+                g.kernel_init_buffer(self.sun_wilson_loop_reduce_id, b)
+            self.argument_wilson_index = g.kernel_init_constant(self.sun_wilson_loop_reduce_id, size_w)
         # Polyakov loop
         if self.PL_level > 0:
             self.program_polyakov = g.program_create(None, oc + f" -D PL={self.PL_level}")
@@ -348,14 +410,30 @@ class Model:
                 g.kernel_init_buffer(self.sun_polyakov_reduce_id, b)
             self.argument_polyakov_index = g.kernel_init_constant(
                 self.sun_polyakov_reduce_id, [size_p, offset_p, self.lattice_polyakov_loop_size, 0])
+        if self.PL_level > 2:      # suncl.cpp:3590-3644
+            self.sun_polyakov_diff_id, self.sun_polyakov_diff_reduce_id, self.argument_polyakov_diff_index = {}, {}, {}
+            for a in "xyz":
+                k = g.kernel_init(f"lattice_polyakov_diff_{a}", 1, [self.lattice_polyakov_size], [wg])
+                ws = g.kernel_get_worksize(k)
+                offset_d = g.buffer_size_align(int(math.ceil(self.lattice_polyakov_size / ws)), ws)
+                for b in (self.lattice_table, self.lattice_measurement, self.lattice_parameters, self.lattice_lds):
+                    g.kernel_init_buffer(k, b)
+                g.kernel_init_constant(k, offset_d)
+                size_d = int(math.ceil(self.lattice_polyakov_size / ws))
+                r = g.kernel_init(f"reduce_polyakov_diff_{a}_double2", 1, [wg], [wg])
+                for b in (self.lattice_measurement, self.lattice_polyakov_loop_diff[a], self.lattice_lds):
+                    g.kernel_init_buffer(r, b)
+                self.argument_polyakov_diff_index[a] = g.kernel_init_constant(r, [size_d, offset_d, self.lattice_polyakov_loop_size, 0])
+                self.sun_polyakov_diff_id[a], self.sun_polyakov_diff_reduce_id[a] = k, r
 
     # ------------------------------------------------------------------ run loop (suncl.cpp:5212-5505)
     def _measure(self):
+        """Measurements of the current configuration into slot ITER_counter, in the reference's order (suncl.cpp:5416-5482)."""
         g = self.GPU0
-        if self.get_plaquettes_avr:
-            g.kernel_run(self.sun_measurement_plq_id)
-            g.kernel_init_constant_reset(self.sun_measurement_plq_reduce_id, self.ITER_counter, self.argument_plq_index)
-            g.kernel_run(self.sun_measurement_plq_reduce_id)
+        if self.get_wilson_loop:
+            g.kernel_run(self.sun_measurement_wilson_id)
+            g.kernel_init_constant_reset(self.sun_wilson_loop_reduce_id, self.ITER_counter, self.argument_wilson_index)
+            g.kernel_run(self.sun_wilson_loop_reduce_id)
         if self.get_actions_avr:
             g.kernel_run(self.sun_measurement_id)
             g.kernel_init_constant_reset(self.sun_measurement_reduce_id, self.ITER_counter, self.argument_measurement_index)
@@ -365,6 +443,17 @@ class Model:
             g.kernel_run(self.sun_polyakov_id)
             g.kernel_init_constant_reset(self.sun_polyakov_reduce_id, self.ITER_counter, self.argument_polyakov_index)
             g.kernel_run(self.sun_polyakov_reduce_id)
+        if self.PL_level > 2:
+            g.kernel_run(self.sun_clear_measurement_id)
+            for a in "xyz":
+                g.kernel_run(self.sun_polyakov_diff_id[a])
+                g.kernel_init_constant_reset(self.sun_polyakov_diff_reduce_id[a], self.ITER_counter, self.argument_polyakov_diff_index[a])
+                g.kernel_run(self.sun_polyakov_diff_reduce_id[a])
+        if self.get_plaquettes_avr or self.get_Fmunu or self.get_F0mu:
+            g.kernel_run(self.sun_clear_measurement_id)
+            g.kernel_run(self.sun_measurement_plq_id)
+            g.kernel_init_constant_reset(self.sun_measurement_plq_reduce_id, self.ITER_counter, self.argument_plq_index)
+            g.kernel_run(self.sun_measurement_plq_reduce_id)
 
     def lattice_sweep(self):
         """One sweep: 8 x (produce, update) + reunitarisation  (suncl.cpp:5357-5377)."""
@@ -454,15 +543,49 @@ class Model:
                 o = self.lattice_polyakov_loop_size
                 A["Polyakov_loop_P2"] = self._series(e[o: o + self.ITER, 0].copy(), float(self.lattice_full_n1n2n3 * self.lattice_group ** 2))
                 A["Polyakov_loop_P4"] = self._series(e[o: o + self.ITER, 1].copy(), float(self.lattice_full_n1n2n3 * self.lattice_group ** 4))
+        if self.PL_level > 2:      # suncl.cpp:1500-1560: per-slice series, result r of slice i at [r + i * lattice_polyakov_loop_size]
+            # the reference divides every axis by full_n2n3 * group (suncl.cpp:1516, 1544): exact for cubic spatial volumes
+            pden_slice = lambda n: float(self.lattice_full_size[1] * self.lattice_full_size[2] * self.lattice_group)
+            for ax, a in enumerate("xyz"):
+                n = self.lattice_full_size[ax]
+                e = g.buffer_map(self.lattice_polyakov_loop_diff[a], np.float64).reshape(-1, 2)
+                o = self.lattice_polyakov_loop_size
+                A[f"PL_{a.upper()}"] = [self._series(e[i * o: i * o + self.ITER, 0].copy(), pden_slice(n)) for i in range(n)]
+                A[f"PL_{a.upper()}_im"] = [self._series(e[i * o: i * o + self.ITER, 1].copy(), pden_slice(n)) for i in range(n)]
+        if self.get_wilson_loop:   # suncl.cpp:1606-1612
+            w = g.buffer_map(self.lattice_wilson_loop, np.float64)[: self.ITER]
+            A["Wilson_loop"] = self._series(w.copy(), den)
+        if self.get_Fmunu or self.get_F0mu:     # suncl.cpp:1613-1672
+            e = g.buffer_map(self.lattice_energies_plq, np.float64).reshape(-1, 2)
+            o = self.lattice_energies_offset
+            i1, i2 = self.Fmunu_indices()
+            planes = ("xy", "xz", "yz") if self.get_Fmunu else ("xt", "yt", "zt")
+            for q, pl in enumerate(planes):
+                for c, reim in enumerate(("re", "im")):
+                    A[f"Fmunu_{pl}_{i1}_{reim}"] = self._series(e[(1 + q) * o: (1 + q) * o + self.ITER, c].copy(), float(self.lattice_full_site))
+                    A[f"Fmunu_{pl}_{i2}_{reim}"] = self._series(e[(4 + q) * o: (4 + q) * o + self.ITER, c].copy(), float(self.lattice_full_site))
         return A
+
+    def Fmunu_indices(self) -> tuple[int, int]:
+        """Generator numbers used in the data names (model::Fmunu_defaults, suncl.cpp:2094-2127)."""
+        if self.lattice_group == 2:
+            return (1 if self.Fmunu_gen1 == 1 else 3), 2
+        return (self.Fmunu_gen1 or 3), (self.Fmunu_gen2 or 8)
 
     # lattice_write_results (suncl.cpp:1679-1854)
     def columns(self) -> list[str]:
         cols = []
         if self.get_plaquettes_avr: cols += ["Plq_spat", "Plq_temp", "Plq_total"]
+        if self.get_wilson_loop: cols += ["Wilson_loop"]
         if self.get_actions_avr: cols += ["S_spat", "S_temp", "S_total"]
         if self.PL_level > 0: cols += ["Polyakov_loop", "Polyakov_loop_im"]
         if self.PL_level > 1: cols += ["Polyakov_loop_P2", "Polyakov_loop_P4"]
+        if self.get_Fmunu or self.get_F0mu:
+            i1, i2 = self.Fmunu_indices()
+            planes = ("xy", "xz", "yz") if self.get_Fmunu else ("xt", "yt", "zt")
+            for i in (i1, i2):
+                for pl in planes:
+                    cols += [f"Fmunu_{pl}_{i}_re", f"Fmunu_{pl}_{i}_im"]
         return cols
 
     def lattice_write_results(self, filename: str | None = None) -> str:

@@ -31,16 +31,17 @@ INIT = """\tPLATFORM = 0
 \tINTS = {ints}
 \tPRNG = {prng}
 \tRANDSERIES = 54
-\tPL_LEVEL = 2
+\tPL_LEVEL = {pl}
 \tPHI = {phi:.13e}
-"""
+{extra}"""
 
 
 def run_reference_host(tmp_path, **kw):
     if not os.path.exists(BIN):
         pytest.skip("integration/_build/QCDGPU_b200 not built (needs the reference tree: make -C integration)")
-    cfg = dict(group=3, ls=8, lt=8, iter=4, beta=6.0, nav=2, ints=1, prng="RANLUX3", phi=0.0)
+    cfg = dict(group=3, ls=8, lt=8, iter=4, beta=6.0, nav=2, ints=1, prng="RANLUX3", phi=0.0, pl=2, extra="")
     cfg.update(kw)
+    cfg["extra"] = "".join(f"\t{line}\n" for line in cfg["extra"].split(";") if line)
     (tmp_path / "init.dat").write_text(INIT.format(**cfg))
     r = subprocess.run([BIN, "init.dat"], cwd=tmp_path, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
@@ -78,3 +79,31 @@ def test_reference_host_twisted_run_verifies(tmp_path):
     """PHI != 0 (init.dat sample value 3.0): twisted loads in staples, measurements and the CPU check."""
     text, _ = run_reference_host(tmp_path, group=3, ints=0, beta=6.0, phi=3.0, ls=6, lt=4)
     assert "Verification successfully passed" in text, text[-3000:]
+
+
+@pytest.mark.parametrize("group,beta,extra", [
+    (2, 3.5, "GETWILSON = 1;WILSONR = 3;WILSONT = 2;FMUNU = 1"),          # the reference's sample init.dat, on 8^4
+    (3, 6.0, "GETWILSON = 1;WILSONR = 2;WILSONT = 3;FMUNU = 1"),
+    (3, 6.0, "F0MU = 1;FMUNU1 = 1;FMUNU5 = 1"),
+])
+def test_reference_sample_configuration_wilson_fmunu_polyakov_slices(tmp_path, group, beta, extra):
+    """SU(N)/init.dat enables GETWILSON, PL_LEVEL = 3, FMUNU and the twist PHI = 3: every kernel that configuration
+    initialises runs, and the reference's LatticeCheckCPU (Wilson loop su3cpu.cpp:1435-1520, Fmunu 1293-1345) agrees."""
+    text, stdout = run_reference_host(tmp_path, group=group, ints=0, beta=beta, phi=3.0, pl=3, extra=extra)
+    assert "Verification successfully passed" in text, text[-4000:]
+    vals = last_values(text)
+    names = ["S_total", "Plq_total", "Polyakov_loop"] + (["Wilson_loop"] if "GETWILSON" in extra else [])
+    for name in names:
+        assert name in vals, (name, sorted(vals))
+        c, g = vals[name]["CPU"], vals[name]["GPU"]
+        assert abs(c) > 1e-6 and abs(1.0 - g / c) < 1e-11, (name, c, g)
+    fm = [k for k in vals if k.startswith("Fmunu_") and "abs" not in k]
+    assert len(fm) >= 12, sorted(vals)
+    for k in fm:
+        c, g = vals[k].get("CPU"), vals[k].get("GPU")
+        if c is not None and g is not None and abs(c) > 1e-9:
+            assert abs(1.0 - g / c) < 1e-9, (k, c, g)
+    # slice-resolved Polyakov loop table is written and adds up to the total
+    assert "Differentiated Polyakov loop data" in text
+    row = [l for l in text.splitlines() if l.startswith("PL             ")][0].split()[1:]
+    assert len(row) == 8
