@@ -640,8 +640,8 @@ __device__ __forceinline__ void heatbath_su3(R* table, const Geom& g, R beta, ui
 template <typename R, int MU, bool TBC, class Prn>
 __device__ __forceinline__ void update_site_su3(R* table, const Geom& g, R beta, const Twist<R>& tw, uint32_t gindex, Prn& prn) {
     Coord p = gid_to_coords(g, gindex);
-    M3r2<R> m0 = load3<R, MU, TBC>(table, g, gindex, p.x, tw);
     M3<R> S = staple3<R, MU, TBC>(table, g, p, gindex, tw);
+    M3r2<R> m0 = load3<R, MU, TBC>(table, g, gindex, p.x, tw);     // after the staples: 24 registers less while they are formed
     heatbath_su3<R, MU, Prn>(table, g, beta, gindex, m0, S, prn);
 }
 // same with the links arriving through the shared-memory ring (begin() was called earlier)
