@@ -141,15 +141,19 @@ def reference_main(args):
 
 
 # ---------------------------------------------------------------------------------------------- native arm
-def build_model(dims, fused=True, device=0):
+def build_model(dims, fused=True, device=0, group=None, precision=None, phi=0.0):
     from qcdgpu_b200 import Model
     m = Model()
     m.desired_device = device
-    m.lattice_group = WORKLOAD["group"]
+    m.lattice_group = WORKLOAD["group"] if group is None else group
     m.lattice_full_size = list(dims)
-    m.precision = WORKLOAD["precision"]
+    m.precision = WORKLOAD["precision"] if precision is None else precision
+    m.PHI = phi
+    if m.lattice_group == 2 and group is not None:
+        m.BETA = 2.5
     m.ints = WORKLOAD["ints"]
-    m.BETA = WORKLOAD["beta"]
+    if not (m.lattice_group == 2 and group is not None):
+        m.BETA = WORKLOAD["beta"]
     m.NHIT = WORKLOAD["nhit"]
     m.PRNG0.PRNG_generator = WORKLOAD["prng"]
     m.PRNG0.PRNG_randseries = WORKLOAD["randseries"]
@@ -164,7 +168,8 @@ def build_model(dims, fused=True, device=0):
 def native_single(args):
     import numpy as np
     dims = tuple(int(x) for x in args.dims.split("x")) if args.dims else WORKLOAD["dims"]
-    m = build_model(dims, fused=not args.buffered)
+    m = build_model(dims, fused=not args.buffered, group=args.group, precision=args.precision, phi=args.phi)
+    diag = args.group is not None or args.precision is not None or args.phi != 0.0
     g = m.GPU0
     if args.materialize:
         g.set_fused_prng(False)      # PRNG_instances == PRNGSTEP, but every produce() writes the PRN buffer
@@ -210,27 +215,31 @@ def native_single(args):
     upd_ns = sum(t[0] * t[2] for t in tk) / max(1, sum(t[2] for t in tk))
     gs_ns = g.kernel_get_execution_time(m.sun_GramSchmidt_id)[0]
     peak, peak_kind = measured_peaks()
-    bytes_per_launch = 4.5 * V * 96.0
+    link_bytes = (12 if m.lattice_group == 3 else 4) * (8 if m.precision == 1 else 4)
+    bytes_per_launch = 4.5 * V * link_bytes
     achieved = bytes_per_launch / (upd_ns * 1e-9) / 1e9
     # DRAM bytes of one launch of that kernel from the committed ncu --set full capture (same command, 64^4 fused only)
     traffic, traffic_src = None, None
-    if tuple(dims) == (64, 64, 64, 64) and not args.buffered and not args.materialize:
+    if tuple(dims) == (64, 64, 64, 64) and not args.buffered and not args.materialize and not diag:
         traffic, traffic_src = NCU_DRAM_BYTES_PER_LAUNCH, "profiles/r01_ncu_update_v3_lazy_conversion.json (dram__bytes_read.sum + dram__bytes_write.sum)"
     regs = g.update_kernel_registers(m.program_update, 0, 2 if not args.buffered else 0)
+    kname = ("update_kernel_rlx<%d,%s,MU,%s,223>" if not args.buffered else "update_kernel<%d,%s,MU,%s,PrnBuffered>") % (
+        m.lattice_group, "double" if m.precision == 1 else "float", "true" if args.phi != 0.0 else "false")
     plq_total = float(plq.sum() / (6.0 * V)) if plq is not None else None
     # ---- CPU baseline: the reference itself, 1 core, bounded sample
     cpu_v, cpu_dt = (None, None) if args.no_cpu else run_reference_cpu(1, 12, 3)
     out = {
         "metric": "SU(3) link updates/sec", "value": value, "unit": "link-updates/s", "n_gpus": 1,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"SU(3) {'x'.join(map(str, dims))} fp64 heat-bath sweeps (8 passes + reunitarisation), beta=6.0, "
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64" if m.precision == 1 else "f32", "data": "synthetic",
+        "config": {"workload": f"SU({m.lattice_group}) {'x'.join(map(str, dims))} {'fp64' if m.precision == 1 else 'fp32'} heat-bath sweeps (8 passes + reunitarisation), beta={m.BETA}, "
                                f"NHIT=10, RANLUX3 ({'fused in-register' if not args.buffered else 'buffered'}), cold start",
-                   "l2_policy": "inputs_larger_than_L2 (link table 6.44 GB vs 126 MB L2)", "sweeps_per_s": args.steps / (ms * 1e-3),
+                   "l2_policy": (f"inputs_larger_than_L2 (link table {4 * V * link_bytes / 1e9:.2f} GB vs 126 MB L2)" if 4 * V * link_bytes > 126e6
+                                 else f"diagnostic configuration: link table {4 * V * link_bytes / 1e6:.1f} MB fits the L2, no flush"), "sweeps_per_s": args.steps / (ms * 1e-3),
                    "plaquette_after_run": plq_total, "update_kernel_registers": regs},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_kind,
-                     "kernel": ("update_kernel_rlx<3,double,MU,false,223>" if not args.buffered else "update_kernel<3,double,MU,false,PrnBuffered>"),
+                     "kernel": kname,
                      "avg_launch_us": upd_ns / 1e3, "algorithmic_bytes_per_launch": bytes_per_launch,
                      "fp64_gflops": FLOPS_PER_LINK_UPDATE * (V / 2) / (upd_ns * 1e-9) / 1e9,
                      "reunitarisation_launch_us": gs_ns / 1e3},
@@ -255,6 +264,9 @@ def main():
     ap.add_argument("--dims", default="")
     ap.add_argument("--buffered", action="store_true", help="reference-layout PRN buffer instead of the fused generator")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--group", type=int, default=None, help="diagnostic: 2 or 3 (default: the BASELINE workload, SU(3))")
+    ap.add_argument("--precision", type=int, default=None, help="diagnostic: 0 single, 1 double, 2 mixed")
+    ap.add_argument("--phi", type=float, default=0.0, help="diagnostic: twist angle (turns -D TBC on)")
     ap.add_argument("--materialize", action="store_true", help="one generator per update thread, PRN buffer written (diagnostic)")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -313,6 +313,38 @@ def test_fused_prng_equals_buffered(gen, sun, prec):
     np.testing.assert_array_equal(tables[0].view(np.uint8), tables[1].view(np.uint8))
 
 
+_KEEP_SCRIPT = r"""
+import sys, numpy as np
+sys.path.insert(0, sys.argv[1])
+from test_gpu_parity import make_model
+sun, prec, beta = int(sys.argv[2]), int(sys.argv[3]), float(sys.argv[4])
+tables = []
+for fused in (False, True):
+    m = make_model(sun, (4, 4, 4, 8), prec, ints=0, prng="RANLUX3", fused=True, iters=4, beta=beta)
+    if not fused:
+        m.GPU0.set_fused_prng(False)
+    m.lattice_simulate()
+    tables.append(m.table_numpy())
+    m.close()
+assert np.array_equal(tables[0].view(np.uint8), tables[1].view(np.uint8)), float(np.abs(tables[0] - tables[1]).max())
+print("IDENTICAL")
+"""
+
+
+@pytest.mark.parametrize("keep", [1, 3, 7])
+@pytest.mark.parametrize("sun,prec,beta", [(3, 1, 1.0), (3, 0, 6.0), (2, 1, 0.5)])
+def test_two_phase_kernel_overflow_path_is_bit_exact(keep, sun, prec, beta):
+    """The two-phase RANLUX kernel parks only `keep` samples per thread and regenerates the rest of a pass's stream from a
+    state snapshot (ranlux_overflow).  With QCDGPU_RLX_KEEP forced far below the 6+ samples every link consumes (and a small
+    beta, i.e. many rejected trials), every thread takes that path; the lattice must still equal the buffered run bit for bit."""
+    import subprocess
+    import sys
+    env = dict(os.environ, QCDGPU_RLX_KEEP=str(keep))
+    here = os.path.dirname(os.path.abspath(__file__))
+    r = subprocess.run([sys.executable, "-c", _KEEP_SCRIPT, here, str(sun), str(prec), str(beta)], env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "IDENTICAL" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+
+
 # ---------------------------------------------------------------------------------- overrelaxation
 @pytest.mark.parametrize("sun", [3, 2])
 def test_overrelaxation(sun):
