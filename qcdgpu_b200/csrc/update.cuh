@@ -425,7 +425,10 @@ __device__ __forceinline__ M3<R> staple3(const R* table, const Geom& g, const Co
 #ifndef QCD_STAGE_K
 #define QCD_STAGE_K 0
 #endif
-constexpr int kUpdateThreads = 128;
+#ifndef QCD_UPDATE_THREADS
+#define QCD_UPDATE_THREADS 128
+#endif
+constexpr int kUpdateThreads = QCD_UPDATE_THREADS;
 constexpr int kStageK = QCD_STAGE_K;
 template <typename R> constexpr size_t stage_bytes() { return size_t(kStageK) * 3 * (sizeof(V4<R>) / 16) * 16 * kUpdateThreads; }
 
@@ -739,7 +742,7 @@ __device__ __forceinline__ Twist<R> make_twist(const R* params) {
 }
 
 template <int SUN, typename R, int MU, bool TBC, class Prn>
-__global__ void __launch_bounds__(kUpdateThreads, Prn::kMinBlocks)
+__global__ void __launch_bounds__(kUpdateThreads, (Prn::kMinBlocks * 128) / kUpdateThreads > 0 ? (Prn::kMinBlocks * 128) / kUpdateThreads : 1)
 update_kernel(R* __restrict__ table, const R* __restrict__ params, const __grid_constant__ Geom g, int odd, typename Prn::Args pargs) {
     uint32_t GID = blockIdx.x * blockDim.x + threadIdx.x;
     if (GID >= g.nthreads) return;
@@ -758,7 +761,7 @@ update_kernel(R* __restrict__ table, const R* __restrict__ params, const __grid_
     prn.finish();
 }
 template <int SUN, typename R, int MU, bool TBC, int NSKIP>
-__global__ void __launch_bounds__(kUpdateThreads, (sizeof(R) == 8 && SUN == 3) ? 3 : 4)
+__global__ void __launch_bounds__(kUpdateThreads, (((sizeof(R) == 8 && SUN == 3) ? 3 : 4) * 128) / kUpdateThreads)
 update_kernel_rlx(R* __restrict__ table, const R* __restrict__ params, const __grid_constant__ Geom g, int odd,
                   uint32_t* __restrict__ rtable, uint32_t instances, uint32_t samples, uint32_t keep, uint32_t snapshot) {
     extern __shared__ uint4 prn_smem[];
