@@ -17,6 +17,7 @@
 #include <cstring>
 #include <string>
 #include <vector>
+#include <utility>
 
 using namespace qcd;
 
@@ -80,6 +81,10 @@ struct Buffer {
     size_t map_off = 0, map_len = 0;
     int pending_produce = 0;         // kernel id of a deferred PRN producer writing this buffer
     bool pending_partly_fused = false;   // x-range launches of the current pass already ran that generator in registers
+    // RANLUX state table of the two-phase update kernel: a second table of the same size receives the advanced state and the
+    // two are swapped when the pass is complete, so the state in front of a pass stays readable during it (update.cuh, PrnSmemT)
+    void* twin = nullptr;
+    int swap_seed_buf = 0;           // (on the PRN buffer) state table whose swap waits for the pass's last x-range launch
     bool alive = false;
 };
 
@@ -248,6 +253,21 @@ bool arg_int(const Kernel& k, size_t i, int* out) {
 
 int launch_kernel(qgpu* h, int kid);
 
+// the x-range launches of a pass have all been issued: drop the deferred producer and publish the advanced RANLUX states
+void finish_partial_pass(qgpu* h, int pb) {
+    Buffer& b = h->buffers[pb];
+    b.pending_produce = 0; b.pending_partly_fused = false;
+    if (b.swap_seed_buf && valid_buf(h, b.swap_seed_buf) && h->buffers[b.swap_seed_buf].twin)
+        std::swap(h->buffers[b.swap_seed_buf].dptr, h->buffers[b.swap_seed_buf].twin);
+    b.swap_seed_buf = 0;
+}
+
+// the host is about to look at buffer `bid`: if it is a RANLUX state table whose swap waits for the end of a pass, publish it now
+void settle_state_table(qgpu* h, int bid) {
+    for (size_t i = 1; i < h->buffers.size(); i++)
+        if (h->buffers[i].alive && h->buffers[i].swap_seed_buf == bid) finish_partial_pass(h, (int)i);
+}
+
 // run a deferred PRN producer now (writes the reference-layout buffer)
 int flush_pending(qgpu* h, int bid) {
     if (!valid_buf(h, bid)) return 0;
@@ -313,6 +333,7 @@ int launch_kernel(qgpu* h, int kid) {
             if (c.prng_precision == 2) return fail(h, "kernel %s: PRNG_PRECISION=2 (double PRNs) is not implemented", k.name.c_str());
             Buffer& pbuf = h->buffers[pb];
             bool fused = false;
+            int swap_seed = 0;       // full-range launch of the two-phase RANLUX kernel: swap the state tables right after it
             if (pbuf.pending_produce) {
                 Kernel& pk = h->kernels[pbuf.pending_produce];
                 int samples = 0; arg_int(pk, 2, &samples);
@@ -322,8 +343,16 @@ int launch_kernel(qgpu* h, int kid) {
                 if (fusable) {
                     a.prn_kind = pk.prn_kind; a.prn_table = (uint32_t*)buf_ptr(h, pk, 0);
                     a.prn_instances = (uint32_t)pk.global[0]; a.prn_samples = (uint32_t)samples;
+                    if (pk.prn_kind == PRN_RANLUX3) {      // second state table (see Buffer::twin); without it the kernel works in place
+                        Buffer& sb = h->buffers[buf_id(pk, 0)];
+                        if (!sb.twin && cudaMalloc(&sb.twin, sb.capacity) == cudaSuccess)
+                            CUDA_OK(h, cudaMemcpyAsync(sb.twin, sb.dptr, sb.capacity, cudaMemcpyDeviceToDevice, st));
+                        else if (!sb.twin) { sb.twin = nullptr; (void)cudaGetLastError(); }
+                        a.prn_table_out = (uint32_t*)sb.twin;
+                        swap_seed = sb.twin ? buf_id(pk, 0) : 0;
+                    }
                     if (k.x_count < 0) { pbuf.pending_produce = 0; pbuf.pending_partly_fused = false; }
-                    else pbuf.pending_partly_fused = true;       // the other x-ranges of this pass follow
+                    else { pbuf.pending_partly_fused = true; pbuf.swap_seed_buf = swap_seed; swap_seed = 0; }   // the other x-ranges of this pass follow
                     fused = true;
                 } else if (flush_pending(h, pb) < 0) return -1;
             }
@@ -333,6 +362,7 @@ int launch_kernel(qgpu* h, int kid) {
                 if (pbuf.bytes < need * 16) return fail(h, "kernel %s: PRN buffer holds %zu vec4, the pass may read %zu", k.name.c_str(), pbuf.bytes / 16, need);
             }
             CUDA_OK(h, fn(a, st));
+            if (swap_seed) std::swap(h->buffers[swap_seed].dptr, h->buffers[swap_seed].twin);
             break;
         }
         case K_CLEAR: {
@@ -491,7 +521,7 @@ int launch_kernel(qgpu* h, int kid) {
             if (!buf_ptr(h, k, 0) || !valid_buf(h, pb) || !arg_int(k, 2, &samples)) return fail(h, "kernel %s: arguments (seed table, prns, samples) not set", k.name.c_str());
             if (c.prng_precision == 2) return fail(h, "kernel %s: PRNG_PRECISION=2 (double PRNs) is not implemented", k.name.c_str());
             if (h->buffers[pb].bytes < (size_t)k.global[0] * samples * 16) return fail(h, "kernel %s: PRN buffer too small", k.name.c_str());
-            if (h->buffers[pb].pending_partly_fused) { h->buffers[pb].pending_produce = 0; h->buffers[pb].pending_partly_fused = false; }   // previous pass: consumed by its x-range launches
+            if (h->buffers[pb].pending_partly_fused) finish_partial_pass(h, pb);   // previous pass: consumed by its x-range launches
             if (flush_pending(h, pb) < 0) return -1;   // an unconsumed earlier produce() must still advance the streams
             if (h->fused) { h->buffers[pb].pending_produce = kid; return 0; }   // decided at the consumer
             CUDA_OK(h, launch_prn_produce(k.prn_kind, (uint32_t*)buf_ptr(h, k, 0), h->buffers[pb].dptr, (uint32_t)k.global[0], (uint32_t)samples, st));
@@ -592,6 +622,7 @@ int qgpu_device_finalize(qgpu* h, int error_code) {
     cudaStreamSynchronize(h->stream);
     for (size_t i = 1; i < h->buffers.size(); i++) {
         if (h->buffers[i].dptr) cudaFree(h->buffers[i].dptr);
+        if (h->buffers[i].twin) cudaFree(h->buffers[i].twin);
         if (h->buffers[i].shadow) cudaFreeHost(h->buffers[i].shadow);
         h->buffers[i] = Buffer();
     }
@@ -717,6 +748,7 @@ int qgpu_buffer_init(qgpu* h, int type, size_t size, const void* host_ptr, size_
 }
 int qgpu_buffer_write(qgpu* h, int bid) {
     if (!valid_buf(h, bid)) return fail(h, "buffer_write: bad buffer id %d", bid);
+    settle_state_table(h, bid);
     Buffer& b = h->buffers[bid];
     if (!b.dptr || !b.host_ptr) return 0;
     CUDA_OK(h, cudaSetDevice(h->device));
@@ -731,6 +763,7 @@ void* qgpu_buffer_map_range(qgpu* h, int bid, size_t off, size_t len) {
     if (!b.dptr) { fail(h, "buffer_map: buffer %d has no device storage (LDS)", bid); return nullptr; }
     if (off + len > b.bytes) { fail(h, "buffer_map: range [%zu,+%zu) outside buffer of %zu bytes", off, len, b.bytes); return nullptr; }
     CUDA_OKP(h, cudaSetDevice(h->device));
+    settle_state_table(h, bid);
     if (flush_pending(h, bid) < 0) return nullptr;
     if (!b.shadow) CUDA_OKP(h, cudaMallocHost(&b.shadow, b.bytes));      // pinned: D2H at full PCIe rate
     CUDA_OKP(h, cudaMemcpyAsync((char*)b.shadow + off, (char*)b.dptr + off, len, cudaMemcpyDeviceToHost, h->stream));
@@ -749,6 +782,7 @@ int qgpu_buffer_unmap(qgpu* h, int bid, void* ptr) {
     size_t off = (char*)ptr - (char*)b.shadow;
     if (off != b.map_off) return fail(h, "buffer_unmap: pointer does not match the mapped range");
     CUDA_OK(h, cudaSetDevice(h->device));
+    settle_state_table(h, bid);
     CUDA_OK(h, cudaMemcpyAsync((char*)b.dptr + off, ptr, b.map_len, cudaMemcpyHostToDevice, h->stream));
     CUDA_OK(h, cudaStreamSynchronize(h->stream));
     return 0;
@@ -759,6 +793,7 @@ int qgpu_buffer_kill(qgpu* h, int bid) {
     CUDA_OK(h, cudaSetDevice(h->device));
     CUDA_OK(h, cudaStreamSynchronize(h->stream));
     if (b.dptr) cudaFree(b.dptr);
+    if (b.twin) cudaFree(b.twin);
     if (b.shadow) cudaFreeHost(b.shadow);
     b = Buffer();
     return 0;
@@ -766,7 +801,7 @@ int qgpu_buffer_kill(qgpu* h, int bid) {
 size_t qgpu_buffer_size_bytes(qgpu* h, int bid) { return valid_buf(h, bid) ? h->buffers[bid].bytes : 0; }
 unsigned qgpu_buffer_size_align_step(qgpu*, unsigned size, unsigned step) { return (1 + (size - 1) / step) * step; }   // clinterface.cpp:1587-1590
 unsigned qgpu_buffer_size_align(qgpu* h, unsigned size) { return qgpu_buffer_size_align_step(h, size, (unsigned)h->info.max_workgroup_size); }
-void* qgpu_buffer_device_ptr(qgpu* h, int bid) { return valid_buf(h, bid) ? h->buffers[bid].dptr : nullptr; }
+void* qgpu_buffer_device_ptr(qgpu* h, int bid) { if (valid_buf(h, bid)) settle_state_table(h, bid); return valid_buf(h, bid) ? h->buffers[bid].dptr : nullptr; }
 
 int qgpu_synchronize(qgpu* h) {
     CUDA_OK(h, cudaSetDevice(h->device));

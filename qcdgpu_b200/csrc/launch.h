@@ -27,6 +27,8 @@ struct UpdateArgs {
     int prn_kind;
     const void* prns;       // float4* (buffered)
     uint32_t* prn_table;    // generator state (fused)
+    uint32_t* prn_table_out;  // RANLUX two-phase kernel: where the advanced state goes (!= prn_table: the state in front of the
+                              // pass stays readable for the whole launch; == prn_table or null: in place)
     uint32_t prn_instances;
     uint32_t prn_samples;
     int overrelax;          // 1: overrelaxation pass instead of heat bath (no PRNs)

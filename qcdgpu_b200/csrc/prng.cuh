@@ -140,21 +140,14 @@ struct Ranlux {
     // Parked samples stay RAW (four seeds << 8): only the ~7 of 33 that a link really consumes get converted, by the
     // consumer.  The exception is a sample containing a number below 2^-12, whose fix-up needs a seed that is gone
     // later: it is converted here and flagged in `*converted` (bit k).  Whole 24-number blocks avoid the register rotation.
-    // If `snap` is given, the generator state in front of sample `keep` is left there (26 words, word w at snap[w * stride]):
-    // a consumer that runs past the parked samples regenerates the rest of the pass's stream from it (ranlux_overflow).
     template <int NSKIP> __device__ __forceinline__ void run_pass(uint4* out, uint32_t stride, uint32_t keep, uint32_t samples,
-                                                                  unsigned long long* converted, uint32_t* snap = nullptr) {
+                                                                  unsigned long long* converted) {
         uint32_t k = 0;
         unsigned long long conv = 0ull;
 #pragma unroll 1
         while (k < samples) {
-            if (snap != nullptr && k == keep) {     // canonical ring here: every path below ends on a sample boundary
-#pragma unroll
-                for (int w = 0; w < 24; w++) snap[w * stride] = s[w];
-                snap[24 * stride] = carry; snap[25 * stride] = left;
-            }
             if (left == 0) { luxury_skip<NSKIP>(); left = 24; }
-            if (left == 24 && k + 6 <= samples && (snap == nullptr || k >= keep || k + 6 <= keep)) {
+            if (left == 24 && k + 6 <= samples) {
                 uint32_t old[9];
 #pragma unroll
                 for (int i = 0; i < 9; i++) old[i] = s[i];
@@ -230,17 +223,18 @@ __device__ __forceinline__ void ranlux_store(const Ranlux& r, uint32_t* table, u
     table[size_t(24) * instances + i] = r.carry;
     table[size_t(25) * instances + i] = r.left;
 }
-// Rare path of the two-phase kernel: sample number keep + `skip` of the pass, regenerated from the state snapshot that
-// run_pass left in shared memory.  Not inlined: its 26 state registers must not count against the physics phase.
+// Rare path of the two-phase kernel: sample number `index` of the pass, regenerated from the generator state in front of
+// the pass (word w at state[w * instances]; the kernel writes the advanced state to the other table).  Not inlined: its
+// 26 state registers must not count against the physics phase.
 template <int NSKIP>
-__device__ __noinline__ float4 ranlux_overflow(const uint32_t* snap, uint32_t stride, uint32_t skip) {
+__device__ __noinline__ float4 ranlux_overflow(const uint32_t* state, uint32_t instances, uint32_t index) {
     Ranlux r;
 #pragma unroll
-    for (int w = 0; w < 24; w++) r.s[w] = snap[w * stride];
-    r.carry = snap[24 * stride]; r.left = snap[25 * stride];
+    for (int w = 0; w < 24; w++) r.s[w] = state[size_t(w) * instances];
+    r.carry = state[size_t(24) * instances]; r.left = state[size_t(25) * instances];
     F4 v = r.template next4<NSKIP>();
 #pragma unroll 1
-    for (uint32_t i = 0; i < skip; i++) v = r.template next4<NSKIP>();
+    for (uint32_t i = 0; i < index; i++) v = r.template next4<NSKIP>();
     return make_float4(v.x, v.y, v.z, v.w);
 }
 // ranlux_init (prngcl_ranlux.cl:97-157): 24 seeds from one 31-bit seed through L'Ecuyer's LCG

@@ -90,19 +90,21 @@ struct PrnRanlux {
 // RANLUX, two-phase: phase 1 of the kernel runs the whole generator work of the pass (all `samples` vec4,
 // luxury skips included) and parks the first `keep` vec4 in shared memory; phase 2 (the fp64/fp32 physics) reads them
 // from there.  The 26 state registers are dead during phase 2, which is what lets three blocks share an SM.
-// A link consumes 6-8 vec4 on average and at most 3 (NHIT+1) NHITPar = 33: `keep` defaults to 12 (update_inst.cu), and a
-// thread that needs more regenerates them from the state snapshot taken in front of sample `keep` (ranlux_overflow;
-// probability ~1e-5 per link at beta = 6).  Shared memory per block: 24.6 + 13.3 KB instead of 67.6 KB.
+// A link consumes 6-8 vec4 on average and at most 3 (NHIT+1) NHITPar = 33: `keep` defaults to 12 (update_inst.cu).  The
+// advanced generator state is written to a SECOND table (the backend swaps the two after the pass), so the state in front
+// of the pass stays intact and a thread that needs more than `keep` samples regenerates them from it (ranlux_overflow;
+// probability ~1e-5 per link at beta = 6).  Shared memory per block: 24.6 KB instead of 67.6 KB.
 template <int NSKIP>
 struct PrnSmemT {
     struct Args { int dummy; };
-    const uint4* p; uint32_t k, stride, keep; unsigned long long converted; const uint32_t* snap;
-    __device__ __forceinline__ PrnSmemT(const uint4* base, uint32_t stride_, unsigned long long conv, uint32_t keep_, const uint32_t* snap_)
-        : p(base), k(0), stride(stride_), keep(keep_), converted(conv), snap(snap_) {}
+    const uint4* p; uint32_t k, stride, keep; unsigned long long converted; const uint32_t* state; uint32_t instances;
+    __device__ __forceinline__ PrnSmemT(const uint4* base, uint32_t stride_, unsigned long long conv, uint32_t keep_,
+                                        const uint32_t* state_, uint32_t instances_)
+        : p(base), k(0), stride(stride_), keep(keep_), converted(conv), state(state_), instances(instances_) {}
     // parked samples are raw seeds << 8 unless flagged as already converted (run_pass, prng.cuh)
     __device__ __forceinline__ F4 get(uint32_t i) const {
         if (i >= keep) {
-            float4 v = ranlux_overflow<NSKIP>(snap, stride, i - keep);
+            float4 v = ranlux_overflow<NSKIP>(state, instances, i);
             return { v.x, v.y, v.z, v.w };
         }
         uint4 r = p[i * stride];
@@ -763,10 +765,8 @@ update_kernel(R* __restrict__ table, const R* __restrict__ params, const __grid_
 template <int SUN, typename R, int MU, bool TBC, int NSKIP>
 __global__ void __launch_bounds__(kUpdateThreads, (((sizeof(R) == 8 && SUN == 3) ? 3 : 4) * 128) / kUpdateThreads)
 update_kernel_rlx(R* __restrict__ table, const R* __restrict__ params, const __grid_constant__ Geom g, int odd,
-                  uint32_t* __restrict__ rtable, uint32_t instances, uint32_t samples, uint32_t keep, uint32_t snapshot) {
+                  const uint32_t* rtable, uint32_t* rtable_out, uint32_t instances, uint32_t samples, uint32_t keep) {
     extern __shared__ uint4 prn_smem[];
-    // [keep vec4 per thread][26 snapshot words per thread, only if the pass can consume more than `keep`]
-    uint32_t* snap = snapshot ? reinterpret_cast<uint32_t*>(prn_smem + size_t(keep) * kUpdateThreads) + threadIdx.x : nullptr;
     uint32_t GID = blockIdx.x * blockDim.x + threadIdx.x;
     if (GID >= g.nthreads) return;
     GID = remap_gid(g, GID);
@@ -775,8 +775,8 @@ update_kernel_rlx(R* __restrict__ table, const R* __restrict__ params, const __g
     if (g.debug_skip != 1u) {   // phase 1: the pass's whole RANLUX work
         Ranlux r;
         ranlux_load(r, rtable, instances, GID);
-        r.template run_pass<NSKIP>(prn_smem + threadIdx.x, kUpdateThreads, keep, samples, &converted, snap);
-        ranlux_store(r, rtable, instances, GID);
+        r.template run_pass<NSKIP>(prn_smem + threadIdx.x, kUpdateThreads, keep, samples, &converted);
+        ranlux_store(r, rtable_out, instances, GID);
     }
     if (g.debug_skip == 2u) return;
     // phase 2: the link update
@@ -784,7 +784,8 @@ update_kernel_rlx(R* __restrict__ table, const R* __restrict__ params, const __g
     const Twist<R> tw = make_twist<SUN, R, TBC>(params);
     uint32_t gindex = parity_gid(g, GID, odd != 0);
     typedef PrnSmemT<NSKIP> PrnSmem;
-    PrnSmem prn(prn_smem + threadIdx.x, kUpdateThreads, converted, snapshot ? keep : 0xffffffffu, snap);
+    // in place (rtable_out == rtable) the launcher parks every sample a link can consume, the rare path is unreachable
+    PrnSmem prn(prn_smem + threadIdx.x, kUpdateThreads, converted, (rtable_out != rtable) ? keep : 0xffffffffu, rtable + GID, instances);
     if (SUN == 3) update_site_su3<R, MU, TBC, PrnSmem>(table, g, beta, tw, gindex, prn);
     else          update_site_su2<R, MU, TBC, PrnSmem>(table, g, beta, tw, gindex, prn);
 }

@@ -37,12 +37,19 @@ static cudaError_t launch_rlx(const UpdateArgs& a, cudaStream_t st) {
     // the most a link can consume in a pass (SU(2): one Kennedy-Pendleton instance, su2_update_cl.cl:534-550)
     uint32_t need = (INST_SUN == 3 ? 3u : 1u) * (a.geom.nhit + 1u) * a.geom.nhitpar;
     if (need > a.prn_samples) need = a.prn_samples;
-    // parked per thread: `keep` samples; the rest is regenerated on demand from a state snapshot (update.cuh, PrnSmemT)
+    // With a separate output table the state in front of the pass survives the launch: park `keep` samples per thread, the rest
+    // is regenerated on demand (update.cuh, PrnSmemT).  In place: park everything a link can consume.
     static int keep_env = -1;
     if (keep_env < 0) { const char* e = getenv("QCDGPU_RLX_KEEP"); keep_env = e ? atoi(e) : 12; if (keep_env < 1) keep_env = 1; if (keep_env > 64) keep_env = 64; }
-    uint32_t keep = need < (uint32_t)keep_env ? need : (uint32_t)keep_env;
-    const uint32_t snapshot = keep < need ? 1u : 0u;
-    size_t smem = size_t(keep) * kUpdateThreads * sizeof(float4) + (snapshot ? size_t(26) * kUpdateThreads * sizeof(uint32_t) : 0);
+    uint32_t* out = a.prn_table_out ? a.prn_table_out : a.prn_table;
+    uint32_t keep = need;
+    if (out != a.prn_table && (uint32_t)keep_env < need) keep = (uint32_t)keep_env;
+    size_t smem = size_t(keep) * kUpdateThreads * sizeof(float4);
+    if (smem > 200 * 1024 || keep > 64) {   // does not fit (smem, or the 64-bit "already converted" mask): state-in-registers variant
+        if (out != a.prn_table) return cudaErrorInvalidValue;
+        PrnRanlux<223>::Args pa = { a.prn_table, a.prn_instances, a.prn_samples };
+        return launch_one<TBC, PrnRanlux<223>>(a, pa, st);
+    }
     auto kern = update_kernel_rlx<INST_SUN, RealT, INST_MU, TBC, 223>;
     static size_t configured = 0;
     if (smem > configured) {
@@ -53,7 +60,7 @@ static cudaError_t launch_rlx(const UpdateArgs& a, cudaStream_t st) {
     dim3 block(kUpdateThreads), grid((a.geom.nthreads + kUpdateThreads - 1) / kUpdateThreads);
     if (grid.x == 0) return cudaSuccess;
     kern<<<grid, block, smem, st>>>(static_cast<RealT*>(a.table), static_cast<const RealT*>(a.params), a.geom, a.odd,
-                                    a.prn_table, a.prn_instances, a.prn_samples, keep, snapshot);
+                                    a.prn_table, out, a.prn_instances, a.prn_samples, keep);
     return cudaGetLastError();
 }
 template <bool TBC>
