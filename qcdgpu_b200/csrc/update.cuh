@@ -770,11 +770,11 @@ update_kernel_rlx(R* __restrict__ table, const R* __restrict__ params, const __g
     uint32_t GID = blockIdx.x * blockDim.x + threadIdx.x;
     if (GID >= g.nthreads) return;
     GID = remap_gid(g, GID);
-    prefetch_site_head<SUN, R, MU>(table, g, parity_gid(g, GID, odd != 0));
     unsigned long long converted = 0ull;
+    Ranlux r;
+    if (g.debug_skip != 1u) ranlux_load(r, rtable, instances, GID);     // 26 DRAM loads in flight while the site's addresses are formed
+    prefetch_site_head<SUN, R, MU>(table, g, parity_gid(g, GID, odd != 0));
     if (g.debug_skip != 1u) {   // phase 1: the pass's whole RANLUX work
-        Ranlux r;
-        ranlux_load(r, rtable, instances, GID);
         r.template run_pass<NSKIP>(prn_smem + threadIdx.x, kUpdateThreads, keep, samples, &converted);
         ranlux_store(r, rtable_out, instances, GID);
     }
