@@ -84,6 +84,43 @@ __device__ __forceinline__ uint32_t remap_gid(const Geom& g, uint32_t k) {
     const uint32_t yz = r - xi * P;
     return yz + P * (t + g.n4 * (g.upd_x0 + x0 + xi));
 }
+// remap_gid + parity_gid + gid_to_coords in one go: the tiled thread index already splits into (x, t, yz), so the site's
+// GID, lattice index and coordinates cost 4 integer divisions instead of 9.  Same values as the three functions above
+// (2 GID + odd = (2 yh + odd) + N2 z + N2 N3 (t + N4 x); the checkerboard correction moves y by at most one inside its pair).
+struct SiteId { uint32_t GID, gindex; Coord p; };
+__device__ __forceinline__ SiteId thread_site(const Geom& g, uint32_t k, bool odd) {
+    const uint32_t H = g.n2 >> 1, P = H * g.n3;              // threads per y-row, per (x,t) plane
+    uint32_t x, t, yz;
+    if (g.tile_x == 0) {
+        const uint32_t G0 = k + g.upd_x0 * g.n4 * P, XP = g.n4 * P;
+        x = G0 / XP;
+        const uint32_t r = G0 - x * XP;
+        t = r / P;
+        yz = r - t * P;
+    } else {
+        const uint32_t chunk = g.tile_x * g.n4 * P;
+        const uint32_t xc = k / chunk;
+        uint32_t r = k - xc * chunk;
+        const uint32_t x0 = xc * g.tile_x;
+        const uint32_t wp = min(g.tile_x, g.upd_nx - x0) * P;
+        t = r / wp;
+        r -= t * wp;
+        const uint32_t xi = r / P;
+        yz = r - xi * P;
+        x = g.upd_x0 + x0 + xi;
+    }
+    const uint32_t z = yz / H, yh = yz - z * H;
+    SiteId s;
+    s.GID = yz + P * (t + g.n4 * x);
+    const uint32_t o = odd ? 1u : 0u;
+    const uint32_t y0 = 2u * yh + o;
+    const uint32_t par = (x + y0 + z + t) & 1u;
+    const int adj = odd ? -int(par ^ 1u) : int(par);
+    s.gindex = uint32_t(int(2u * s.GID + o) + adj);
+    s.p.x = x; s.p.y = uint32_t(int(y0) + adj); s.p.z = z; s.p.t = t;
+    if (g.biglat) { s.gindex += g.n234; s.p.x += 1u; }
+    return s;
+}
 template <int DIR> __device__ __forceinline__ Coord nb_plus(const Geom& g, Coord c) {
     // sun_common.cl:455-483
     if (DIR == 0) { c.x++; if (!g.biglat && c.x >= g.n1) c.x = 0; }

@@ -545,9 +545,8 @@ template <typename R, int MU, bool TBC> struct Su3Stage {
 
 // first things a site update will read: its own link and the first plane (issued before the generator phase)
 template <int SUN, typename R, int MU>
-__device__ __forceinline__ void prefetch_site_head(const R* table, const Geom& g, uint32_t gindex) {
+__device__ __forceinline__ void prefetch_site_head(const R* table, const Geom& g, uint32_t gindex, const Coord& p) {
     constexpr int NPL = (SUN == 3) ? 3 : 1;
-    Coord p = gid_to_coords(g, gindex);
     Coord pmu = nb_plus<MU>(g, p);
     PlaneSites s0 = plane_sites<MU, PlaneOrder<MU>::n0>(g, p, pmu);
     prefetch_link<R, MU, NPL>(table, g, gindex);
@@ -651,8 +650,7 @@ __device__ __forceinline__ V4<R> staple2(const R* table, const Geom& g, const Co
 template <typename R, int MU, class Prn>
 __device__ __forceinline__ void heatbath_su3(R* table, const Geom& g, R beta, uint32_t gindex, const M3r2<R>& m0, const M3<R>& S, Prn& prn);
 template <typename R, int MU, bool TBC, class Prn>
-__device__ __forceinline__ void update_site_su3(R* table, const Geom& g, R beta, const Twist<R>& tw, uint32_t gindex, Prn& prn) {
-    Coord p = gid_to_coords(g, gindex);
+__device__ __forceinline__ void update_site_su3(R* table, const Geom& g, R beta, const Twist<R>& tw, uint32_t gindex, const Coord& p, Prn& prn) {
     M3<R> S = staple3<R, MU, TBC>(table, g, p, gindex, tw);
     M3r2<R> m0 = load3<R, MU, TBC>(table, g, gindex, p.x, tw);     // after the staples: 24 registers less while they are formed
     heatbath_su3<R, MU, Prn>(table, g, beta, gindex, m0, S, prn);
@@ -681,8 +679,7 @@ __device__ __forceinline__ void heatbath_su3(R* table, const Geom& g, R beta, ui
     store3<R, MU>(table, g, gindex, U.e[0], U.e[1]);
 }
 template <typename R, int MU, bool TBC, class Prn>
-__device__ __forceinline__ void update_site_su2(R* table, const Geom& g, R beta, const Twist<R>& tw, uint32_t gindex, Prn& prn) {
-    Coord p = gid_to_coords(g, gindex);
+__device__ __forceinline__ void update_site_su2(R* table, const Geom& g, R beta, const Twist<R>& tw, uint32_t gindex, const Coord& p, Prn& prn) {
     V4<R> S = staple2<R, MU, TBC>(table, g, p, gindex, tw);
     // su2_update_cl.cl:448-461: aH = S^+/|S|, det = 2|S|
     R n = Mth<R>::sqrt_(S.x * S.x + S.y * S.y + S.z * S.z + S.w * S.w);
@@ -748,18 +745,19 @@ __global__ void __launch_bounds__(kUpdateThreads, (Prn::kMinBlocks * 128) / kUpd
 update_kernel(R* __restrict__ table, const R* __restrict__ params, const __grid_constant__ Geom g, int odd, typename Prn::Args pargs) {
     uint32_t GID = blockIdx.x * blockDim.x + threadIdx.x;
     if (GID >= g.nthreads) return;
-    GID = remap_gid(g, GID);
+    const SiteId site = thread_site(g, GID, odd != 0);
+    GID = site.GID;
     const R beta = params[0];
     const Twist<R> tw = make_twist<SUN, R, TBC>(params);
-    uint32_t gindex = parity_gid(g, GID, odd != 0);
+    const uint32_t gindex = site.gindex;
     Prn prn(pargs, g, GID, gindex);
     if constexpr (SUN == 3 && kStageK > 0) {
         extern __shared__ uint4 dyn_smem[];
         Su3Stage<R, MU, TBC> stage;
         stage.begin(dyn_smem + threadIdx.x, table, g, gindex);
         update_site_su3_staged<R, MU, TBC, Prn>(table, g, beta, tw, stage, prn);
-    } else if constexpr (SUN == 3) update_site_su3<R, MU, TBC, Prn>(table, g, beta, tw, gindex, prn);
-    else          update_site_su2<R, MU, TBC, Prn>(table, g, beta, tw, gindex, prn);
+    } else if constexpr (SUN == 3) update_site_su3<R, MU, TBC, Prn>(table, g, beta, tw, gindex, site.p, prn);
+    else          update_site_su2<R, MU, TBC, Prn>(table, g, beta, tw, gindex, site.p, prn);
     prn.finish();
 }
 template <int SUN, typename R, int MU, bool TBC, int NSKIP>
@@ -769,11 +767,14 @@ update_kernel_rlx(R* __restrict__ table, const R* __restrict__ params, const __g
     extern __shared__ uint4 prn_smem[];
     uint32_t GID = blockIdx.x * blockDim.x + threadIdx.x;
     if (GID >= g.nthreads) return;
-    GID = remap_gid(g, GID);
+    const SiteId site = thread_site(g, GID, odd != 0);
+    GID = site.GID;
     unsigned long long converted = 0ull;
     Ranlux r;
     if (g.debug_skip != 1u) ranlux_load(r, rtable, instances, GID);     // 26 DRAM loads in flight while the site's addresses are formed
-    prefetch_site_head<SUN, R, MU>(table, g, parity_gid(g, GID, odd != 0));
+    const uint32_t gindex = site.gindex;
+    const Coord p = site.p;                                               // kept across the generator phase (5 registers)
+    prefetch_site_head<SUN, R, MU>(table, g, gindex, p);
     if (g.debug_skip != 1u) {   // phase 1: the pass's whole RANLUX work
         r.template run_pass<NSKIP>(prn_smem + threadIdx.x, kUpdateThreads, keep, samples, &converted);
         ranlux_store(r, rtable_out, instances, GID);
@@ -782,20 +783,18 @@ update_kernel_rlx(R* __restrict__ table, const R* __restrict__ params, const __g
     // phase 2: the link update
     const R beta = params[0];
     const Twist<R> tw = make_twist<SUN, R, TBC>(params);
-    uint32_t gindex = parity_gid(g, GID, odd != 0);
     typedef PrnSmemT<NSKIP> PrnSmem;
     // in place (rtable_out == rtable) the launcher parks every sample a link can consume, the rare path is unreachable
     PrnSmem prn(prn_smem + threadIdx.x, kUpdateThreads, converted, (rtable_out != rtable) ? keep : 0xffffffffu, rtable + GID, instances);
-    if (SUN == 3) update_site_su3<R, MU, TBC, PrnSmem>(table, g, beta, tw, gindex, prn);
-    else          update_site_su2<R, MU, TBC, PrnSmem>(table, g, beta, tw, gindex, prn);
+    if (SUN == 3) update_site_su3<R, MU, TBC, PrnSmem>(table, g, beta, tw, gindex, p, prn);
+    else          update_site_su2<R, MU, TBC, PrnSmem>(table, g, beta, tw, gindex, p, prn);
 }
 template <int SUN, typename R, int MU>
 __global__ void __launch_bounds__(kUpdateThreads)
 overrelax_kernel(R* __restrict__ table, const __grid_constant__ Geom g, int odd) {
     uint32_t GID = blockIdx.x * blockDim.x + threadIdx.x;
     if (GID >= g.nthreads) return;
-    GID = remap_gid(g, GID);
-    uint32_t gindex = parity_gid(g, GID, odd != 0);
+    const uint32_t gindex = thread_site(g, GID, odd != 0).gindex;
     if (SUN == 3) overrelax_site_su3<R, MU>(table, g, gindex);
     else          overrelax_site_su2<R, MU>(table, g, gindex);
 }
