@@ -32,7 +32,7 @@ class OrcCfg(C.Structure):
 def build(force: bool = False) -> str:
     if force or not os.path.exists(LIB_PATH) or any(
             os.path.getmtime(os.path.join(ORACLE_DIR, f)) > os.path.getmtime(LIB_PATH)
-            for f in ("qcd_oracle.c", "qcd_oracle_lattice.inc", "qcd_oracle.h")):
+            for f in ("qcd_oracle.c", "qcd_oracle_lattice.inc", "qcd_oracle.h", "on_oracle.c", "on_oracle.inc", "on_oracle.h")):
         subprocess.check_call(["make", "-C", ORACLE_DIR, "liboracle.so"], stdout=subprocess.DEVNULL)
     return LIB_PATH
 
@@ -189,3 +189,95 @@ def host_stream(generator: str, randseries: int, n: int) -> np.ndarray:
     out = np.empty(n, dtype=np.float32)
     lib().orc_prng_host_stream(PRNG_IDS[generator], randseries, n, out.ctypes.data_as(C.c_void_p))
     return out
+
+
+# ---------------------------------------------------------------------------------------------- O(N) scalar branch
+ON_CHECK_BIN = os.path.join(ORACLE_DIR, "_ref", "on_check")
+# defaults of the reference's O(N)/QCDGPU.cpp:119-126
+ON_DEFAULTS = dict(z=0.1561573990981998, lam=0.25, zeta=0.25, eta=0.1, b=9.661840260273483, skgroup=4)
+
+
+class OrcOnCfg(C.Structure):
+    _fields_ = [("n1", C.c_uint32), ("n2", C.c_uint32), ("n3", C.c_uint32), ("n4", C.c_uint32),
+                ("prngstep", C.c_uint32), ("nhit", C.c_uint32), ("skgroup", C.c_uint32)]
+
+
+def on_params(z, lam, zeta, eta, b, dtype=np.float64, size=64) -> np.ndarray:
+    p = np.zeros(size, dtype=np.float64)
+    lib().orc_on_params(C.c_double(z), C.c_double(lam), C.c_double(zeta), C.c_double(eta), C.c_double(b),
+                        p.ctypes.data_as(C.c_void_p))
+    return p.astype(dtype)
+
+
+@dataclass
+class OnLattice:
+    """Oracle-side O(N) lattice: one real per site, index gid = y + z N2 + t N2 N3 + x N2 N3 N4."""
+    dims: tuple
+    precision: str = "f64"
+    nhit: int = 10
+    wg: int = 64
+    z: float = ON_DEFAULTS["z"]
+    lam: float = ON_DEFAULTS["lam"]
+    zeta: float = ON_DEFAULTS["zeta"]
+    eta: float = ON_DEFAULTS["eta"]
+    b: float = ON_DEFAULTS["b"]
+    skgroup: int = ON_DEFAULTS["skgroup"]
+
+    def __post_init__(self):
+        n1, n2, n3, n4 = self.dims
+        self.sites = n1 * n2 * n3 * n4
+        self.prngstep = align(self.sites // 2, self.wg)
+        self.dtype = np.float64 if self.precision == "f64" else np.float32
+        self.table = np.zeros(align(self.sites, self.wg), dtype=self.dtype)
+        self.cfg = OrcOnCfg(n1, n2, n3, n4, self.prngstep, self.nhit, self.skgroup)
+        self.params = on_params(self.z, self.lam, self.zeta, self.eta, self.b, self.dtype)
+
+    def _fn(self, name):
+        return getattr(lib(), f"{name}_{self.precision}")
+
+    def _t(self):
+        return self.table.ctypes.data_as(C.c_void_p)
+
+    def _p(self):
+        return self.params.ctypes.data_as(C.c_void_p)
+
+    def init_cold(self):
+        self._fn("orc_on_init_cold")(C.byref(self.cfg), self._t())
+
+    def init_hot(self, prns):
+        prns = np.ascontiguousarray(prns, dtype=np.float32)
+        self._fn("orc_on_init_hot")(C.byref(self.cfg), self._t(), prns.ctypes.data_as(C.c_void_p), self._p())
+
+    def update(self, prns, odd: int) -> float:
+        prns = np.ascontiguousarray(prns, dtype=np.float32)
+        acc = C.c_double()
+        self._fn("orc_on_update")(C.byref(self.cfg), self._t(), self._p(), prns.ctypes.data_as(C.c_void_p), odd, C.byref(acc))
+        return acc.value
+
+    def _two(self, name, *extra):
+        out = (C.c_double * 2)()
+        self._fn(name)(C.byref(self.cfg), self._t(), self._p(), *extra, out)
+        return out[0], out[1]
+
+    def measure_action(self):
+        return self._two("orc_on_measure_action")
+
+    def measure_plq(self):
+        return self._two("orc_on_measure_plq")
+
+    def measure_corr(self, step):
+        s = (C.c_uint32 * 4)(*step)
+        return self._two("orc_on_measure_corr", s)
+
+    def reference_check(self, step=(1, 1, 1, 1)):
+        """Run the UNMODIFIED reference checker (oracle/_ref/on_check) on this table: per-site means
+        (S, phi, phi^2, variance, corr1, corr2) as SU::lattice_check_cpu stores them."""
+        import tempfile
+        with tempfile.NamedTemporaryFile(suffix=".bin") as f:
+            f.write(self.table[:self.sites].tobytes())
+            f.flush()
+            args = [ON_CHECK_BIN, f.name, *map(str, self.dims), "1" if self.precision == "f64" else "0",
+                    repr(self.z), repr(self.lam), repr(self.zeta), repr(self.eta), repr(self.b), str(self.skgroup),
+                    *map(str, step)]
+            out = subprocess.check_output(args, text=True)
+        return [float(v) for v in out.split()]
