@@ -41,6 +41,7 @@ def _units():
                           [f"-DINST_SUN={sun}", f"-DINST_PREC={prec}", f"-DINST_MU={mu}"]))
             u.append((f"measure_{sun}_{prec}.o", "measure_inst.cu", [f"-DINST_SUN={sun}", f"-DINST_PREC={prec}"]))
     u.append(("misc.o", "misc_inst.cu", []))
+    u.append(("on_model.o", "on_inst.cu", []))
     u.append(("dispatch.o", "dispatch.cu", []))
     u.append(("backend.o", "backend.cu", []))
     # heaviest first

@@ -39,13 +39,17 @@ struct ProgramCfg {
     int fmunu_gen1 = 0, fmunu_gen2 = 0;      // -D FMUNU1/2/4 and FMUNU5/6/7 (0: lambda_3 resp. lambda_8)
     uint32_t plk = 0, plk_axis[3] = { 0, 0, 0 };   // -D PLK, PLKx, PLKy, PLKz (slice-resolved kernels)
     bool has_lattice = false;
+    // O(N) scalar branch (reference tree O(N)/, options assembled in O(N)/suncl/suncl.cpp:1454-1482)
+    bool on_model = false, acc_rate = false, on_sub_scheme = false;
+    uint32_t skgroup = 4, n1exact = 0;
 };
 
 enum KernelKind {
     K_NONE = 0, K_INIT_COLD, K_INIT_GID, K_INIT_HOT, K_GRAMSCHMIDT, K_UPDATE, K_OVERRELAX, K_CLEAR,
     K_MEASURE, K_REDUCE_MEAS, K_MEASURE_PLQ, K_REDUCE_PLQ, K_POLYAKOV, K_REDUCE_POLYAKOV,
     K_POLYAKOV_DIFF, K_REDUCE_POLYAKOV_DIFF, K_WILSON, K_REDUCE_WILSON,
-    K_RANLUX_INIT, K_PRODUCE
+    K_RANLUX_INIT, K_PRODUCE,
+    K_ON_INIT_COLD, K_ON_INIT_HOT, K_ON_UPDATE, K_ON_MEASURE, K_ON_REDUCE
 };
 
 struct Arg {
@@ -176,6 +180,11 @@ void parse_options(const char* opt, ProgramCfg& c) {
         else if (name == "PLKx") c.plk_axis[0] = (uint32_t)v;
         else if (name == "PLKy") c.plk_axis[1] = (uint32_t)v;
         else if (name == "PLKz") c.plk_axis[2] = (uint32_t)v;
+        else if (name == "ON_MODEL") c.on_model = true;
+        else if (name == "ACC_RATE") c.acc_rate = true;
+        else if (name == "ON_SUB_SCHEME") c.on_sub_scheme = true;
+        else if (name == "SKGROUP") c.skgroup = (uint32_t)v;
+        else if (name == "N1EXACT") c.n1exact = (uint32_t)v;
     }
 }
 
@@ -232,6 +241,17 @@ const NameMap kNames[] = {
     { "lattice_measurement_wilson", K_WILSON, 0, 0, 0 }, { "reduce_wilson_double2", K_REDUCE_WILSON, 0, 0, 0 },
     { "ranlux_init", K_RANLUX_INIT, 0, 0, 0 },
     { "ranlux", K_PRODUCE, 0, 0, -1 }, { "xor128", K_PRODUCE, 0, 0, PRN_XOR128 }, { "pm", K_PRODUCE, 0, 0, PRN_PM }, { "mrg32k3a", K_PRODUCE, 0, 0, PRN_MRG32K3A },
+};
+
+// kernel names of a program created with -D ON_MODEL (O(N)/oncl/oncl.cl, on_measurements_cl.cl); dir = what is measured
+const NameMap kNamesOn[] = {
+    { "lattice_init_cold", K_ON_INIT_COLD, 0, 0, 0 }, { "lattice_init_hot", K_ON_INIT_HOT, 0, 0, 0 },
+    { "update_even", K_ON_UPDATE, 0, 0, 0 }, { "update_odd", K_ON_UPDATE, 0, 1, 0 },
+    { "clear_measurement", K_CLEAR, 0, 0, 0 },
+    { "lattice_measurement", K_ON_MEASURE, 0, 0, 0 }, { "lattice_measurement_plq", K_ON_MEASURE, 1, 0, 0 },
+    { "lattice_measurement_correlator", K_ON_MEASURE, 2, 0, 0 },
+    { "reduce_measurement_double2", K_ON_REDUCE, 0, 0, 0 }, { "reduce_measurement_plq_double2", K_ON_REDUCE, 0, 0, 0 },
+    { "reduce_acceptance_rate", K_ON_REDUCE, 0, 0, 0 },
 };
 
 int ranlux_kind(int skip) {
@@ -527,6 +547,83 @@ int launch_kernel(qgpu* h, int kid) {
             CUDA_OK(h, launch_prn_produce(k.prn_kind, (uint32_t*)buf_ptr(h, k, 0), h->buffers[pb].dptr, (uint32_t)k.global[0], (uint32_t)samples, st));
             break;
         }
+        // ------------------------------------------------------------ O(N) scalar branch
+        case K_ON_INIT_COLD: case K_ON_INIT_HOT: {
+            Geom g = make_geom(c);
+            const size_t rb = prec ? 8 : 4;
+            if (!buf_ptr(h, k, 0) || h->buffers[buf_id(k, 0)].bytes < (size_t)g.sites * rb) return fail(h, "kernel %s: argument 0 (lattice_table) not set or smaller than the lattice", k.name.c_str());
+            const void* prns = nullptr; const void* params = nullptr;
+            if (k.kind == K_ON_INIT_HOT) {
+                if (!buf_ptr(h, k, 1) || !buf_ptr(h, k, 2)) return fail(h, "kernel %s: arguments (prns, lattice_parameters) not set", k.name.c_str());
+                if (flush_pending(h, buf_id(k, 1)) < 0) return -1;
+                if (h->buffers[buf_id(k, 1)].bytes < (size_t)g.sites * 16) return fail(h, "kernel %s: PRN buffer too small for a hot start (%zu < %u vec4)", k.name.c_str(), h->buffers[buf_id(k, 1)].bytes / 16, g.sites);
+                if (h->buffers[buf_id(k, 2)].bytes < 23 * rb) return fail(h, "kernel %s: lattice_parameters must hold 23 values", k.name.c_str());
+                prns = buf_ptr(h, k, 1); params = buf_ptr(h, k, 2);
+            }
+            CUDA_OK(h, launch_on_init(prec, buf_ptr(h, k, 0), params, prns, g.sites, st));
+            break;
+        }
+        case K_ON_UPDATE: {
+            OnArgs a;
+            memset(&a, 0, sizeof(a));
+            a.table = buf_ptr(h, k, 0); a.params = buf_ptr(h, k, 1);
+            if (!a.table || !a.params) return fail(h, "kernel %s: arguments (lattice_table, lattice_parameters) not set", k.name.c_str());
+            if (h->buffers[buf_id(k, 1)].bytes < 23 * (size_t)(prec ? 8 : 4)) return fail(h, "kernel %s: lattice_parameters must hold 23 values", k.name.c_str());
+            a.geom = make_geom(c); a.geom.tile_x = 0; a.skgroup = c.skgroup; a.odd = k.odd;
+            if (c.acc_rate) {                                      // (lds, lattice_measurement) follow the PRN buffer
+                a.acc = (double2*)buf_ptr(h, k, 4);
+                if (!a.acc) return fail(h, "kernel %s: -D ACC_RATE needs argument 4 (lattice_measurement)", k.name.c_str());
+                if (h->buffers[buf_id(k, 4)].capacity < (size_t)((a.geom.nthreads + kOnBlock - 1) / kOnBlock) * 16) return fail(h, "kernel %s: measurement buffer too small for the acceptance partials", k.name.c_str());
+            }
+            int pb = buf_id(k, 2);
+            if (!valid_buf(h, pb)) return fail(h, "kernel %s: argument 2 (prns) not set", k.name.c_str());
+            Buffer& pbuf = h->buffers[pb];
+            const uint32_t need = (uint32_t)(c.nhit >> 1) + (uint32_t)(c.nhit & 1);        // vec4 a site can consume (oncl.cl:147-207)
+            bool fused = false;
+            if (pbuf.pending_produce) {
+                Kernel& pk = h->kernels[pbuf.pending_produce];
+                int samples = 0; arg_int(pk, 2, &samples);
+                if (h->fused && (uint32_t)pk.global[0] == a.geom.prngstep && a.geom.nthreads <= a.geom.prngstep &&
+                    (pk.prn_kind == PRN_XOR128 || pk.prn_kind == PRN_PM || pk.prn_kind == PRN_MRG32K3A) && (uint32_t)samples >= need) {
+                    a.prn_kind = pk.prn_kind; a.prn_table = (uint32_t*)buf_ptr(h, pk, 0);
+                    a.prn_instances = (uint32_t)pk.global[0]; a.prn_samples = (uint32_t)samples;
+                    pbuf.pending_produce = 0; fused = true;
+                } else if (flush_pending(h, pb) < 0) return -1;
+            }
+            if (!fused) {
+                a.prn_kind = PRN_BUFFERED; a.prns = pbuf.dptr;
+                size_t need_v4 = (size_t)a.geom.prngstep * (need - 1) + a.geom.nthreads;
+                if (pbuf.bytes < need_v4 * 16) return fail(h, "kernel %s: PRN buffer holds %zu vec4, the pass may read %zu", k.name.c_str(), pbuf.bytes / 16, need_v4);
+            }
+            CUDA_OK(h, launch_on_update(prec, a, st));
+            break;
+        }
+        case K_ON_MEASURE: {
+            OnArgs a;
+            memset(&a, 0, sizeof(a));
+            a.table = buf_ptr(h, k, 0); a.params = buf_ptr(h, k, 2);
+            double2* out = (double2*)buf_ptr(h, k, 1);
+            if (!a.table || !a.params || !out) return fail(h, "kernel %s: arguments (table, measurement, parameters) not set", k.name.c_str());
+            if (h->buffers[buf_id(k, 2)].bytes < 23 * (size_t)(prec ? 8 : 4)) return fail(h, "kernel %s: lattice_parameters must hold 23 values", k.name.c_str());
+            a.geom = make_geom(c); a.skgroup = c.skgroup;
+            uint32_t step[4] = { 0, 0, 0, 0 };
+            if (k.dir == 2) {
+                if (k.args.size() < 5 || k.args[4].type != Arg::U32X4) return fail(h, "kernel %s: argument 4 (lattice_stepz) not set", k.name.c_str());
+                memcpy(step, k.args[4].u4, 16);
+                if (step[0] > c.n1 || step[1] > c.n2 || step[2] > c.n3 || step[3] > c.n4) return fail(h, "kernel %s: correlator step larger than the lattice (one wrap only, neighbours.cl:204-218)", k.name.c_str());
+            }
+            if (h->buffers[buf_id(k, 1)].capacity < (size_t)((a.geom.sites + kOnBlock - 1) / kOnBlock) * 16) return fail(h, "kernel %s: measurement buffer too small", k.name.c_str());
+            CUDA_OK(h, launch_on_measure(prec, a, k.dir, step, out, st));
+            break;
+        }
+        case K_ON_REDUCE: {
+            int size = 0, index = 0;
+            if (!arg_int(k, 3, &size) || !arg_int(k, 4, &index)) return fail(h, "kernel %s: arguments (size, index) not set", k.name.c_str());
+            if (!buf_ptr(h, k, 0) || !buf_ptr(h, k, 1)) return fail(h, "kernel %s: buffers not set", k.name.c_str());
+            if (h->buffers[buf_id(k, 0)].capacity < (size_t)size * 16 || h->buffers[buf_id(k, 1)].capacity < ((size_t)index + 1) * 16) return fail(h, "kernel %s: size/index outside the buffers", k.name.c_str());
+            CUDA_OK(h, launch_on_reduce_add((const double2*)buf_ptr(h, k, 0), (uint32_t)size, (double2*)buf_ptr(h, k, 1), (uint32_t)index, st));
+            break;
+        }
         default:
             return fail(h, "kernel '%s' is not implemented in qcdgpu_b200", k.name.c_str());
     }
@@ -640,8 +737,14 @@ int qgpu_get_device_info(qgpu* h, qgpu_device_info* out) {
 int qgpu_program_create(qgpu* h, const char* /*source*/, const char* options) {
     ProgramCfg c;
     parse_options(options, c);
+    if (c.on_model) {
+        if (c.sun != 1) return fail(h, "program_create: -D ON_MODEL needs SUN=1 (one real per site), got SUN=%d", c.sun);
+        if (c.on_sub_scheme) return fail(h, "program_create: -D ON_SUB_SCHEME (symmetric differences) is not implemented in qcdgpu_b200");
+        if (c.n1exact && c.n1exact != c.n1) return fail(h, "program_create: the multi-part O(N) lattice (N1EXACT=%u != N1=%u) is not implemented in qcdgpu_b200", c.n1exact, c.n1);
+        if (c.nhit < 1) return fail(h, "program_create: NHIT=%d", c.nhit);
+    }
     if (c.has_lattice) {
-        if (c.sun != 2 && c.sun != 3) return fail(h, "program_create: SUN=%d is not supported (2 or 3)", c.sun);
+        if (!c.on_model && c.sun != 2 && c.sun != 3) return fail(h, "program_create: SUN=%d is not supported (2 or 3)", c.sun);
         if (c.nd != 4) return fail(h, "program_create: ND=%d is not supported (4)", c.nd);
         if (!c.n1 || !c.n2 || !c.n3 || !c.n4) return fail(h, "program_create: N1..N4 missing in '%s'", c.options.c_str());
         if (c.n2 & 1) return fail(h, "program_create: N2 must be even for the checkerboard (sun_common.cl:351-380)");
@@ -661,7 +764,9 @@ int qgpu_kernel_init(qgpu* h, const char* name, unsigned dims, const size_t* glo
     if (!h->active_program) return fail(h, "kernel_init('%s') before program_create", name);
     Kernel k;
     k.name = name; k.program = h->active_program;
-    for (const NameMap& m : kNames) if (k.name == m.name) { k.kind = m.kind; k.dir = m.dir; k.odd = m.odd; k.prn_kind = m.prn; }
+    const bool on_model = h->programs[k.program].on_model;
+    if (on_model) { for (const NameMap& m : kNamesOn) if (k.name == m.name) { k.kind = m.kind; k.dir = m.dir; k.odd = m.odd; k.prn_kind = m.prn; } }
+    else for (const NameMap& m : kNames) if (k.name == m.name) { k.kind = m.kind; k.dir = m.dir; k.odd = m.odd; k.prn_kind = m.prn; }
     if (k.kind == K_NONE) return fail(h, "kernel '%s' is not implemented in qcdgpu_b200", name);
     if (k.kind == K_PRODUCE && k.prn_kind < 0) {
         k.prn_kind = ranlux_kind(h->programs[k.program].rl_skip);
@@ -671,6 +776,7 @@ int qgpu_kernel_init(qgpu* h, const char* name, unsigned dims, const size_t* glo
     // clinterface.cpp:1158-1169: explicit local size wins, else the (limited) kernel work-group size
     if (local && local[0]) { k.local0 = local[0]; k.local_given = true; }
     else k.local0 = (k.kind == K_UPDATE || k.kind == K_OVERRELAX) ? 128 : (h->limit_wg ? h->limit_wg : 128);
+    if (k.kind == K_ON_UPDATE || k.kind == K_ON_MEASURE || k.kind == K_ON_INIT_COLD || k.kind == K_ON_INIT_HOT) { k.local0 = kOnBlock; k.local_given = false; }
     if (k.local0 > 128 && (k.kind == K_MEASURE || k.kind == K_MEASURE_PLQ || k.kind == K_POLYAKOV || k.kind == K_WILSON)) k.local0 = 128;
     h->kernels.push_back(k);
     return (int)h->kernels.size() - 1;

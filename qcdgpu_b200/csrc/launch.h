@@ -73,6 +73,18 @@ cudaError_t launch_copy_planes(int prec, void* dst, size_t dst_row, uint32_t xd,
                                const void* src, size_t src_row, uint32_t xs, int sp0, int sps,
                                uint32_t n234, int nplanes, cudaStream_t);
 
+// ---- O(N) scalar branch (on_model.cuh)
+struct OnArgs {
+    void* table; const void* params; Geom geom; uint32_t skgroup; int odd;
+    int prn_kind; const void* prns; uint32_t* prn_table; uint32_t prn_instances, prn_samples;
+    double2* acc;            // -D ACC_RATE: per-block acceptance sums (.x even pass, .y odd pass), or null
+};
+constexpr uint32_t kOnBlock = 128;   // threads per block of every O(N) kernel (= what kernel_get_worksize reports)
+cudaError_t launch_on_update(int prec, const OnArgs&, cudaStream_t);
+cudaError_t launch_on_init(int prec, void* table, const void* params, const void* prns /* null: cold */, uint32_t sites, cudaStream_t);
+cudaError_t launch_on_measure(int prec, const OnArgs&, int what, const uint32_t step[4], double2* out, cudaStream_t);
+cudaError_t launch_on_reduce_add(const double2* table, uint32_t size, double2* dst, uint32_t index, cudaStream_t);
+
 int update_kernel_regs(int sun, int prec, int mu, int tbc, int prn_kind);   // registers/thread (cudaFuncGetAttributes)
 
 }  // namespace qcd

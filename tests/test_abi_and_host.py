@@ -95,3 +95,27 @@ def test_host_rand_matches_glibc():
     assert list(got) == want
     host_srand(54)
     assert list(host_rand_fill(3, 2147483647, 1)) == [w % 2147483647 + 1 for w in want[:3]]
+
+
+def test_on_model_host_logic(tmp_path):
+    """O(N) branch host mirror: parameter derivation (O(N)/suncl/suncl.cpp:1244-1253) against the checker's restatement,
+    init.dat keys (:249-300) and the option string (:1454-1482).  No device call."""
+    import numpy as np
+    import oracle_lib as O
+    from qcdgpu_b200.on_model import OnModel
+    m = OnModel()
+    szl, max_u = m.on_parameters()
+    p = O.on_params(m.ON_z, m.ON_lambda, m.ON_zeta, m.ON_eta, m.ON_b)
+    assert szl == p[21] and abs(max_u - p[22]) < 1e-15
+    m.ON_eta, m.ON_b = 0.0, 4.0
+    assert abs(m.on_parameters()[1] - O.on_params(m.ON_z, m.ON_lambda, m.ON_zeta, 0.0, 4.0)[22]) < 1e-15
+    f = tmp_path / "init.dat"
+    f.write_text("\tGROUP = 1\n\tLS = 32\n\tLT = 32\n\tNHIT = 10\n\tPRNG = XOR128\n\tRANDSERIES = 45\n\tSKGROUP = 4\n"
+                 "\tON_Z = 2.0e-01\n\tON_LAMBDA = 5.0e-01 # quartic\n\tON_ZETA = 0.5\n\tON_ETA = 0.0\n\tON_B = 4.0\n\tINTS = 0\n")
+    m = OnModel()
+    m.lattice_get_init_file(str(f))
+    assert m.lattice_full_size == [32, 32, 32, 32] and (m.ON_z, m.ON_lambda, m.ON_zeta, m.ON_eta, m.ON_b) == (0.2, 0.5, 0.5, 0.0, 4.0)
+    assert m.PRNG0.PRNG_generator == "XOR128" and m.ints == 0 and m.ON_SK_group == 4
+    m.lattice_table_row_size = 32 ** 4
+    o = m.options_common()
+    assert "-D ON_MODEL" in o and "-D SUN=1" in o and "-D SKGROUP=4" in o and "-D N1EXACT=32" in o and "-D ACC_RATE" in o
