@@ -29,7 +29,7 @@ sys.path.insert(0, ROOT)
 
 WORKLOAD = dict(group=3, dims=(64, 64, 64, 64), precision=1, beta=6.0, nhit=10, prng="RANLUX3", randseries=54, ints=1)
 BYTES_PER_LINK_UPDATE = 9 * 96      # SU(3) 2-row fp64: 4 V link reads + V/2 link writes per pass, 8 passes / 4 V links
-NCU_DRAM_BYTES_PER_LAUNCH = 8.148278e9 + 1.934906e9   # profiles/r01_ncu_update_v4_keep12.json
+NCU_DRAM_BYTES_PER_LAUNCH = 8.134629e9 + 1.964846e9   # profiles/r01_ncu_update_v5.json
 FLOPS_PER_LINK_UPDATE = 4700
 
 
@@ -221,7 +221,7 @@ def native_single(args):
     # DRAM bytes of one launch of that kernel from the committed ncu --set full capture (same command, 64^4 fused only)
     traffic, traffic_src = None, None
     if tuple(dims) == (64, 64, 64, 64) and not args.buffered and not args.materialize and not diag:
-        traffic, traffic_src = NCU_DRAM_BYTES_PER_LAUNCH, "profiles/r01_ncu_update_v4_keep12.json (dram__bytes_read.sum + dram__bytes_write.sum)"
+        traffic, traffic_src = NCU_DRAM_BYTES_PER_LAUNCH, "profiles/r01_ncu_update_v5.json (dram__bytes_read.sum + dram__bytes_write.sum)"
     regs = g.update_kernel_registers(m.program_update, 0, 2 if not args.buffered else 0)
     kname = ("update_kernel_rlx<%d,%s,MU,%s,223>" if not args.buffered else "update_kernel<%d,%s,MU,%s,PrnBuffered>") % (
         m.lattice_group, "double" if m.precision == 1 else "float", "true" if args.phi != 0.0 else "false")
@@ -255,6 +255,63 @@ def native_single(args):
     m.close()
 
 
+def native_on(args):
+    """Diagnostic (BASELINE config 4): O(4) scalar model, Metropolis sweeps (odd + even pass) with XOR128 in registers.
+    Prints site updates/s; the bound is the FP64 pipe (4 log + exp + sqrt per proposal, NHIT proposals per site), not HBM."""
+    import numpy as np
+    from qcdgpu_b200.on_model import OnModel
+    dims = tuple(int(x) for x in args.dims.split("x")) if args.dims else (32, 32, 32, 32)
+    m = OnModel()
+    m.lattice_full_size = list(dims)
+    m.precision = 1 if args.precision is None else args.precision
+    m.ints, m.NHIT, m.ITER = 0, 10, 64
+    m.get_acceptance_rate = not args.no_acc
+    m.fused_prng = not args.buffered
+    m.PRNG0.PRNG_generator, m.PRNG0.PRNG_randseries = "XOR128", 45
+    m.lattice_init()
+    m.lattice_start()
+    g = m.GPU0
+    for _ in range(args.warmup):
+        m.lattice_update()
+    g.synchronize()
+    l0 = g.launch_count()
+    g.timer_start()
+    for _ in range(args.steps):
+        m.lattice_update()
+    ms = g.timer_stop()
+    launches = g.launch_count() - l0
+    g.set_debug(profiling=True)
+    for _ in range(3):
+        m.lattice_update()
+    g.set_debug(profiling=False)
+    tk = [g.kernel_get_execution_time(k)[0] for k in m.sun_update_id.values()]
+    m.lattice_measure()
+    m.ITER_counter += 1
+    A = m.lattice_analysis()
+    V = m.lattice_full_site
+    # CPU baseline: the reference has no CPU implementation of this update; the C restatement (1 core) on a 12^4 sample
+    cpu = None
+    if not args.no_cpu:
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        import oracle_lib as O
+        L = O.OnLattice((12, 12, 12, 12), precision="f64" if m.precision == 1 else "f32")
+        L.init_cold()
+        rng = np.random.default_rng(1)
+        prns = rng.random((6 * L.prngstep, 4), dtype=np.float32)
+        t0 = time.perf_counter(); n = 0
+        while time.perf_counter() - t0 < 5.0:
+            L.update(prns, 1); L.update(prns, 0); n += 1
+        cpu = n * L.sites / (time.perf_counter() - t0)
+    out = {"metric": "O(4) site updates/sec (diagnostic, not the BASELINE metric)", "value": V * args.steps / (ms * 1e-3), "unit": "site-updates/s",
+           "n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "dtype": "f64" if m.precision == 1 else "f32",
+           "config": {"workload": f"O(4) scalar model {'x'.join(map(str, dims))}, NHIT=10 multi-hit Metropolis, XOR128 ({'in registers' if m.fused_prng else 'buffered'}), hot start",
+                      "acceptance_sums": m.get_acceptance_rate, "S_after_run": float(A["S"]["data"][1]), "phi_after_run": float(A["Phi"]["data"][1])},
+           "update_kernel_us": [t / 1e3 for t in tk], "proposals_per_s": V * 10 * args.steps / (ms * 1e-3), "gpu_launches": int(launches),
+           "cpu_baseline": {"value": cpu, "unit": "site-updates/s", "cores": 1, "kind": "port", "sample": "oracle/on_oracle.c, 12^4, 5 s"}}
+    print(json.dumps(out))
+    m.close()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -268,7 +325,11 @@ def main():
     ap.add_argument("--precision", type=int, default=None, help="diagnostic: 0 single, 1 double, 2 mixed")
     ap.add_argument("--phi", type=float, default=0.0, help="diagnostic: twist angle (turns -D TBC on)")
     ap.add_argument("--materialize", action="store_true", help="one generator per update thread, PRN buffer written (diagnostic)")
+    ap.add_argument("--on", action="store_true", help="diagnostic: the O(N) scalar branch (BASELINE config 4) instead of the gauge sweep")
+    ap.add_argument("--no-acc", action="store_true", help="diagnostic (--on): without the -D ACC_RATE acceptance sums")
     args = ap.parse_args()
+    if args.on:
+        return native_on(args)
     if args.impl == "reference":
         return reference_main(args)
     world = int(os.environ.get("WORLD_SIZE", "1"))
