@@ -49,6 +49,79 @@ struct F4 { float x, y, z, w; };
     QCD_SWB(11, 21) QCD_SWB(10, 20) QCD_SWB(9, 19) QCD_SWB(8, 18) QCD_SWB(7, 17) QCD_SWB(6, 16)             \
     QCD_SWB(5, 15) QCD_SWB(4, 14) QCD_SWB(3, 13) QCD_SWB(2, 12) QCD_SWB(1, 11) QCD_SWB(0, 10)
 
+// Packed ring (whole luxury periods of the two-phase kernel): the 24 seeds as one 576-bit number in 18 words, limb m
+// (m = 0 the oldest, x[n-24]) at bit 24 m.  x[n] = x[n-10] - x[n-24] - borrow for four consecutive n is then one
+// 96-bit subtraction: three subc.cc on words, the minuend being the same number 240 bits = 7.5 words further on (one
+// funnel shift per word), and no low byte to clear: 1.5 ALU operations per step instead of 2, with the borrow chain
+// 0.75 instructions per step long (measured 3.5 against 4.5 clocks per step with three warps per scheduler,
+// tools/microbench/swb_pack.cu).  24 steps bring the ring back to the same registers.
+#define QCD_PK_OPERANDS(w, c)                                                                                        \
+    "+r"(w[0]), "+r"(w[1]), "+r"(w[2]), "+r"(w[3]), "+r"(w[4]), "+r"(w[5]), "+r"(w[6]), "+r"(w[7]), "+r"(w[8]),      \
+    "+r"(w[9]), "+r"(w[10]), "+r"(w[11]), "+r"(w[12]), "+r"(w[13]), "+r"(w[14]), "+r"(w[15]), "+r"(w[16]), "+r"(w[17]), "+r"(c)
+#define QCD_PK_PRE  "{\n\t.reg .u32 t, a;\n\tsub.cc.u32 t, 0, %18;\n\t"
+#define QCD_PK_POST "subc.u32 t, 0, 0;\n\tand.b32 %18, t, 1;\n\t}"
+#define QCD_PK(D, LO, HI) "shf.r.wrap.b32 a, %" #LO ", %" #HI ", 16;\n\tsubc.cc.u32 %" #D ", a, %" #D ";\n\t"
+#define QCD_PK_CHUNK0 QCD_PK(0, 10, 11) QCD_PK(1, 11, 12) QCD_PK(2, 12, 13)
+#define QCD_PK_24 QCD_PK_CHUNK0 QCD_PK(3, 13, 14) QCD_PK(4, 14, 15) QCD_PK(5, 15, 16) QCD_PK(6, 16, 17) QCD_PK(7, 17, 0)   \
+    QCD_PK(8, 0, 1) QCD_PK(9, 1, 2) QCD_PK(10, 2, 3) QCD_PK(11, 3, 4) QCD_PK(12, 4, 5) QCD_PK(13, 5, 6) QCD_PK(14, 6, 7)   \
+    QCD_PK(15, 7, 8) QCD_PK(16, 8, 9) QCD_PK(17, 9, 10)
+// seven steps = one chunk of four + three limbs (72 bits: two words and the low byte of a third, %19 in / out)
+#define QCD_PK_TAIL7 QCD_PK_CHUNK0 QCD_PK(3, 13, 14) QCD_PK(4, 14, 15)                                                 \
+    "shf.r.wrap.b32 a, %15, %16, 16;\n\tand.b32 a, a, 0xFF;\n\tand.b32 %19, %5, 0xFF;\n\tsubc.cc.u32 %19, a, %19;\n\t"
+
+struct RanluxPacked {
+    uint32_t w[18];
+    // s[23 - m] = limb m << 8
+    __device__ __forceinline__ void pack(const uint32_t (&s)[24]) {
+#pragma unroll
+        for (int q = 0; q < 6; q++) {
+            const uint32_t y0 = s[23 - 4 * q], y1 = s[22 - 4 * q], y2 = s[21 - 4 * q], y3 = s[20 - 4 * q];
+            w[3 * q + 0] = __byte_perm(y0, y1, 0x5321);
+            w[3 * q + 1] = __byte_perm(y1, y2, 0x6532);
+            w[3 * q + 2] = __byte_perm(y2, y3, 0x7653);
+        }
+    }
+    // limb m << 8 (m compile-time after unrolling)
+    __device__ __forceinline__ uint32_t limb8(int m) const {
+        const int j = 3 * (m >> 2);
+        switch (m & 3) {
+            case 0: return w[j] << 8;
+            case 1: return __byte_perm(w[j], w[j + 1], 0x5430) & 0xFFFFFF00u;
+            case 2: return __byte_perm(w[j + 1], w[j + 2], 0x4320) & 0xFFFFFF00u;
+            default: return w[j + 2] & 0xFFFFFF00u;
+        }
+    }
+    __device__ __forceinline__ void unpack(uint32_t (&s)[24]) const {
+#pragma unroll
+        for (int m = 0; m < 24; m++) s[23 - m] = limb8(m);
+    }
+    __device__ __forceinline__ void rotation24(uint32_t& carry) {
+        asm volatile(QCD_PK_PRE QCD_PK_24 QCD_PK_POST : QCD_PK_OPERANDS(w, carry));
+    }
+    // seven steps, then the window is moved back onto the word grid (it starts at bit 168 = word 5, bit 8)
+    __device__ __forceinline__ void tail7(uint32_t& carry) {
+        uint32_t n5;
+        asm volatile("{\n\t.reg .u32 t, a;\n\tsub.cc.u32 t, 0, %18;\n\t" QCD_PK_TAIL7
+                     "subc.u32 t, 0, 0;\n\tand.b32 %18, t, 1;\n\tand.b32 %19, %19, 0xFF;\n\t}"
+                     : QCD_PK_OPERANDS(w, carry), "=r"(n5));
+        uint32_t t[18];
+#pragma unroll
+        for (int k = 0; k < 18; k++) {
+            const uint32_t lo = (5 + k < 18) ? w[5 + k] : w[5 + k - 18];
+            const uint32_t hi = (6 + k < 18) ? w[6 + k] : (6 + k - 18 < 5 ? w[6 + k - 18] : n5);
+            t[k] = __funnelshift_r(lo, hi, 8);
+        }
+#pragma unroll
+        for (int k = 0; k < 18; k++) w[k] = t[k];
+    }
+    // luxury skip of 223 = 9 x 24 + 7 steps
+    __device__ __forceinline__ void skip223(uint32_t& carry) {
+#pragma unroll 1
+        for (int b = 0; b < 9; b++) rotation24(carry);
+        tail7(carry);
+    }
+};
+
 struct Ranlux {
     uint32_t s[24];   // seed << 8
     uint32_t carry;   // 0 / 1
@@ -142,49 +215,61 @@ struct Ranlux {
     // later: it is converted here and flagged in `*converted` (bit k).  Whole 24-number blocks avoid the register rotation.
     template <int NSKIP> __device__ __forceinline__ void run_pass(uint4* out, uint32_t stride, uint32_t keep, uint32_t samples,
                                                                   unsigned long long* converted) {
+        static_assert(NSKIP == 223, "the packed period path is written for RANLUX3 (223 = 9 x 24 + 7)");
         uint32_t k = 0;
         unsigned long long conv = 0ull;
 #pragma unroll 1
         while (k < samples) {
-            if (left == 0) { luxury_skip<NSKIP>(); left = 24; }
-            if (left == 24 && k + 6 <= samples) {
-                uint32_t old[9];
+            if (left == 0) {
+                // period boundary: whole periods (skip + 24 numbers = 6 samples), and the skip of a started one, in packed form
+                RanluxPacked pk;
+                pk.pack(s);
+#pragma unroll 1
+                do {
+                    pk.skip223(carry);
+                    if (k + 6 > samples) { left = 24; break; }
+                    if (k < keep) {
+                        // the "uni < 2^-12" fix-up of number n reads x[n-9]: for n <= 8 a limb that leaves the window in this block
+                        uint32_t old[9];
 #pragma unroll
-                for (int i = 0; i < 9; i++) old[i] = s[i];
-                block24();
-                if (k < keep) {
+                        for (int i = 0; i < 9; i++) old[i] = pk.limb8(15 + i);
+                        pk.rotation24(carry);
 #pragma unroll
-                    for (int q = 0; q < 6; q++) {
-                        uint32_t w[4], nx[4];
+                        for (int q = 0; q < 6; q++) {
+                            uint32_t w[4], nx[4];
 #pragma unroll
-                        for (int e = 0; e < 4; e++) {
-                            const int n = 4 * q + e;
-                            w[e] = s[23 - n];
-                            nx[e] = (n <= 8) ? old[8 - n] : s[32 - n];
+                            for (int e = 0; e < 4; e++) {
+                                const int n = 4 * q + e;
+                                w[e] = pk.limb8(n);
+                                nx[e] = (n <= 8) ? old[n] : pk.limb8(n - 9);
+                            }
+                            if (min(min(w[0], w[1]), min(w[2], w[3])) < (4096u << 8)) {
+#pragma unroll
+                                for (int e = 0; e < 4; e++) w[e] = __float_as_uint(to_float(w[e], nx[e]));
+                                conv |= 1ull << (k + q);
+                            }
+                            if (k + q < keep) out[(k + q) * stride] = make_uint4(w[0], w[1], w[2], w[3]);
                         }
-                        if (min(min(w[0], w[1]), min(w[2], w[3])) < (4096u << 8)) {
-#pragma unroll
-                            for (int e = 0; e < 4; e++) w[e] = __float_as_uint(to_float(w[e], nx[e]));
-                            conv |= 1ull << (k + q);
-                        }
-                        if (k + q < keep) out[(k + q) * stride] = make_uint4(w[0], w[1], w[2], w[3]);
+                    } else {
+                        pk.rotation24(carry);
                     }
-                }
-                k += 6; left = 0;
-            } else {
-                asm volatile(QCD_SWB_PRE QCD_SWB_4 QCD_SWB_POST : QCD_SWB_OPERANDS(s, carry));
-                if (k < keep) {
-                    uint32_t w[4] = { s[23], s[22], s[21], s[20] };
-                    if (min(min(w[0], w[1]), min(w[2], w[3])) < (4096u << 8)) {
-#pragma unroll
-                        for (int e = 0; e < 4; e++) w[e] = __float_as_uint(to_float(w[e], s[8 - e]));
-                        conv |= 1ull << k;
-                    }
-                    out[k * stride] = make_uint4(w[0], w[1], w[2], w[3]);
-                }
-                rotate<4>();
-                left -= 4; k++;
+                    k += 6;
+                } while (k < samples);
+                pk.unpack(s);
+                continue;
             }
+            asm volatile(QCD_SWB_PRE QCD_SWB_4 QCD_SWB_POST : QCD_SWB_OPERANDS(s, carry));
+            if (k < keep) {
+                uint32_t w[4] = { s[23], s[22], s[21], s[20] };
+                if (min(min(w[0], w[1]), min(w[2], w[3])) < (4096u << 8)) {
+#pragma unroll
+                    for (int e = 0; e < 4; e++) w[e] = __float_as_uint(to_float(w[e], s[8 - e]));
+                    conv |= 1ull << k;
+                }
+                out[k * stride] = make_uint4(w[0], w[1], w[2], w[3]);
+            }
+            rotate<4>();
+            left -= 4; k++;
         }
         *converted = conv;
     }

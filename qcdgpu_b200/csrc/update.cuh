@@ -760,25 +760,43 @@ update_kernel(R* __restrict__ table, const R* __restrict__ params, const __grid_
     else          update_site_su2<R, MU, TBC, Prn>(table, g, beta, tw, gindex, site.p, prn);
     prn.finish();
 }
+#ifdef QCD_TRACE
+// diagnostic build (-DQCD_TRACE): clock64 of thread 0 at kernel entry, lock acquired, generator done, site done; and %smid
+static __device__ unsigned long long g_trace[5 * 65536];
+#define QCD_TRACE_MARK(i) if (threadIdx.x == 0 && blockIdx.x < 65536u) g_trace[5 * blockIdx.x + (i)] = clock64()
+#else
+#define QCD_TRACE_MARK(i)
+#endif
+
 template <int SUN, typename R, int MU, bool TBC, int NSKIP>
 __global__ void __launch_bounds__(kUpdateThreads, (((sizeof(R) == 8 && SUN == 3) ? 3 : 4) * 128) / kUpdateThreads)
 update_kernel_rlx(R* __restrict__ table, const R* __restrict__ params, const __grid_constant__ Geom g, int odd,
                   const uint32_t* rtable, uint32_t* rtable_out, uint32_t instances, uint32_t samples, uint32_t keep) {
     extern __shared__ uint4 prn_smem[];
+    QCD_TRACE_MARK(0);
     uint32_t GID = blockIdx.x * blockDim.x + threadIdx.x;
-    if (GID >= g.nthreads) return;
-    const SiteId site = thread_site(g, GID, odd != 0);
+    const bool active = GID < g.nthreads;
+    const SiteId site = thread_site(g, active ? GID : 0u, odd != 0);
     GID = site.GID;
     unsigned long long converted = 0ull;
     Ranlux r;
-    if (g.debug_skip != 1u) ranlux_load(r, rtable, instances, GID);     // 26 DRAM loads in flight while the site's addresses are formed
+    if (active && g.debug_skip != 1u) ranlux_load(r, rtable, instances, GID);     // 26 DRAM loads in flight while the site's addresses are formed
+    // (prefetching the state of the block that will take this block's place into the L2 was measured: the 26 extra instructions
+    //  per warp cost more than the shorter wait saves, 34.4 -> 35.0 ms per sweep)
     const uint32_t gindex = site.gindex;
     const Coord p = site.p;                                               // kept across the generator phase (5 registers)
-    prefetch_site_head<SUN, R, MU>(table, g, gindex, p);
+    if (active) prefetch_site_head<SUN, R, MU>(table, g, gindex, p);
     if (g.debug_skip != 1u) {   // phase 1: the pass's whole RANLUX work
-        r.template run_pass<NSKIP>(prn_smem + threadIdx.x, kUpdateThreads, keep, samples, &converted);
-        ranlux_store(r, rtable_out, instances, GID);
+        // (Serialising the generator phase per SM with a lock was measured: the resident blocks of an SM are already out of
+        //  step -- 1.17 blocks in this phase at a time, tools/trace_phases.py -- and the lock costs 4.04 -> 4.11 ms per pass.)
+        QCD_TRACE_MARK(1);
+        if (active) {
+            r.template run_pass<NSKIP>(prn_smem + threadIdx.x, kUpdateThreads, keep, samples, &converted);
+            ranlux_store(r, rtable_out, instances, GID);
+        }
+        QCD_TRACE_MARK(2);
     }
+    if (!active) return;
     if (g.debug_skip == 2u) return;
     // phase 2: the link update
     const R beta = params[0];
@@ -788,6 +806,10 @@ update_kernel_rlx(R* __restrict__ table, const R* __restrict__ params, const __g
     PrnSmem prn(prn_smem + threadIdx.x, kUpdateThreads, converted, (rtable_out != rtable) ? keep : 0xffffffffu, rtable + GID, instances);
     if (SUN == 3) update_site_su3<R, MU, TBC, PrnSmem>(table, g, beta, tw, gindex, p, prn);
     else          update_site_su2<R, MU, TBC, PrnSmem>(table, g, beta, tw, gindex, p, prn);
+    QCD_TRACE_MARK(3);
+#ifdef QCD_TRACE
+    if (threadIdx.x == 0 && blockIdx.x < 65536u) { uint32_t sm; asm volatile("mov.u32 %0, %%smid;" : "=r"(sm)); g_trace[5 * blockIdx.x + 4] = sm; }
+#endif
 }
 template <int SUN, typename R, int MU>
 __global__ void __launch_bounds__(kUpdateThreads)

@@ -45,6 +45,10 @@ static cudaError_t launch_rlx(const UpdateArgs& a, cudaStream_t st) {
     uint32_t keep = need;
     if (out != a.prn_table && (uint32_t)keep_env < need) keep = (uint32_t)keep_env;
     size_t smem = size_t(keep) * kUpdateThreads * sizeof(float4);
+    // diagnostic: unused shared memory per block, to measure the kernel at 2 or 1 resident blocks per SM
+    static int pad_env = -1;
+    if (pad_env < 0) { const char* e = getenv("QCDGPU_SMEM_PAD_KB"); pad_env = e ? atoi(e) : 0; }
+    smem += size_t(pad_env) * 1024;
     if (smem > 200 * 1024 || keep > 64) {   // does not fit (smem, or the 64-bit "already converted" mask): state-in-registers variant
         if (out != a.prn_table) return cudaErrorInvalidValue;
         PrnRanlux<223>::Args pa = { a.prn_table, a.prn_instances, a.prn_samples };
@@ -114,3 +118,10 @@ int REGS_NAME(int tbc, int prn_kind) {
 }
 
 }  // namespace qcd
+
+#if defined(QCD_TRACE) && INST_SUN == 3 && INST_PREC == 1 && INST_MU == 0
+// diagnostic build only: copy out the phase time stamps of the last SU(3) fp64 X-direction launch
+extern "C" int qgpu_debug_trace(unsigned long long* out, size_t n) {
+    return (int)cudaMemcpyFromSymbol(out, qcd::g_trace, n * sizeof(unsigned long long));
+}
+#endif
