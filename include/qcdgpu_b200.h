@@ -15,6 +15,10 @@
  * to hand-written CUDA kernels.  Sizes are size_t (the reference overflows `int` above 2 GiB,
  * clinterface.cpp:1296,1324).
  *
+ * The O(N) tree's programs ("-D ON_MODEL -D SUN=1 -D SKGROUP=.. [-D ACC_RATE]", O(N)/suncl/suncl.cpp:1454-1482) bind the kernel
+ * names of O(N)/oncl/oncl.cl and on_measurements_cl.cl (update_even, update_odd, lattice_init_hot, lattice_measurement_correlator,
+ * reduce_acceptance_rate, ...) through the same entry points; see INTEGRATION.md section 3a.
+ *
  * Plain C types only; no CUDA, torch or C++ types cross this boundary.
  * Thread-safety: one handle per host thread, like the reference (one GPU instance per device).
  */

@@ -65,6 +65,8 @@ def load(build_if_missing: bool = True):
     if _lib is not None:
         return _lib
     path = _build.LIB
+    if os.environ.get("QCDGPU_LIB"):       # experiments: a library built with other QCD_NVCC_EXTRA flags (e.g. under _variants/)
+        path, build_if_missing = os.environ["QCDGPU_LIB"], False
     if build_if_missing:
         try:
             path = _build.build()

@@ -769,7 +769,10 @@ static __device__ unsigned long long g_trace[5 * 65536];
 #endif
 
 template <int SUN, typename R, int MU, bool TBC, int NSKIP>
-__global__ void __launch_bounds__(kUpdateThreads, (((sizeof(R) == 8 && SUN == 3) ? 3 : 4) * 128) / kUpdateThreads)
+#ifndef QCD_RLX_MINBLOCKS     // experiment knob: resident blocks per SM the fp64 SU(3) two-phase kernel is compiled for
+#define QCD_RLX_MINBLOCKS ((3 * 128) / kUpdateThreads)
+#endif
+__global__ void __launch_bounds__(kUpdateThreads, (sizeof(R) == 8 && SUN == 3) ? QCD_RLX_MINBLOCKS : (4 * 128) / kUpdateThreads)
 update_kernel_rlx(R* __restrict__ table, const R* __restrict__ params, const __grid_constant__ Geom g, int odd,
                   const uint32_t* rtable, uint32_t* rtable_out, uint32_t instances, uint32_t samples, uint32_t keep) {
     extern __shared__ uint4 prn_smem[];
