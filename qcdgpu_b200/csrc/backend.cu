@@ -18,6 +18,7 @@
 #include <string>
 #include <vector>
 #include <utility>
+#include <cuda.h>
 
 using namespace qcd;
 
@@ -89,6 +90,8 @@ struct Buffer {
     // two are swapped when the pass is complete, so the state in front of a pass stays readable during it (update.cuh, PrnSmemT)
     void* twin = nullptr;
     int swap_seed_buf = 0;           // (on the PRN buffer) state table whose swap waits for the pass's last x-range launch
+    // link table: tensor map (4 reals, ROWSIZE sites, planes) for the TMA staging of the update kernel, made on first use
+    TensorMapBlob tmap, tmap1; uint32_t tmap_rowsize = 0; int tmap_prec = -1; bool tmap_failed = false;
     bool alive = false;
 };
 
@@ -304,6 +307,44 @@ int flush_pending(qgpu* h, int bid) {
     return 0;
 }
 
+// Tensor map over a link table for cp.async.bulk.tensor: dims (4 reals, ROWSIZE, planes), traversal strides (1, 2, 4), box 4 x 64 x 9,
+// i.e. the three vec4 planes of one link direction for 32 sites of one parity of a y-row per box.  Null when the driver entry point is missing or the table does not qualify.
+const TensorMapBlob* link_tensor_map(qgpu* h, int bid, const ProgramCfg& c, const Geom& g, const TensorMapBlob** one_site) {
+    *one_site = nullptr;
+    if (!valid_buf(h, bid)) return nullptr;
+    Buffer& b = h->buffers[bid];
+    const int prec = prec_index(c);
+    if (b.tmap_failed) return nullptr;
+    if (b.tmap_rowsize == g.rowsize && b.tmap_prec == prec) { *one_site = &b.tmap1; return &b.tmap; }
+    typedef CUresult (*Enc)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                            const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static Enc enc = nullptr; static bool looked = false;
+    if (!looked) {
+        looked = true;
+        void* fn = nullptr; cudaDriverEntryPointQueryResult qr;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qr) == cudaSuccess && qr == cudaDriverEntryPointSuccess) enc = (Enc)fn;
+        (void)cudaGetLastError();
+    }
+    const size_t rb = prec ? 8 : 4;
+    const uint64_t planes = (c.sun == 3) ? 12 : 4;
+    if (!enc || ((uintptr_t)b.dptr & 15u) || b.bytes < (size_t)g.rowsize * planes * 4 * rb) { b.tmap_failed = true; return nullptr; }
+    static_assert(sizeof(CUtensorMap) == sizeof(TensorMapBlob), "CUtensorMap is 128 bytes");
+    cuuint64_t gdim[3] = { 4, g.rowsize, planes }, gstr[2] = { 4 * rb, (cuuint64_t)g.rowsize * 4 * rb };
+    cuuint32_t box[3] = { 4, 64, 9 }, estr[3] = { 1, 2, 4 };      // 32 sites of one parity x planes DIR, DIR + 4, DIR + 8
+    CUresult r = enc(reinterpret_cast<CUtensorMap*>(&b.tmap), prec ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, b.dptr,
+                     gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { b.tmap_failed = true; return nullptr; }
+    cuuint32_t box1[3] = { 4, 2, 9 };                              // the same for a single site
+    r = enc(reinterpret_cast<CUtensorMap*>(&b.tmap1), prec ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, b.dptr,
+            gdim, gstr, box1, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { b.tmap_failed = true; return nullptr; }
+    b.tmap_rowsize = g.rowsize; b.tmap_prec = prec;
+    *one_site = &b.tmap1;
+    return &b.tmap;
+}
+
 int launch_kernel(qgpu* h, int kid) {
     Kernel& k = h->kernels[kid];
     const ProgramCfg& c = h->programs[k.program];
@@ -364,6 +405,7 @@ int launch_kernel(qgpu* h, int kid) {
                     a.prn_kind = pk.prn_kind; a.prn_table = (uint32_t*)buf_ptr(h, pk, 0);
                     a.prn_instances = (uint32_t)pk.global[0]; a.prn_samples = (uint32_t)samples;
                     if (pk.prn_kind == PRN_RANLUX3) {      // second state table (see Buffer::twin); without it the kernel works in place
+                        if (c.sun == 3) a.tmap = link_tensor_map(h, buf_id(k, 0), c, a.geom, &a.tmap1);
                         Buffer& sb = h->buffers[buf_id(pk, 0)];
                         if (!sb.twin && cudaMalloc(&sb.twin, sb.capacity) == cudaSuccess)
                             CUDA_OK(h, cudaMemcpyAsync(sb.twin, sb.dptr, sb.capacity, cudaMemcpyDeviceToDevice, st));

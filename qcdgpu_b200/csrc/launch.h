@@ -18,6 +18,9 @@ enum PrnKind : int {
     PRN_RANLUX0  = 6, PRN_RANLUX1 = 7, PRN_RANLUX2 = 8, PRN_RANLUX4 = 9,   // buffered-only luxury levels
 };
 
+// CUtensorMap (128 bytes, 64-byte aligned) without pulling cuda.h into this header
+struct alignas(64) TensorMapBlob { unsigned char bytes[128]; };
+
 struct UpdateArgs {
     void* table;            // R*
     const void* params;     // R*: [0]=beta/N [1]=phi [2]=omega   (suncl.cpp:3939-3953)
@@ -32,6 +35,8 @@ struct UpdateArgs {
     uint32_t prn_instances;
     uint32_t prn_samples;
     int overrelax;          // 1: overrelaxation pass instead of heat bath (no PRNs)
+    const TensorMapBlob* tmap;   // tensor maps over the link table (4 reals, ROWSIZE sites, planes), or null: TMA staging of the staple links;
+    const TensorMapBlob* tmap1;  // box = 32 sites of one parity x 3 planes, and 1 site x 3 planes
 };
 typedef cudaError_t (*UpdateLaunchFn)(const UpdateArgs&, cudaStream_t);
 // [sun-2][prec][mu]

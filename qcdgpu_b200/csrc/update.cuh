@@ -655,10 +655,177 @@ __device__ __forceinline__ void update_site_su3(R* table, const Geom& g, R beta,
     M3r2<R> m0 = load3<R, MU, TBC>(table, g, gindex, p.x, tw);     // after the staples: 24 registers less while they are formed
     heatbath_su3<R, MU, Prn>(table, g, beta, gindex, m0, S, prn);
 }
+// ---------------------------------------------------------------- SU(3) link staging by TMA (warp = one y-row of one parity)
+// With N2 a multiple of 64 the 32 lanes of a warp update 32 consecutive sites of one parity of one y-row, so every (link, plane)
+// they read is 32 vec4 at a stride of two elements: ONE tensor-map box per link (cp.async.bulk.tensor.3d, traversal strides (1, 2, 4),
+// box 4 x 64 x 9 -> 3 planes of 32 x sizeof(vec4) bytes) issued by lane 0, landing in a per-warp ring of kTmaK link slots (3 planes each) and
+// announced through one mbarrier per slot.  The links of the next staple so arrive while the current one is multiplied, without
+// registers and without the half-used 16-byte LDGSTS sectors that made the cp.async ring above lose; the physics phase otherwise
+// waits for the first use of a loaded link 19 times per update (43 % of its stall samples, profiles/r01_ncu_update_v6_packed.json).
+// The box starts at lane 0's site; a lane whose own site is not at (lane 0's site + 2 lane) -- the one y +- 1 neighbour per row that
+// wraps around -- loads its three planes itself.  tools/microbench/tma_rows.cu measures the access pattern in isolation.
+#ifndef QCD_TMA_PF     // experiment knob: lane 0 also prefetches the boxes of the next plane into the L2 (measured slower)
+#define QCD_TMA_PF 0
+#endif
+constexpr int kTmaK = 3;
+template <typename R> __host__ __device__ constexpr uint32_t tma_plane_bytes() { return 32u * uint32_t(sizeof(V4<R>)); }
+template <typename R> __host__ __device__ constexpr uint32_t tma_slot_bytes() { return 3u * tma_plane_bytes<R>(); }
+// per warp: kTmaK link slots, kTmaK 128-byte slots for the one wrapped-around site of a row, kTmaK mbarriers
+template <typename R> __host__ __device__ constexpr size_t tma_stage_bytes() { return size_t(kUpdateThreads / 32) * kTmaK * (tma_slot_bytes<R>() + 128 + 8); }
+
+template <typename R, int MU, bool TBC> struct Su3StageTma {
+    uint32_t buf, xbuf, bar;    // shared-memory addresses of this warp's slot 0, wrapped-site slot 0 and mbarrier 0
+    const void* tmap;           // CUtensorMap over the link table: (4 reals, ROWSIZE sites, 12 planes), box = 32 sites x 3 planes
+    const void* tmap1;          // same tensor, box = 1 site x 3 planes
+    const R* table;
+    uint32_t gindex, px, lane;
+    PlaneSites s0, s1, s2;
+
+    // link L of the site's read sequence (same order as Su3Stage): site and direction
+    template <int L> __device__ __forceinline__ uint32_t link_gid() const {
+        if constexpr (L >= 18) return gindex;
+        constexpr int pl = L / 6, i = L % 6;
+        const PlaneSites& s = (pl == 0) ? s0 : (pl == 1) ? s1 : s2;
+        return (i == 0) ? s.g_pnu : (i == 1) ? gindex : (i == 2) ? s.g_pmu : (i == 3) ? s.g_pmnmu : s.g_pmn;
+    }
+    template <int L> __host__ __device__ static constexpr int link_dir() {
+        if (L >= 18) return MU;
+        return (L % 6 == 0 || L % 6 == 4) ? MU : plane_nu<MU>(L / 6);
+    }
+    // can the site of link L be a y +- 1 neighbour (the only move that breaks "lane 0's site + 2 lane")?
+    template <int L> __host__ __device__ static constexpr bool may_wrap() {
+        if (L >= 18) return false;
+        const int i = L % 6, NU = plane_nu<MU>(L / 6);
+        return (i == 1) ? false : (i == 2) ? (MU == 1) : (i == 3) ? (MU == 1 || NU == 1) : (NU == 1);
+    }
+    template <int L> __device__ __forceinline__ void issue() const {
+        if constexpr (L <= 18) {
+            constexpr int SLOT = L % kTmaK, DIR = link_dir<L>();
+            uint32_t gidb = 0, wrapped = 0;
+            int start = int(link_gid<L>());     // box start = "site of lane 0" of the unwrapped row
+            if constexpr (may_wrap<L>()) {      // the first or the last lane of a row may wrap: lane 1 never does, it is the reference;
+                const int gid = start;          // the wrapped lane's site comes through a box of its own
+                start = __shfl_sync(0xffffffffu, gid, 1) - 2;
+                const uint32_t bad = __ballot_sync(0xffffffffu, gid != start + 2 * int(lane));
+                wrapped = bad;
+                gidb = uint32_t(__shfl_sync(0xffffffffu, gid, bad ? (__ffs(int(bad)) - 1) : 0));
+            }
+            if (lane == 0) {
+                const int gid0 = start;
+                const uint32_t b = bar + 8u * SLOT, d = buf + SLOT * tma_slot_bytes<R>();
+                const uint32_t bytes = tma_slot_bytes<R>() + (wrapped ? 3u * uint32_t(sizeof(V4<R>)) : 0u);
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(b), "r"(bytes) : "memory");
+                // one box per link: planes DIR, DIR + 4, DIR + 8 through the traversal stride of the plane dimension
+                asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                             :: "r"(d), "l"(tmap), "r"(0), "r"(gid0), "r"(DIR), "r"(b) : "memory");
+                if (wrapped)
+                    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                                 :: "r"(xbuf + 128u * SLOT), "l"(tmap1), "r"(0), "r"(int(gidb)), "r"(DIR), "r"(b) : "memory");
+            }
+            __syncwarp();
+        }
+    }
+    // lane 0: pull the three boxes of link L towards the L2 (one instruction per KB instead of one prefetch per thread and sector)
+    template <int L> __device__ __forceinline__ void prefetch_l2_link() const {
+        constexpr int DIR = link_dir<L>();
+        const uint32_t gid0 = link_gid<L>();
+        asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global [%0, {%1, %2, %3}];" :: "l"(tmap), "r"(0), "r"(int(gid0)), "r"(DIR) : "memory");
+    }
+    template <int L0, int L1> __device__ __forceinline__ void prefetch_l2_links() const {
+        if constexpr (L0 < L1) { prefetch_l2_link<L0>(); prefetch_l2_links<L0 + 1, L1>(); }
+    }
+    template <int L> __device__ __forceinline__ M3r2<R> take(const Geom& g, const Twist<R>& tw) const {
+        constexpr int SLOT = L % kTmaK, DIR = link_dir<L>();
+        const uint32_t gid = link_gid<L>();
+        const int start = may_wrap<L>() ? __shfl_sync(0xffffffffu, int(gid), 1) - 2 : 0;
+        {
+            const uint32_t b = bar + 8u * SLOT, phase = (L / kTmaK) & 1;
+            uint32_t done = 0;
+            while (!done)
+                asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                             : "=r"(done) : "r"(b), "r"(phase) : "memory");
+        }
+        V4<R> v[3];
+        // this lane's vec4 of plane k: in the link slot, or (the row's wrapped-around y neighbour) in the one-site slot
+        uint32_t a = buf + SLOT * tma_slot_bytes<R>() + lane * uint32_t(sizeof(V4<R>)), step = tma_plane_bytes<R>();
+        if constexpr (may_wrap<L>()) {
+            if (int(gid) != start + 2 * int(lane)) { a = xbuf + 128u * SLOT; step = uint32_t(sizeof(V4<R>)); }
+        }
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            if constexpr (sizeof(R) == 8) {
+                asm volatile("ld.shared.v2.f64 {%0,%1}, [%2];" : "=d"(v[k].x), "=d"(v[k].y) : "r"(a + k * step) : "memory");
+                asm volatile("ld.shared.v2.f64 {%0,%1}, [%2];" : "=d"(v[k].z), "=d"(v[k].w) : "r"(a + k * step + 16u) : "memory");
+            } else {
+                asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v[k].x), "=f"(v[k].y), "=f"(v[k].z), "=f"(v[k].w) : "r"(a + k * step) : "memory");
+            }
+        }
+        M3r2<R> m = unpack3(v[0], v[1], v[2]);
+        if constexpr (TBC && DIR == 1) {
+            constexpr int pl = (L < 18) ? L / 6 : 0, i = L % 6;
+            const PlaneSites& s = (pl == 0) ? s0 : (pl == 1) ? s1 : s2;
+            const uint32_t x = (L == 18 || i == 1) ? px : (i == 0) ? s.x_pnu : (i == 2) ? s.x_pmu : (i == 3) ? s.x_pmnmu : s.x_pmn;
+            twist3(m, g, x, tw);
+        }
+        // every lane has read the slot: it can be refilled.  The refill is a write through the async proxy; order it after these
+        // generic-proxy reads (without the fence a whole warp read a half-refilled slot about once in 10^6 updates)
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        issue<L + kTmaK>();
+        return m;
+    }
+    // called by all 32 lanes of a full warp; smem_warp = this warp's ring, bars = this warp's kTmaK mbarriers
+    __device__ __forceinline__ void begin(uint32_t smem_warp, uint32_t xslots, uint32_t bars, const void* tm, const void* tm1, const R* tab, const Geom& g, uint32_t gi, const Coord& p) {
+        buf = smem_warp; xbuf = xslots; bar = bars; tmap = tm; tmap1 = tm1; table = tab; gindex = gi; px = p.x; lane = threadIdx.x & 31u;
+        Coord pmu = nb_plus<MU>(g, p);
+        s0 = plane_sites<MU, PlaneOrder<MU>::n0>(g, p, pmu);
+        s1 = plane_sites<MU, PlaneOrder<MU>::n1>(g, p, pmu);
+        s2 = plane_sites<MU, PlaneOrder<MU>::n2>(g, p, pmu);
+        if (lane == 0) {
+#pragma unroll
+            for (int k = 0; k < kTmaK; k++) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(bar + 8u * k) : "memory");
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncwarp();
+        issue<0>(); issue<1>(); issue<2>();
+        static_assert(kTmaK == 3, "prologue written for three slots");
+        if (QCD_TMA_PF && lane == 0) prefetch_l2_links<3, 9>();      // the next six links towards the L2; the rest follows one plane ahead of the ring
+        __syncwarp();
+    }
+    template <int PL> __device__ __forceinline__ void plane(const Geom& g, const Twist<R>& tw, M3<R>& S) const {
+        if (QCD_TMA_PF && lane == 0) prefetch_l2_links<6 * PL + 9, (6 * PL + 15 < 19) ? 6 * PL + 15 : 19>();   // L2 prefetch runs six links ahead of the ring
+        __syncwarp();
+        {   // forward: A B^+ C^+ = A (C B)^+
+            M3r2<R> B = take<6 * PL + 0>(g, tw);
+            M3<R> Bf = complete(B), D, F;
+            M3r2<R> C = take<6 * PL + 1>(g, tw);
+            mul_r2_full(C, Bf, D);
+            M3r2<R> A = take<6 * PL + 2>(g, tw);
+            mul_r2_dag(A, D, F);
+            if (PL == 0) S = F; else acc3(S, F);
+        }
+        {   // backward: A2^+ B2^+ C2 = (B2 A2)^+ C2
+            M3r2<R> A2 = take<6 * PL + 3>(g, tw);
+            M3<R> Af = complete(A2), E, G;
+            M3r2<R> B2 = take<6 * PL + 4>(g, tw);
+            mul_r2_full(B2, Af, E);
+            M3r2<R> C2 = take<6 * PL + 5>(g, tw);
+            M3<R> Cf = complete(C2);
+            mul_dag_full(E, Cf, G);
+            acc3(S, G);
+        }
+    }
+    __device__ __forceinline__ void staple_and_link(const Geom& g, const Twist<R>& tw, M3<R>& S, M3r2<R>& m0) const {
+        plane<0>(g, tw, S);
+        plane<1>(g, tw, S);
+        plane<2>(g, tw, S);
+        m0 = take<18>(g, tw);
+    }
+};
 // same with the links arriving through the shared-memory ring (begin() was called earlier)
-template <typename R, int MU, bool TBC, class Prn>
+template <typename R, int MU, bool TBC, class Prn, class Stage>
 __device__ __forceinline__ void update_site_su3_staged(R* table, const Geom& g, R beta, const Twist<R>& tw,
-                                                       const Su3Stage<R, MU, TBC>& stage, Prn& prn) {
+                                                       const Stage& stage, Prn& prn) {
     M3<R> S;
     M3r2<R> m0;
     stage.staple_and_link(g, tw, S, m0);
@@ -752,10 +919,10 @@ update_kernel(R* __restrict__ table, const R* __restrict__ params, const __grid_
     const uint32_t gindex = site.gindex;
     Prn prn(pargs, g, GID, gindex);
     if constexpr (SUN == 3 && kStageK > 0) {
-        extern __shared__ uint4 dyn_smem[];
+        extern __shared__ __align__(128) uint4 dyn_smem[];
         Su3Stage<R, MU, TBC> stage;
         stage.begin(dyn_smem + threadIdx.x, table, g, gindex);
-        update_site_su3_staged<R, MU, TBC, Prn>(table, g, beta, tw, stage, prn);
+        update_site_su3_staged<R, MU, TBC, Prn, Su3Stage<R, MU, TBC>>(table, g, beta, tw, stage, prn);
     } else if constexpr (SUN == 3) update_site_su3<R, MU, TBC, Prn>(table, g, beta, tw, gindex, site.p, prn);
     else          update_site_su2<R, MU, TBC, Prn>(table, g, beta, tw, gindex, site.p, prn);
     prn.finish();
@@ -775,7 +942,7 @@ template <int SUN, typename R, int MU, bool TBC, int NSKIP>
 __global__ void __launch_bounds__(kUpdateThreads, (sizeof(R) == 8 && SUN == 3) ? QCD_RLX_MINBLOCKS : (4 * 128) / kUpdateThreads)
 update_kernel_rlx(R* __restrict__ table, const R* __restrict__ params, const __grid_constant__ Geom g, int odd,
                   const uint32_t* rtable, uint32_t* rtable_out, uint32_t instances, uint32_t samples, uint32_t keep) {
-    extern __shared__ uint4 prn_smem[];
+    extern __shared__ __align__(128) uint4 prn_smem[];
     QCD_TRACE_MARK(0);
     uint32_t GID = blockIdx.x * blockDim.x + threadIdx.x;
     const bool active = GID < g.nthreads;
@@ -813,6 +980,38 @@ update_kernel_rlx(R* __restrict__ table, const R* __restrict__ params, const __g
 #ifdef QCD_TRACE
     if (threadIdx.x == 0 && blockIdx.x < 65536u) { uint32_t sm; asm volatile("mov.u32 %0, %%smid;" : "=r"(sm)); g_trace[5 * blockIdx.x + 4] = sm; }
 #endif
+}
+// update_kernel_rlx with the links of the staples staged by TMA (SU(3), full warps, N2 a multiple of 64; chosen by the launcher)
+template <typename R, int MU, bool TBC, int NSKIP>
+__global__ void __launch_bounds__(kUpdateThreads, (sizeof(R) == 8) ? QCD_RLX_MINBLOCKS : (4 * 128) / kUpdateThreads)
+update_kernel_rlx_tma(R* __restrict__ table, const R* __restrict__ params, const __grid_constant__ Geom g, int odd,
+                      const uint32_t* rtable, uint32_t* rtable_out, uint32_t instances, uint32_t samples, uint32_t keep,
+                      const __grid_constant__ TensorMapBlob tmap, const __grid_constant__ TensorMapBlob tmap1) {
+    extern __shared__ __align__(128) uint4 prn_smem[];
+    const SiteId site = thread_site(g, blockIdx.x * blockDim.x + threadIdx.x, odd != 0);      // the launcher guarantees full blocks
+    const uint32_t GID = site.GID;
+    unsigned long long converted = 0ull;
+    Ranlux r;
+    if (g.debug_skip != 1u) ranlux_load(r, rtable, instances, GID);
+    const uint32_t gindex = site.gindex;
+    const Coord p = site.p;
+    // ring of this warp behind the parked samples, mbarriers behind the rings
+    const uint32_t base = (uint32_t)__cvta_generic_to_shared(prn_smem) + keep * uint32_t(kUpdateThreads * sizeof(uint4));
+    const uint32_t warp = threadIdx.x >> 5;
+    Su3StageTma<R, MU, TBC> stage;
+    constexpr uint32_t NW = kUpdateThreads / 32, RING = kTmaK * tma_slot_bytes<R>();
+    stage.begin(base + warp * RING, base + NW * RING + warp * (kTmaK * 128u), base + NW * (RING + kTmaK * 128u) + warp * (kTmaK * 8u),
+                &tmap, &tmap1, table, g, gindex, p);
+    if (g.debug_skip != 1u) {   // phase 1: the pass's whole RANLUX work (the first three links land meanwhile)
+        r.template run_pass<NSKIP>(prn_smem + threadIdx.x, kUpdateThreads, keep, samples, &converted);
+        ranlux_store(r, rtable_out, instances, GID);
+    }
+    if (g.debug_skip == 2u) return;
+    const R beta = params[0];
+    const Twist<R> tw = make_twist<3, R, TBC>(params);
+    typedef PrnSmemT<NSKIP> PrnSmem;
+    PrnSmem prn(prn_smem + threadIdx.x, kUpdateThreads, converted, (rtable_out != rtable) ? keep : 0xffffffffu, rtable + GID, instances);
+    update_site_su3_staged<R, MU, TBC, PrnSmem, Su3StageTma<R, MU, TBC>>(table, g, beta, tw, stage, prn);
 }
 template <int SUN, typename R, int MU>
 __global__ void __launch_bounds__(kUpdateThreads)

@@ -54,6 +54,24 @@ static cudaError_t launch_rlx(const UpdateArgs& a, cudaStream_t st) {
         PrnRanlux<223>::Args pa = { a.prn_table, a.prn_instances, a.prn_samples };
         return launch_one<TBC, PrnRanlux<223>>(a, pa, st);
     }
+#if INST_SUN == 3
+    // links of the staples staged by TMA: full warps that are one y-row of one parity each (update.cuh, Su3StageTma)
+    static int tma_env = -1;
+    if (tma_env < 0) { const char* e = getenv("QCDGPU_TMA"); tma_env = e ? atoi(e) : 1; }
+    if (tma_env && a.tmap && a.tmap1 && kUpdateThreads == 128 && a.geom.n2 % 64u == 0u && a.geom.nthreads % kUpdateThreads == 0u) {
+        auto kt = update_kernel_rlx_tma<RealT, INST_MU, TBC, 223>;
+        const size_t smem_t = smem + tma_stage_bytes<RealT>();
+        static size_t configured_t = 0;
+        if (smem_t > configured_t) {
+            cudaError_t e = cudaFuncSetAttribute(kt, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_t);
+            if (e != cudaSuccess) return e;
+            configured_t = smem_t;
+        }
+        kt<<<a.geom.nthreads / kUpdateThreads, kUpdateThreads, smem_t, st>>>(static_cast<RealT*>(a.table), static_cast<const RealT*>(a.params), a.geom, a.odd,
+                                                                           a.prn_table, out, a.prn_instances, a.prn_samples, keep, *a.tmap, *a.tmap1);
+        return cudaGetLastError();
+    }
+#endif
     auto kern = update_kernel_rlx<INST_SUN, RealT, INST_MU, TBC, 223>;
     static size_t configured = 0;
     if (smem > configured) {

@@ -313,6 +313,22 @@ def test_fused_prng_equals_buffered(gen, sun, prec):
     np.testing.assert_array_equal(tables[0].view(np.uint8), tables[1].view(np.uint8))
 
 
+@pytest.mark.parametrize("dims,prec,phi", [((2, 64, 2, 4), 1, 0.0), ((4, 64, 4, 2), 1, 3.0), ((2, 128, 2, 2), 1, 0.0), ((2, 64, 4, 4), 0, 0.0)])
+def test_tma_staged_links_equal_plain_loads(dims, prec, phi):
+    """N2 a multiple of 64: a warp of the two-phase RANLUX kernel is one y-row of one parity and the links of the staples arrive
+    through TMA boxes in shared memory (update.cuh, Su3StageTma), the row's wrapped-around y neighbour through a one-site box.
+    Same arithmetic on the same values: the lattice must equal the buffered kernel's (plain loads) bit for bit, twist included."""
+    tables = []
+    for fused in (False, True):
+        m = make_model(3, dims, prec, ints=0, prng="RANLUX3", fused=True, iters=3, beta=5.7, phi=phi)
+        if not fused:
+            m.GPU0.set_fused_prng(False)
+        m.lattice_simulate()
+        tables.append(m.table_numpy())
+        m.close()
+    np.testing.assert_array_equal(tables[0].view(np.uint8), tables[1].view(np.uint8))
+
+
 _KEEP_SCRIPT = r"""
 import sys, numpy as np
 sys.path.insert(0, sys.argv[1])
