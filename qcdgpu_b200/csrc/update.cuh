@@ -667,7 +667,13 @@ __device__ __forceinline__ void update_site_su3(R* table, const Geom& g, R beta,
 #ifndef QCD_TMA_PF     // experiment knob: lane 0 also prefetches the boxes of the next plane into the L2 (measured slower)
 #define QCD_TMA_PF 0
 #endif
-constexpr int kTmaK = 3;
+#ifndef QCD_TMA_SYNC_AFTER_ISSUE     // experiment knob: warp barrier behind lane 0's TMA issue (not needed for correctness)
+#define QCD_TMA_SYNC_AFTER_ISSUE 0
+#endif
+#ifndef QCD_TMA_K     // links in flight per warp (ring slots of 3 planes each)
+#define QCD_TMA_K 3
+#endif
+constexpr int kTmaK = QCD_TMA_K;
 template <typename R> __host__ __device__ constexpr uint32_t tma_plane_bytes() { return 32u * uint32_t(sizeof(V4<R>)); }
 template <typename R> __host__ __device__ constexpr uint32_t tma_slot_bytes() { return 3u * tma_plane_bytes<R>(); }
 // per warp: kTmaK link slots, kTmaK 128-byte slots for the one wrapped-around site of a row, kTmaK mbarriers
@@ -722,7 +728,9 @@ template <typename R, int MU, bool TBC> struct Su3StageTma {
                     asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
                                  :: "r"(xbuf + 128u * SLOT), "l"(tmap1), "r"(0), "r"(int(gidb)), "r"(DIR), "r"(b) : "memory");
             }
+#if QCD_TMA_SYNC_AFTER_ISSUE
             __syncwarp();
+#endif
         }
     }
     // lane 0: pull the three boxes of link L towards the L2 (one instruction per KB instead of one prefetch per thread and sector)
@@ -787,13 +795,15 @@ template <typename R, int MU, bool TBC> struct Su3StageTma {
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
         __syncwarp();
-        issue<0>(); issue<1>(); issue<2>();
-        static_assert(kTmaK == 3, "prologue written for three slots");
-        if (QCD_TMA_PF && lane == 0) prefetch_l2_links<3, 9>();      // the next six links towards the L2; the rest follows one plane ahead of the ring
+        prologue<0>();
+        if (QCD_TMA_PF && lane == 0) prefetch_l2_links<kTmaK, kTmaK + 6>();      // the next six links towards the L2; the rest follows one plane ahead of the ring
         __syncwarp();
     }
+    template <int L> __device__ __forceinline__ void prologue() const {
+        if constexpr (L < kTmaK) { issue<L>(); prologue<L + 1>(); }
+    }
     template <int PL> __device__ __forceinline__ void plane(const Geom& g, const Twist<R>& tw, M3<R>& S) const {
-        if (QCD_TMA_PF && lane == 0) prefetch_l2_links<6 * PL + 9, (6 * PL + 15 < 19) ? 6 * PL + 15 : 19>();   // L2 prefetch runs six links ahead of the ring
+        if (QCD_TMA_PF && lane == 0) prefetch_l2_links<(6 * PL + 6 + kTmaK < 19) ? 6 * PL + 6 + kTmaK : 19, (6 * PL + 12 + kTmaK < 19) ? 6 * PL + 12 + kTmaK : 19>();   // L2 prefetch runs six links ahead of the ring
         __syncwarp();
         {   // forward: A B^+ C^+ = A (C B)^+
             M3r2<R> B = take<6 * PL + 0>(g, tw);
