@@ -387,7 +387,12 @@ int launch_kernel(qgpu* h, int kid) {
             const uint32_t full_threads = (c.biglat ? c.n1 - 2 : c.n1) * (a.geom.n234 / 2);
             UpdateLaunchFn fn = get_update_launcher(c.sun, prec, k.dir);
             if (!fn) return fail(h, "kernel %s: no CUDA instantiation for SUN=%d PRECISION=%d", k.name.c_str(), c.sun, c.precision);
-            if (k.kind == K_OVERRELAX) { a.overrelax = 1; CUDA_OK(h, fn(a, st)); break; }
+            if (k.kind == K_OVERRELAX) {
+                a.overrelax = 1;
+                if (c.sun == 3) a.tmap = link_tensor_map(h, buf_id(k, 0), c, a.geom, &a.tmap1);
+                CUDA_OK(h, fn(a, st));
+                break;
+            }
             if (c.gid_upd) { a.prn_kind = PRN_GID; CUDA_OK(h, fn(a, st)); break; }
             int pb = buf_id(k, 2);
             if (!valid_buf(h, pb)) return fail(h, "kernel %s: argument 2 (prns) not set", k.name.c_str());

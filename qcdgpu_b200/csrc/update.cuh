@@ -1042,4 +1042,32 @@ overrelax_kernel(R* __restrict__ table, const __grid_constant__ Geom g, int odd)
     else          overrelax_site_su2<R, MU>(table, g, gindex);
 }
 
+// overrelaxation pass with the links staged by TMA (SU(3), full warps, N2 a multiple of 64; chosen by the launcher)
+#ifndef QCD_OR_TMA_MINBLOCKS
+#define QCD_OR_TMA_MINBLOCKS 3
+#endif
+template <typename R, int MU>
+__global__ void __launch_bounds__(kUpdateThreads, (sizeof(R) == 8) ? (QCD_OR_TMA_MINBLOCKS * 128) / kUpdateThreads : (4 * 128) / kUpdateThreads)
+overrelax_kernel_tma(R* __restrict__ table, const __grid_constant__ Geom g, int odd,
+                     const __grid_constant__ TensorMapBlob tmap, const __grid_constant__ TensorMapBlob tmap1) {
+    extern __shared__ __align__(128) uint4 prn_smem[];
+    const SiteId site = thread_site(g, blockIdx.x * blockDim.x + threadIdx.x, odd != 0);      // the launcher guarantees full blocks
+    const uint32_t base = (uint32_t)__cvta_generic_to_shared(prn_smem), warp = threadIdx.x >> 5;
+    constexpr uint32_t NW = kUpdateThreads / 32, RING = kTmaK * tma_slot_bytes<R>();
+    Su3StageTma<R, MU, false> stage;
+    stage.begin(base + warp * RING, base + NW * RING + warp * (kTmaK * 128u), base + NW * (RING + kTmaK * 128u) + warp * (kTmaK * 8u),
+                &tmap, &tmap1, table, g, site.gindex, site.p);
+    const Twist<R> tw = { R(1), R(0), R(1), R(0) };
+    M3<R> S;
+    M3r2<R> m0;
+    stage.staple_and_link(g, tw, S, m0);
+    M3<R> U = complete(m0);
+    M3<R> W = mul_full(U, S);
+    or_subgroup<R, 0, 1>(U, W);
+    or_subgroup<R, 0, 2>(U, W);
+    or_subgroup<R, 1, 2>(U, W);
+    gram_schmidt3(U.e[0], U.e[1]);
+    store3<R, MU>(table, g, site.gindex, U.e[0], U.e[1]);
+}
+
 }  // namespace qcd

@@ -105,6 +105,22 @@ static cudaError_t launch_tbc(const UpdateArgs& a, cudaStream_t st) {
 
 cudaError_t LAUNCH_NAME(const UpdateArgs& a, cudaStream_t st) {
     if (a.overrelax) {
+#if INST_SUN == 3
+        static int or_tma_env = -1;
+        if (or_tma_env < 0) { const char* e = getenv("QCDGPU_TMA"); or_tma_env = e ? atoi(e) : 1; }
+        if (or_tma_env && a.tmap && a.tmap1 && kUpdateThreads == 128 && a.geom.n2 % 64u == 0u && a.geom.nthreads > 0 && a.geom.nthreads % kUpdateThreads == 0u) {
+            auto kt = overrelax_kernel_tma<RealT, INST_MU>;
+            const size_t smem_t = tma_stage_bytes<RealT>();
+            static bool configured_or = false;
+            if (!configured_or) {
+                cudaError_t e = cudaFuncSetAttribute(kt, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_t);
+                if (e != cudaSuccess) return e;
+                configured_or = true;
+            }
+            kt<<<a.geom.nthreads / kUpdateThreads, kUpdateThreads, smem_t, st>>>(static_cast<RealT*>(a.table), a.geom, a.odd, *a.tmap, *a.tmap1);
+            return cudaGetLastError();
+        }
+#endif
         dim3 block(kUpdateThreads), grid((a.geom.nthreads + kUpdateThreads - 1) / kUpdateThreads);
         if (grid.x == 0) return cudaSuccess;
         overrelax_kernel<INST_SUN, RealT, INST_MU><<<grid, block, 0, st>>>(static_cast<RealT*>(a.table), a.geom, a.odd);

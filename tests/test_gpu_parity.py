@@ -362,11 +362,11 @@ def test_two_phase_kernel_overflow_path_is_bit_exact(keep, sun, prec, beta):
 
 
 # ---------------------------------------------------------------------------------- overrelaxation
-@pytest.mark.parametrize("sun", [3, 2])
-def test_overrelaxation(sun):
+@pytest.mark.parametrize("sun,dims", [(3, (4, 4, 4, 4)), (2, (4, 4, 4, 4)), (3, (2, 64, 2, 4)), (3, (4, 128, 2, 2))])
+def test_overrelaxation(sun, dims):
     """New capability (not in the reference): checked against the oracle's definition and its invariant --
-    the total action is unchanged by an overrelaxation pass."""
-    m = make_model(sun, (4, 4, 4, 4), 1, ints=0, instances=64, or_steps=1, beta=6.0 if sun == 3 else 2.5)
+    the total action is unchanged by an overrelaxation pass.  N2 = 64, 128: the kernel with the links staged by TMA."""
+    m = make_model(sun, dims, 1, ints=0, instances=64, or_steps=1, beta=6.0 if sun == 3 else 2.5)
     m.lattice_start()
     L = make_oracle(m)
     L.table[:] = m.table_numpy()
