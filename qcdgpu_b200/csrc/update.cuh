@@ -16,6 +16,7 @@
 //   * the PRN source is a template parameter: the reference-layout buffer, the closed-form
 //     INTS=2 pseudo-randoms, or a generator whose state lives in registers (fused mode).
 #pragma once
+#include <math_constants.h>
 #include "lattice.cuh"
 #include "prng.cuh"
 
@@ -183,13 +184,14 @@ template <> struct Mth<double> {
 #else
     // log of a positive normal number (the Kennedy-Pendleton arguments are 1 - r, r a float in (0, 1): 2^-24 <= x < 1), error below
     // 1 ulp: the classic argument reduction x = 2^k (1 + f), sqrt(2)/2 < 1 + f < sqrt(2), s = f / (2 + f), log(1 + f) = f - f^2/2 +
-    // s (f^2/2 + R(s^2)) with the degree-7 minimax polynomial R of Sun's fdlibm (e_log.c); special cases go to the library.  libdevice's
+    // s (f^2/2 + R(s^2)) with the degree-7 minimax polynomial R of Sun's fdlibm (e_log.c).  libdevice's
     // log costs about three times the instructions; with it the 64^4 pass takes 3.85 instead of 3.67 ms.
     static __device__ __forceinline__ double log_(double x) {
         int hx = __double2hiint(x);
         const int lx = __double2loint(x);
-        // zero (XOR128 / PM / the INTS=2 closed forms can deliver r = 1), subnormal, negative, inf, nan: the library's answer
-        if (hx < 0x00100000 || hx >= 0x7ff00000) return log(x);
+        // zero (XOR128 / PM / the INTS=2 closed forms can deliver r = 1): -inf as the library; an argument 1 - r is never negative or
+        // subnormal (those, inf and nan give nan); no call into the library here -- its inlined body would cost what this function saves
+        if (hx < 0x00100000 || hx >= 0x7ff00000) return (x == 0.0) ? -CUDART_INF : CUDART_NAN;
         int k = (hx >> 20) - 1023;
         hx &= 0x000fffff;
         const int i = (hx + 0x95f64) & 0x100000;
@@ -212,8 +214,52 @@ template <> struct Mth<double> {
         return dk * 6.93147180369123816490e-01 - ((hfsq - (s * (hfsq + R) + dk * 1.90821492927058770002e-10)) - f);
     }
 #endif
+#ifdef QCD_LIBDEVICE_TRIG
     static __device__ __forceinline__ double cos2pi(double x) { return cospi(2.0 * x); }
     static __device__ __forceinline__ void sincos2pi(double x, double* s, double* c) { sincospi(2.0 * x, s, c); }
+#else
+    // sin and cos of 2 pi x for 0 <= x <= 1 (a float PRN): 4 x = q + r with q the nearest integer, |r| <= 1/2, so the angle is
+    // q pi/2 + z with |z| = |r| pi/2 <= pi/4: Taylor series of sin z (to z^17) and cos z (to z^18) in Horner form, truncation below
+    // 5e-17, then the quadrant swap.  No argument checks and none of sincospi's generality: cospi + sincospi cost the pass up to
+    // 0.18 ms (measured with float stand-ins), this about half of it.
+    static __device__ __forceinline__ void sincos_quadrant(double x, double& sn, double& cs, int& q) {
+        const double t = 4.0 * x;
+        const double qd = rint(t);
+        q = int(qd);
+        const double z = (t - qd) * 1.5707963267948966192;
+        const double z2 = z * z;
+        double ps = fma(z2, 2.8114572543455207632e-15, -7.6471637318198164759e-13);     // 1/17!, -1/15!
+        ps = fma(ps, z2, 1.6059043836821614599e-10);                                     //  1/13!
+        ps = fma(ps, z2, -2.5052108385441718775e-08);                                    // -1/11!
+        ps = fma(ps, z2, 2.7557319223985890653e-06);                                     //  1/9!
+        ps = fma(ps, z2, -1.9841269841269841270e-04);                                    // -1/7!
+        ps = fma(ps, z2, 8.3333333333333333333e-03);                                     //  1/5!
+        ps = fma(ps, z2, -1.6666666666666666667e-01);                                    // -1/3!
+        sn = fma(ps * z2, z, z);
+        double pc = fma(z2, -1.5619206968586226462e-16, 4.7794773323873852974e-14);      // -1/18!, 1/16!
+        pc = fma(pc, z2, -1.1470745597729724714e-11);                                    // -1/14!
+        pc = fma(pc, z2, 2.0876756987868098979e-09);                                     //  1/12!
+        pc = fma(pc, z2, -2.7557319223985890653e-07);                                    // -1/10!
+        pc = fma(pc, z2, 2.4801587301587301587e-05);                                     //  1/8!
+        pc = fma(pc, z2, -1.3888888888888888889e-03);                                    // -1/6!
+        pc = fma(pc, z2, 4.1666666666666666667e-02);                                     //  1/4!
+        pc = fma(pc, z2, -0.5);
+        cs = fma(pc, z2, 1.0);
+    }
+    static __device__ __forceinline__ double cos2pi(double x) {
+        double sn, cs; int q;
+        sincos_quadrant(x, sn, cs, q);
+        const double v = (q & 1) ? sn : cs;                 // q = 0..4: cos, -sin, -cos, sin, cos
+        return ((q + 1) & 2) ? -v : v;
+    }
+    static __device__ __forceinline__ void sincos2pi(double x, double* s, double* c) {
+        double sn, cs; int q;
+        sincos_quadrant(x, sn, cs, q);
+        const double sv = (q & 1) ? cs : sn, cv = (q & 1) ? sn : cs;   // sin: sin, cos, -sin, -cos; cos: cos, -sin, -cos, sin
+        *s = (q & 2) ? -sv : sv;
+        *c = ((q + 1) & 2) ? -cv : cv;
+    }
+#endif
 };
 template <> struct Mth<float> {
     static __device__ __forceinline__ float sqrt_(float x) { return sqrtf(x); }

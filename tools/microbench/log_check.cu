@@ -15,6 +15,13 @@ template <int WHICH> __global__ void k(const float* r, double* out, int n, int r
     for (int j = 0; j < reps; j++) { acc += WHICH ? log(x) : Mth<double>::log_(x); x = fma(x, 0.999999, 1e-9); }
     out[i] = acc;
 }
+__global__ void ktrig(const float* r, double* out, int n) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double s, c;
+    Mth<double>::sincos2pi(double(r[i]), &s, &c);
+    out[3 * i] = s; out[3 * i + 1] = c; out[3 * i + 2] = Mth<double>::cos2pi(double(r[i]));
+}
 int main() {
     const int n = 1 << 22;
     std::vector<float> h(n);
@@ -38,6 +45,19 @@ int main() {
         if (fabs(a[i] - b[i]) > maxabs) maxabs = fabs(a[i] - b[i]);
     }
     printf("max error of log_ vs long-double log: %.3f ulp (r = %.9g), max |log_ - libdevice log| = %.3e\n", maxulp, h[worst], maxabs);
+    {   // sin / cos of 2 pi x against long double
+        double* dt; cudaMalloc(&dt, size_t(n) * 24);
+        ktrig<<<n / 256, 256>>>(dr, dt, n);
+        std::vector<double> t(size_t(n) * 3);
+        cudaMemcpy(t.data(), dt, size_t(n) * 24, cudaMemcpyDeviceToHost);
+        double worst = 0;
+        for (int i = 0; i < n; i++) {
+            long double a = 2.0L * 3.14159265358979323846264338327950288L * (long double)h[i];
+            double es = fabs(t[3 * i] - (double)sinl(a)), ec = fabs(t[3 * i + 1] - (double)cosl(a)), e2 = fabs(t[3 * i + 2] - (double)cosl(a));
+            worst = fmax(worst, fmax(es, fmax(ec, e2)));
+        }
+        printf("max absolute error of sincos2pi / cos2pi vs long double: %.3e\n", worst);
+    }
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
     for (int w = 0; w < 2; w++) {
         cudaEventRecord(e0);
