@@ -179,6 +179,7 @@ using PrnMrg = PrnSmallState<Mrg32k3a, 8>;
 template <typename R> struct Mth;
 template <> struct Mth<double> {
     static __device__ __forceinline__ double sqrt_(double x) { return sqrt(x); }
+    static __device__ __forceinline__ double rcp_(double x) { return fast_rcp(x); }      // positive normal arguments only
 #ifdef QCD_LIBDEVICE_LOG
     static __device__ __forceinline__ double log_(double x) { return log(x); }
 #else
@@ -263,6 +264,7 @@ template <> struct Mth<double> {
 };
 template <> struct Mth<float> {
     static __device__ __forceinline__ float sqrt_(float x) { return sqrtf(x); }
+    static __device__ __forceinline__ float rcp_(float x) { return 1.0f / x; }
     static __device__ __forceinline__ float log_(float x) { return logf(x); }
     static __device__ __forceinline__ float cos2pi(float x) { return cospif(2.0f * x); }
     static __device__ __forceinline__ void sincos2pi(float x, float* s, float* c) { sincospif(2.0f * x, s, c); }
@@ -291,7 +293,7 @@ template <typename R> __device__ __forceinline__ V4<R> kp_compose(R delta, const
 }
 template <typename R, class Prn>
 __device__ __forceinline__ bool kp_heatbath(Prn& prn, const Geom& g, const V4<R>& aH, R bdet, V4<R>& out) {
-    R ibdet = R(1) / bdet;
+    R ibdet = Mth<R>::rcp_(bdet);
     if constexpr (Prn::kGid) {
         double r[4];
         prn.trial_d(r);
@@ -655,7 +657,7 @@ __device__ __forceinline__ V4<R> block_dagger(const M3<R>& W, R& det) {
     aH.y = -(W.e[A][B].re - W.e[B][A].re);
     aH.w = -(W.e[A][B].im + W.e[B][A].im);
     det = Mth<R>::sqrt_(aH.x * aH.x + aH.y * aH.y + aH.z * aH.z + aH.w * aH.w);
-    R id = R(1) / det;
+    R id = Mth<R>::rcp_(det);
     aH.x *= id; aH.y *= id; aH.z *= id; aH.w *= id;
     return aH;
 }
