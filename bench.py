@@ -29,7 +29,7 @@ sys.path.insert(0, ROOT)
 
 WORKLOAD = dict(group=3, dims=(64, 64, 64, 64), precision=1, beta=6.0, nhit=10, prng="RANLUX3", randseries=54, ints=1)
 BYTES_PER_LINK_UPDATE = 9 * 96      # SU(3) 2-row fp64: 4 V link reads + V/2 link writes per pass, 8 passes / 4 V links
-NCU_DRAM_BYTES_PER_LAUNCH = 8.147838e9 + 1.876264e9   # profiles/r01_ncu_update_v8.json
+NCU_DRAM_BYTES_PER_LAUNCH = 8.148279e9 + 2.030778e9   # profiles/r01_ncu_update_v9.json
 FLOPS_PER_LINK_UPDATE = 4700
 
 
@@ -222,7 +222,7 @@ def native_single(args):
     # DRAM bytes of one launch of that kernel from the committed ncu --set full capture (same command, 64^4 fused only)
     traffic, traffic_src = None, None
     if tuple(dims) == (64, 64, 64, 64) and not args.buffered and not args.materialize and not diag:
-        traffic, traffic_src = NCU_DRAM_BYTES_PER_LAUNCH, "profiles/r01_ncu_update_v8.json (dram__bytes_read.sum + dram__bytes_write.sum)"
+        traffic, traffic_src = NCU_DRAM_BYTES_PER_LAUNCH, "profiles/r01_ncu_update_v9.json (dram__bytes_read.sum + dram__bytes_write.sum)"
     regs = g.update_kernel_registers(m.program_update, 0, 2 if not args.buffered else 0)
     kname = ("update_kernel_rlx<%d,%s,MU,%s,223>" if not args.buffered else "update_kernel<%d,%s,MU,%s,PrnBuffered>") % (
         m.lattice_group, "double" if m.precision == 1 else "float", "true" if args.phi != 0.0 else "false")
