@@ -29,7 +29,7 @@ sys.path.insert(0, ROOT)
 
 WORKLOAD = dict(group=3, dims=(64, 64, 64, 64), precision=1, beta=6.0, nhit=10, prng="RANLUX3", randseries=54, ints=1)
 BYTES_PER_LINK_UPDATE = 9 * 96      # SU(3) 2-row fp64: 4 V link reads + V/2 link writes per pass, 8 passes / 4 V links
-NCU_DRAM_BYTES_PER_LAUNCH = 8.148279e9 + 2.030778e9   # profiles/r01_ncu_update_v9.json
+NCU_DRAM_BYTES_PER_LAUNCH = 8.151837e9 + 2.028637e9   # profiles/r01_ncu_update_v9.json
 FLOPS_PER_LINK_UPDATE = 4700
 
 
