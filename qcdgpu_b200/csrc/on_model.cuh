@@ -35,14 +35,17 @@ template <typename R> __device__ __forceinline__ OnPar<R> on_par(const R* __rest
     return q;
 }
 template <typename R> __device__ __forceinline__ R on_log(R x);
-template <> __device__ __forceinline__ double on_log<double>(double x) { return log(x); }
+// fp64 logarithms: the positive-normal-argument log of the gauge kernels (update.cuh, Mth<double>::log_, at most 1 ulp off; zero gives
+// -inf as the library does).  Only the two logs of the reference-order action tail (measurement kernel) stay with the library.
+template <> __device__ __forceinline__ double on_log<double>(double x) { return Mth<double>::log_(x); }
+__device__ __forceinline__ double on_dlog(double x) { return Mth<double>::log_(x); }
 template <> __device__ __forceinline__ float on_log<float>(float x) { return logf(x); }
 template <typename R> __device__ __forceinline__ R on_exp(R x);
 template <> __device__ __forceinline__ double on_exp<double>(double x) { return exp(x); }
 template <> __device__ __forceinline__ float on_exp<float>(float x) { return expf(x); }
 
 // o1_log_one_m_Ux, o1_Phi: o1cl.cl:40-52
-template <typename R> __device__ __forceinline__ R on_log1m(R u) { return R(log(1.0 - double(u))); }
+template <typename R> __device__ __forceinline__ R on_log1m(R u) { return R(on_dlog(1.0 - double(u))); }
 template <typename R> __device__ __forceinline__ R on_phi(R l, const OnPar<R>& q) {
     R a = R((-1.0 + 0.5 * double(q.eta) * double(l)) * double(l));
     return R(0.5 * double(a) * double(a) * double(q.b));
@@ -56,9 +59,9 @@ template <typename R, bool EXACT> __device__ __forceinline__ R on_action_tail(R 
     double s2p = sqrt(2.0 * double(Phi));
     double mn = (1.9999999999 < s2p) ? 1.9999999999 : s2p;
     R el = q.eta * l;
-    double lg = EXACT ? log((1.0 - double(el)) / (1.0 - double(u))) : log(1.0 - double(el)) - double(l);
+    double lg = EXACT ? log((1.0 - double(el)) / (1.0 - double(u))) : on_dlog(1.0 - double(el)) - double(l);
     R st = q.szl * term;
-    return R(-q.skm1_2 * log(2.0 - mn) - lg + double(Phi) * (double(Phi) - 1.0 + double(st)) / double(q.z));
+    return R(-q.skm1_2 * (EXACT ? log(2.0 - mn) : on_dlog(2.0 - mn)) - lg + double(Phi) * (double(Phi) - 1.0 + double(st)) / double(q.z));
 }
 // o1_action as the reference writes it (o1cl.cl:54-146, without ON_SUB_SCHEME, which the host never defines)
 template <typename R> __device__ __forceinline__ R on_action_exact(R u, const R nb[4], const OnPar<R>& q) {
