@@ -114,10 +114,15 @@ struct RanluxPacked {
 #pragma unroll
         for (int k = 0; k < 18; k++) w[k] = t[k];
     }
+    // three rotations in one statement: the borrow stays in the carry flag across them (each statement boundary costs three
+    // dependent instructions to park and restore it)
+    __device__ __forceinline__ void rotation72(uint32_t& carry) {
+        asm volatile(QCD_PK_PRE QCD_PK_24 QCD_PK_24 QCD_PK_24 QCD_PK_POST : QCD_PK_OPERANDS(w, carry));
+    }
     // luxury skip of 223 = 9 x 24 + 7 steps
     __device__ __forceinline__ void skip223(uint32_t& carry) {
 #pragma unroll 1
-        for (int b = 0; b < 9; b++) rotation24(carry);
+        for (int b = 0; b < 3; b++) rotation72(carry);
         tail7(carry);
     }
 };
