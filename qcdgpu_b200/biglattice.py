@@ -143,6 +143,11 @@ class BigLattice:
             else:
                 p.GPU0.kernel_run(p.sun_init_id)
         self.finish_edges(self.update_edges(-1))          # a hot start fills halos with unrelated links: take the neighbours' real ones
+        if self.dist is None and len(self.parts) > 1:
+            # This exchange copies ALL planes of the neighbours' boundary slices on the READERS' streams; the owners' first update pass
+            # writes direction X there.  Per-pass exchanges are ordered by plane separation, this one needs the readers to be done.
+            for p in self.parts.values():
+                p.GPU0.synchronize()
         self.measure()
         for p in self.parts.values():
             p.ITER_counter += 1

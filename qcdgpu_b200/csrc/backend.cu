@@ -115,6 +115,7 @@ struct qgpu {
     std::vector<Buffer> buffers;
     int active_program = 0;
     uint64_t launches = 0;
+    uint32_t* ws_counters = nullptr;     // ticket / exit counters of the persistent update kernel (update.cuh), zeroed once: the kernel re-arms them
     qgpu() { programs.resize(1); kernels.resize(1); buffers.resize(1); memset(&info, 0, sizeof(info)); }
 };
 
@@ -291,6 +292,16 @@ void settle_state_table(qgpu* h, int bid) {
         if (h->buffers[i].alive && h->buffers[i].swap_seed_buf == bid) finish_partial_pass(h, (int)i);
 }
 
+// A RANLUX state table with a twin (Buffer::twin) was written outside the two-phase kernel (host write, unmap, the stand-alone
+// producer advancing it in place): bring the twin up to date, because the two-phase kernel writes the twin only for the instances its
+// update threads cover (padding instances and BIGLAT halo slices keep what the twin held) and the tables are swapped after each pass.
+int resync_twin(qgpu* h, int bid) {
+    if (!valid_buf(h, bid)) return 0;
+    Buffer& b = h->buffers[bid];
+    if (!b.twin || !b.dptr) return 0;
+    CUDA_OK(h, cudaMemcpyAsync(b.twin, b.dptr, b.capacity, cudaMemcpyDeviceToDevice, h->stream));
+    return 0;
+}
 // run a deferred PRN producer now (writes the reference-layout buffer)
 int flush_pending(qgpu* h, int bid) {
     if (!valid_buf(h, bid)) return 0;
@@ -304,7 +315,7 @@ int flush_pending(qgpu* h, int bid) {
     if (!arg_int(k, 2, &samples)) return fail(h, "kernel %s: argument 2 (samples) not set", k.name.c_str());
     CUDA_OK(h, launch_prn_produce(k.prn_kind, (uint32_t*)buf_ptr(h, k, 0), buf_ptr(h, k, 1), (uint32_t)k.global[0], (uint32_t)samples, h->stream));
     h->launches++;
-    return 0;
+    return resync_twin(h, buf_id(k, 0));
 }
 
 // Tensor map over a link table for cp.async.bulk.tensor: dims (4 reals, ROWSIZE, planes), traversal strides (1, 2, 4), box 4 x 64 x 9,
@@ -343,6 +354,17 @@ const TensorMapBlob* link_tensor_map(qgpu* h, int bid, const ProgramCfg& c, cons
     b.tmap_rowsize = g.rowsize; b.tmap_prec = prec;
     *one_site = &b.tmap1;
     return &b.tmap;
+}
+
+// reduce_*_double2: partials [off, off + size) of buffer `src` summed into element `index` of buffer `dst`, both ranges checked
+// against what is allocated (a wrong host-side size or index must be a loud error, not an out-of-bounds access)
+int checked_reduce(qgpu* h, const Kernel& k, int src, int dst, size_t off, size_t size, size_t index, cudaStream_t st) {
+    if (!valid_buf(h, src) || !valid_buf(h, dst) || !h->buffers[src].dptr || !h->buffers[dst].dptr)
+        return fail(h, "kernel %s: buffers not set", k.name.c_str());
+    if ((off + size) * 16 > h->buffers[src].capacity || (index + 1) * 16 > h->buffers[dst].capacity)
+        return fail(h, "kernel %s: partials [%zu, %zu) or result slot %zu outside the buffers", k.name.c_str(), off, off + size, index);
+    CUDA_OK(h, launch_reduce_double2((const double2*)h->buffers[src].dptr, (uint32_t)off, (uint32_t)size, (double2*)h->buffers[dst].dptr, (uint32_t)index, st));
+    return 0;
 }
 
 int launch_kernel(qgpu* h, int kid) {
@@ -417,6 +439,12 @@ int launch_kernel(qgpu* h, int kid) {
                         else if (!sb.twin) { sb.twin = nullptr; (void)cudaGetLastError(); }
                         a.prn_table_out = (uint32_t*)sb.twin;
                         swap_seed = sb.twin ? buf_id(pk, 0) : 0;
+                        if (!h->ws_counters) {
+                            if (cudaMalloc(&h->ws_counters, 2 * sizeof(uint32_t)) == cudaSuccess)
+                                CUDA_OK(h, cudaMemsetAsync(h->ws_counters, 0, 2 * sizeof(uint32_t), st));
+                            else { h->ws_counters = nullptr; (void)cudaGetLastError(); }
+                        }
+                        a.ws_counters = h->ws_counters;
                     }
                     if (k.x_count < 0) { pbuf.pending_produce = 0; pbuf.pending_partly_fused = false; }
                     else { pbuf.pending_partly_fused = true; pbuf.swap_seed_buf = swap_seed; swap_seed = 0; }   // the other x-ranges of this pass follow
@@ -452,6 +480,9 @@ int launch_kernel(qgpu* h, int kid) {
             a.nsites = c.biglat ? (c.n1 - 2) * a.geom.n234 : a.geom.sites;
             a.block = (uint32_t)k.local0;
             size_t blocks = (a.nsites + a.block - 1) / a.block;
+            // The host sizes its reducer from its own (aligned) grid, like the reference: write every slot it will sum.
+            a.min_blocks = (uint32_t)((k.global[0] + a.block - 1) / a.block);
+            if (blocks < a.min_blocks) blocks = a.min_blocks;
             size_t slots = blocks;
             if (k.kind == K_MEASURE_PLQ && (c.fmunu || c.f0mu)) {      // only the plaquette kernel has Fmunu variants (sun_measurements_cl.cl:710-1175)
                 int offset = 0;
@@ -469,20 +500,20 @@ int launch_kernel(qgpu* h, int kid) {
         case K_REDUCE_MEAS: {
             int size = 0, index = 0;
             if (!arg_int(k, 3, &size) || !arg_int(k, 4, &index)) return fail(h, "kernel %s: arguments (size, index) not set", k.name.c_str());
-            if (!buf_ptr(h, k, 0) || !buf_ptr(h, k, 1)) return fail(h, "kernel %s: buffers not set", k.name.c_str());
-            CUDA_OK(h, launch_reduce_double2((const double2*)buf_ptr(h, k, 0), 0, (uint32_t)size, (double2*)buf_ptr(h, k, 1), (uint32_t)index, st));
+            if (size < 0 || index < 0) return fail(h, "kernel %s: negative size or index", k.name.c_str());
+            if (checked_reduce(h, k, buf_id(k, 0), buf_id(k, 1), 0, (size_t)size, (size_t)index, st) < 0) return -1;
             break;
         }
         case K_REDUCE_PLQ: {
             int index = 0;
             if (k.args.size() < 5 || k.args[3].type != Arg::U32X4 || !arg_int(k, 4, &index)) return fail(h, "kernel %s: arguments (param, index) not set", k.name.c_str());
-            if (!buf_ptr(h, k, 0) || !buf_ptr(h, k, 1)) return fail(h, "kernel %s: buffers not set", k.name.c_str());
-            CUDA_OK(h, launch_reduce_double2((const double2*)buf_ptr(h, k, 0), 0, k.args[3].u4[0], (double2*)buf_ptr(h, k, 1), (uint32_t)index, st));
+            if (index < 0) return fail(h, "kernel %s: negative index", k.name.c_str());
+            if (checked_reduce(h, k, buf_id(k, 0), buf_id(k, 1), 0, k.args[3].u4[0], (size_t)index, st) < 0) return -1;
             if (c.fmunu || c.f0mu) {   // six projected sums: partials at q*offset, results at index + q*offset2  (sun_measurements_cl.cl:1322-1357)
                 const uint32_t size = k.args[3].u4[0], offset = k.args[3].u4[1], offset2 = k.args[3].u4[2];
                 if (h->buffers[buf_id(k, 1)].capacity < ((size_t)index + 6 * (size_t)offset2 + 1) * 16) return fail(h, "kernel %s: result buffer too small for the Fmunu sums", k.name.c_str());
                 for (uint32_t q = 1; q <= 6; q++) {
-                    CUDA_OK(h, launch_reduce_double2((const double2*)buf_ptr(h, k, 0), q * offset, size, (double2*)buf_ptr(h, k, 1), (uint32_t)index + q * offset2, st));
+                    if (checked_reduce(h, k, buf_id(k, 0), buf_id(k, 1), (size_t)q * offset, size, (size_t)index + (size_t)q * offset2, st) < 0) return -1;
                     h->launches++;
                 }
             }
@@ -499,6 +530,8 @@ int launch_kernel(qgpu* h, int kid) {
             a.geom = make_geom(c); a.tbc = c.tbc ? 1 : 0; a.wilson = 1;
             a.first_site = 0; a.nsites = a.geom.sites; a.block = (uint32_t)k.local0;
             size_t blocks = (a.nsites + a.block - 1) / a.block;
+            a.min_blocks = (uint32_t)((k.global[0] + a.block - 1) / a.block);
+            if (blocks < a.min_blocks) blocks = a.min_blocks;
             if (h->buffers[buf_id(k, 1)].capacity < blocks * 16) return fail(h, "kernel %s: measurement buffer too small (%zu partials needed)", k.name.c_str(), blocks);
             CUDA_OK(h, launch_measure(c.sun, prec, a, st));
             break;
@@ -569,9 +602,10 @@ int launch_kernel(qgpu* h, int kid) {
             int index = 0;
             if (k.args.size() < 5 || k.args[3].type != Arg::U32X4 || !arg_int(k, 4, &index)) return fail(h, "kernel %s: arguments (param, index) not set", k.name.c_str());
             const uint32_t* p = k.args[3].u4;   // size, offset, offset2  (polyakov.cl:405-432)
-            CUDA_OK(h, launch_reduce_double2((const double2*)buf_ptr(h, k, 0), 0, p[0], (double2*)buf_ptr(h, k, 1), (uint32_t)index, st));
+            if (index < 0) return fail(h, "kernel %s: negative index", k.name.c_str());
+            if (checked_reduce(h, k, buf_id(k, 0), buf_id(k, 1), 0, p[0], (size_t)index, st) < 0) return -1;
             if (c.pl >= 2) {
-                CUDA_OK(h, launch_reduce_double2((const double2*)buf_ptr(h, k, 0), p[1], p[0], (double2*)buf_ptr(h, k, 1), (uint32_t)index + p[2], st));
+                if (checked_reduce(h, k, buf_id(k, 0), buf_id(k, 1), p[1], p[0], (size_t)index + p[2], st) < 0) return -1;
                 h->launches++;
             }
             break;
@@ -770,6 +804,7 @@ int qgpu_device_finalize(qgpu* h, int error_code) {
         if (h->buffers[i].shadow) cudaFreeHost(h->buffers[i].shadow);
         h->buffers[i] = Buffer();
     }
+    if (h->ws_counters) { cudaFree(h->ws_counters); h->ws_counters = nullptr; }
     cudaEventDestroy(h->ev0); cudaEventDestroy(h->ev1); cudaEventDestroy(h->evp0); cudaEventDestroy(h->evp1); cudaEventDestroy(h->ev_halo);
     if (h->own_stream) cudaStreamDestroy(h->stream);
     h->stream = nullptr; h->own_stream = false; h->initialized = false;
@@ -907,6 +942,7 @@ int qgpu_buffer_write(qgpu* h, int bid) {
     CUDA_OK(h, cudaSetDevice(h->device));
     if (flush_pending(h, bid) < 0) return -1;
     CUDA_OK(h, cudaMemcpyAsync(b.dptr, b.host_ptr, b.bytes, cudaMemcpyHostToDevice, h->stream));
+    if (resync_twin(h, bid) < 0) return -1;
     CUDA_OK(h, cudaStreamSynchronize(h->stream));
     return 0;
 }
@@ -937,6 +973,7 @@ int qgpu_buffer_unmap(qgpu* h, int bid, void* ptr) {
     CUDA_OK(h, cudaSetDevice(h->device));
     settle_state_table(h, bid);
     CUDA_OK(h, cudaMemcpyAsync((char*)b.dptr + off, ptr, b.map_len, cudaMemcpyHostToDevice, h->stream));
+    if (resync_twin(h, bid) < 0) return -1;
     CUDA_OK(h, cudaStreamSynchronize(h->stream));
     return 0;
 }

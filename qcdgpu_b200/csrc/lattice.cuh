@@ -213,6 +213,16 @@ __device__ __forceinline__ void third_row(const Cx<R> u[3], const Cx<R> v[3], Cx
         w[i].im = -u[j].re * v[k].im - u[j].im * v[k].re + u[k].re * v[j].im + u[k].im * v[j].re;
     }
 }
+// w += conj(u x v): the third row of a product added to the staple sum in the same fused operations
+template <typename R>
+__device__ __forceinline__ void third_row_add(const Cx<R> u[3], const Cx<R> v[3], Cx<R> w[3]) {
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+        const int j = (i + 1) % 3, k = (i + 2) % 3;
+        w[i].re += u[j].re * v[k].re; w[i].re -= u[j].im * v[k].im; w[i].re -= u[k].re * v[j].re; w[i].re += u[k].im * v[j].im;
+        w[i].im -= u[j].re * v[k].im; w[i].im -= u[j].im * v[k].re; w[i].im += u[k].re * v[j].im; w[i].im += u[k].im * v[j].re;
+    }
+}
 template <typename R> __device__ __forceinline__ M3<R> complete(const M3r2<R>& a) {
     M3<R> m;
 #pragma unroll

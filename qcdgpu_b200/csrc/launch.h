@@ -37,6 +37,7 @@ struct UpdateArgs {
     int overrelax;          // 1: overrelaxation pass instead of heat bath (no PRNs)
     const TensorMapBlob* tmap;   // tensor maps over the link table (4 reals, ROWSIZE sites, planes), or null: TMA staging of the staple links;
     const TensorMapBlob* tmap1;  // box = 32 sites of one parity x 3 planes, and 1 site x 3 planes
+    uint32_t* ws_counters;       // two zeroed words owned by the handle: ticket and exit counters of the persistent kernel (it re-arms them itself)
 };
 typedef cudaError_t (*UpdateLaunchFn)(const UpdateArgs&, cudaStream_t);
 // [sun-2][prec][mu]
@@ -49,6 +50,7 @@ struct MeasureArgs {
     // -D FMUNU (fmode 1) / -D F0MU (fmode 2): out_plq also receives six projected partial arrays, `offset` apart
     int fmode, gen1, gen2; uint32_t offset;
     int wilson;                                 // 1: Wilson loop W(R,T) into out_plq[BID].x instead of the plaquettes
+    uint32_t min_blocks;                        // the host's grid: every partial slot its reducer will sum must be written (zeros beyond the sites)
 };
 cudaError_t launch_measure(int sun, int prec, const MeasureArgs&, cudaStream_t);   // dispatch.cu
 

@@ -23,6 +23,7 @@ cudaError_t NAME(launch_measure)(const MeasureArgs& a, cudaStream_t st) {
     uint32_t block = a.block ? a.block : kMeasThreads;
     if (block > kMeasThreads) block = kMeasThreads;
     dim3 grid((a.nsites + block - 1) / block);
+    if (grid.x < a.min_blocks) grid.x = a.min_blocks;      // blocks without a site write a zero partial
     if (grid.x == 0) return cudaSuccess;
     const RealT* t = static_cast<const RealT*>(a.table);
     const RealT* p = static_cast<const RealT*>(a.params);

@@ -65,6 +65,11 @@ struct F4 { float x, y, z, w; };
 #define QCD_PK_24 QCD_PK_CHUNK0 QCD_PK(3, 13, 14) QCD_PK(4, 14, 15) QCD_PK(5, 15, 16) QCD_PK(6, 16, 17) QCD_PK(7, 17, 0)   \
     QCD_PK(8, 0, 1) QCD_PK(9, 1, 2) QCD_PK(10, 2, 3) QCD_PK(11, 3, 4) QCD_PK(12, 4, 5) QCD_PK(13, 5, 6) QCD_PK(14, 6, 7)   \
     QCD_PK(15, 7, 8) QCD_PK(16, 8, 9) QCD_PK(17, 9, 10)
+#define QCD_PK_CHUNK1 QCD_PK(3, 13, 14) QCD_PK(4, 14, 15) QCD_PK(5, 15, 16)
+#define QCD_PK_CHUNK2 QCD_PK(6, 16, 17) QCD_PK(7, 17, 0) QCD_PK(8, 0, 1)
+#define QCD_PK_CHUNK3 QCD_PK(9, 1, 2) QCD_PK(10, 2, 3) QCD_PK(11, 3, 4)
+#define QCD_PK_CHUNK4 QCD_PK(12, 4, 5) QCD_PK(13, 5, 6) QCD_PK(14, 6, 7)
+#define QCD_PK_CHUNK5 QCD_PK(15, 7, 8) QCD_PK(16, 8, 9) QCD_PK(17, 9, 10)
 // seven steps = one chunk of four + three limbs (72 bits: two words and the low byte of a third, %19 in / out)
 #define QCD_PK_TAIL7 QCD_PK_CHUNK0 QCD_PK(3, 13, 14) QCD_PK(4, 14, 15)                                                 \
     "shf.r.wrap.b32 a, %15, %16, 16;\n\tand.b32 a, a, 0xFF;\n\tand.b32 %19, %5, 0xFF;\n\tsubc.cc.u32 %19, a, %19;\n\t"
@@ -114,6 +119,29 @@ struct RanluxPacked {
 #pragma unroll
         for (int k = 0; k < 18; k++) w[k] = t[k];
     }
+    // four steps = one float4 sample: chunk C (0..5, a compile-time constant after unrolling) of a rotation that started at word 0
+    __device__ __forceinline__ void chunk(int C, uint32_t& carry) {
+        switch (C) {
+            case 0: asm volatile(QCD_PK_PRE QCD_PK_CHUNK0 QCD_PK_POST : QCD_PK_OPERANDS(w, carry)); break;
+            case 1: asm volatile(QCD_PK_PRE QCD_PK_CHUNK1 QCD_PK_POST : QCD_PK_OPERANDS(w, carry)); break;
+            case 2: asm volatile(QCD_PK_PRE QCD_PK_CHUNK2 QCD_PK_POST : QCD_PK_OPERANDS(w, carry)); break;
+            case 3: asm volatile(QCD_PK_PRE QCD_PK_CHUNK3 QCD_PK_POST : QCD_PK_OPERANDS(w, carry)); break;
+            case 4: asm volatile(QCD_PK_PRE QCD_PK_CHUNK4 QCD_PK_POST : QCD_PK_OPERANDS(w, carry)); break;
+            default: asm volatile(QCD_PK_PRE QCD_PK_CHUNK5 QCD_PK_POST : QCD_PK_OPERANDS(w, carry)); break;
+        }
+    }
+    // after J chunks of a rotation: renumber the words so that the next chunk is chunk 0 again (w'[i] = w[(i + 3 J) % 18])
+    template <int J> __device__ __forceinline__ void renumber() {
+        uint32_t t[18];
+#pragma unroll
+        for (int i = 0; i < 18; i++) t[i] = w[(i + 3 * J) % 18];
+#pragma unroll
+        for (int i = 0; i < 18; i++) w[i] = t[i];
+    }
+    // the float4 sample made by chunk C (numbers 4 C .. 4 C + 3 of the rotation), raw (seed << 8) unless it holds a number below 2^-12,
+    // whose fix-up reads x[n-9]: limb n - 9 of this rotation, or limb n + 15 (still the previous rotation's: chunks 3.. come later).
+    // Call right after chunk(C).  Returns true if the sample was converted to floats.
+    __device__ __forceinline__ bool sample(int C, uint4& out) const;
     // three rotations in one statement: the borrow stays in the carry flag across them (each statement boundary costs three
     // dependent instructions to park and restore it)
     __device__ __forceinline__ void rotation72(uint32_t& carry) {
@@ -297,6 +325,24 @@ struct Ranlux {
         while (n > 0) { skip4<NSKIP>(); n--; }
     }
 };
+
+__device__ __forceinline__ bool RanluxPacked::sample(int C, uint4& out) const {
+    uint32_t v[4], nx[4];
+#pragma unroll
+    for (int e = 0; e < 4; e++) {
+        const int n = 4 * C + e;
+        v[e] = limb8(n);
+        nx[e] = limb8(n >= 9 ? n - 9 : n + 15);
+    }
+    bool conv = false;
+    if (min(min(v[0], v[1]), min(v[2], v[3])) < (4096u << 8)) {
+#pragma unroll
+        for (int e = 0; e < 4; e++) v[e] = __float_as_uint(Ranlux::to_float(v[e], nx[e]));
+        conv = true;
+    }
+    out = make_uint4(v[0], v[1], v[2], v[3]);
+    return conv;
+}
 
 // state table layout in global memory (this backend's own; the reference's float4 x 7 table is
 // never read by the host except through PRNG::check_seeds):

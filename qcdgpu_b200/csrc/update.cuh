@@ -384,6 +384,37 @@ template <typename R> __device__ __forceinline__ void mul_dag_full(const M3<R>& 
         }
     third_row(G.e[0], G.e[1], G.e[2]);
 }
+// the last product of a staple, added to the staple sum S: rows 0, 1 of the product are formed (the cross product needs them) and
+// added, the third row goes into S by fused operations (six additions less per staple than forming it first)
+template <typename R> __device__ __forceinline__ void mul_r2_dag_add(const M3r2<R>& A, const M3<R>& D, M3<R>& S) {
+    Cx<R> F[2][3];
+#pragma unroll
+    for (int i = 0; i < 2; i++)
+#pragma unroll
+        for (int j = 0; j < 3; j++) {
+            Cx<R> acc = cmulc(A.e[i][0], D.e[j][0]);
+            cfmac(acc, A.e[i][1], D.e[j][1]);
+            cfmac(acc, A.e[i][2], D.e[j][2]);
+            F[i][j] = acc;
+            S.e[i][j].re += acc.re; S.e[i][j].im += acc.im;
+        }
+    third_row_add(F[0], F[1], S.e[2]);
+}
+template <typename R> __device__ __forceinline__ void mul_dag_full_add(const M3<R>& E, const M3<R>& C, M3<R>& S) {
+    Cx<R> G[2][3];
+#pragma unroll
+    for (int i = 0; i < 2; i++)
+#pragma unroll
+        for (int j = 0; j < 3; j++) {
+            Cx<R> acc = { E.e[0][i].re * C.e[0][j].re + E.e[0][i].im * C.e[0][j].im,
+                          E.e[0][i].re * C.e[0][j].im - E.e[0][i].im * C.e[0][j].re };
+            cfmacc(acc, E.e[1][i], C.e[1][j]);
+            cfmacc(acc, E.e[2][i], C.e[2][j]);
+            G[i][j] = acc;
+            S.e[i][j].re += acc.re; S.e[i][j].im += acc.im;
+        }
+    third_row_add(G[0], G[1], S.e[2]);
+}
 #ifdef QCD_S_SMEM
 // staple accumulator parked in shared memory: element e of thread t at sm[e * kThreads + t] (conflict-free)
 template <typename R> struct SmemAcc {
@@ -408,6 +439,9 @@ template <typename R> struct SmemAcc {
             for (int j = 0; j < 3; j++) { S.e[i][j].re = p[(6 * i + 2 * j) * 128]; S.e[i][j].im = p[(6 * i + 2 * j + 1) * 128]; }
         return S;
     }
+    // (experiment only: forms the product first, so its last bits differ from the register accumulator's fused third row)
+    __device__ __forceinline__ void add_r2_dag(const M3r2<R>& A, const M3<R>& D) { M3<R> F; mul_r2_dag(A, D, F); add(F); }
+    __device__ __forceinline__ void add_dag_full(const M3<R>& E, const M3<R>& C) { M3<R> G; mul_dag_full(E, C, G); add(G); }
 };
 #endif
 template <typename R> __device__ __forceinline__ void acc3(M3<R>& S, const M3<R>& F) {
@@ -458,22 +492,22 @@ __device__ __forceinline__ void staple3_plane(const R* table, const Geom& g, uin
     M3r2<R> B2 = load3<R, MU, TBC>(table, g, ps.g_pmn, ps.x_pmn, tw);      // U_mu(p-nu)
     M3r2<R> C2 = load3<R, NU, TBC>(table, g, ps.g_pmn, ps.x_pmn, tw);      // U_nu(p-nu)
     {   // forward: A B^+ C^+ = A (C B)^+
-        M3<R> Bf = complete(B), D, F;
+        M3<R> Bf = complete(B), D;
         mul_r2_full(C, Bf, D);
-        mul_r2_dag(A, D, F);
-        if (first) S.set(F); else S.add(F);
+        if (first) { M3<R> F; mul_r2_dag(A, D, F); S.set(F); } else S.add_r2_dag(A, D);
     }
     {   // backward: A2^+ B2^+ C2 = (B2 A2)^+ C2
-        M3<R> Af = complete(A2), Cf = complete(C2), E, G;
+        M3<R> Af = complete(A2), Cf = complete(C2), E;
         mul_r2_full(B2, Af, E);
-        mul_dag_full(E, Cf, G);
-        S.add(G);
+        S.add_dag_full(E, Cf);
     }
 }
 template <typename R> struct RegAcc {
     M3<R> S;
     __device__ __forceinline__ void set(const M3<R>& F) { S = F; }
     __device__ __forceinline__ void add(const M3<R>& F) { acc3(S, F); }
+    __device__ __forceinline__ void add_r2_dag(const M3r2<R>& A, const M3<R>& D) { mul_r2_dag_add(A, D, S); }
+    __device__ __forceinline__ void add_dag_full(const M3<R>& E, const M3<R>& C) { mul_dag_full_add(E, C, S); }
     __device__ __forceinline__ M3<R> get() const { return S; }
 };
 // plane order of the reference: X:{Y,Z,T} Y:{X,Z,T} Z:{Y,X,T} T:{Y,Z,X}  (su3_update_cl.cl:367-559)
@@ -608,18 +642,16 @@ template <typename R, int MU, bool TBC> struct Su3Stage {
             M3r2<R> C = take<6 * PL + 1>(g, tw);
             mul_r2_full(C, Bf, D);
             M3r2<R> A = take<6 * PL + 2>(g, tw);
-            mul_r2_dag(A, D, F);
-            if (PL == 0) S = F; else acc3(S, F);
+            if (PL == 0) { mul_r2_dag(A, D, F); S = F; } else mul_r2_dag_add(A, D, S);
         }
         {   // backward: A2^+ B2^+ C2 = (B2 A2)^+ C2
             M3r2<R> A2 = take<6 * PL + 3>(g, tw);
-            M3<R> Af = complete(A2), E, G;
+            M3<R> Af = complete(A2), E;
             M3r2<R> B2 = take<6 * PL + 4>(g, tw);
             mul_r2_full(B2, Af, E);
             M3r2<R> C2 = take<6 * PL + 5>(g, tw);
             M3<R> Cf = complete(C2);
-            mul_dag_full(E, Cf, G);
-            acc3(S, G);
+            mul_dag_full_add(E, Cf, S);
         }
     }
     // staple sum, then the site's own link
@@ -655,6 +687,25 @@ __device__ __forceinline__ void rotate_rows(M3<R>& M, const V4<R>& d) {
         M.e[A][j] = na; M.e[B][j] = nb;
     }
 }
+// the same, computing only the columns of the new row A in mask MA and of the new row B in mask MB (bit j = column j): inside the
+// Cabibbo-Marinari loop the compiler cannot see which elements of W and U the later subgroups still read
+template <typename R, int A, int B, int MA, int MB>
+__device__ __forceinline__ void rotate_rows_sel(M3<R>& M, const V4<R>& d) {
+    const Cx<R> u1 = { d.x, d.z }, u2 = { d.y, d.w };
+#pragma unroll
+    for (int j = 0; j < 3; j++) {
+        const Cx<R> ra = M.e[A][j], rb = M.e[B][j];
+        if ((MA >> j) & 1) {
+            Cx<R> na = cmul(u1, ra); cfma(na, u2, rb);
+            M.e[A][j] = na;
+        }
+        if ((MB >> j) & 1) {
+            Cx<R> nb = { -(u2.re * ra.re + u2.im * ra.im), -(u2.re * ra.im - u2.im * ra.re) };
+            cfmacc(nb, u1, rb);
+            M.e[B][j] = nb;
+        }
+    }
+}
 // aH (normalised dagger of the 2x2 block (a,b) of W) and its norm
 template <typename R, int A, int B>
 __device__ __forceinline__ V4<R> block_dagger(const M3<R>& W, R& det) {
@@ -684,10 +735,13 @@ __device__ __forceinline__ void cm_round(M3<R>& U, M3<R>& W, const Geom& g, R be
         }
         V4<R> d;
         if (kp_heatbath<R, Prn>(prn, g, aH, beta * det, d)) {
+            // Only what is read later is formed.  After the round the caller uses rows 0 and 1 of U (Gram-Schmidt, store; the
+            // third row and W are rebuilt for another round): the last subgroup needs no W and no new third row of U.  Of W the
+            // subgroup (0,2) reads the corners of rows 0 and 2 and rotates row 0 into row 2, (1,2) reads columns 1, 2 of rows 1, 2.
             switch (sub) {
-                case 0: rotate_rows<R, 0, 1>(U, d); rotate_rows<R, 0, 1>(W, d); break;
-                case 1: rotate_rows<R, 0, 2>(U, d); rotate_rows<R, 0, 2>(W, d); break;
-                default: rotate_rows<R, 1, 2>(U, d); rotate_rows<R, 1, 2>(W, d); break;
+                case 0: rotate_rows<R, 0, 1>(U, d); rotate_rows_sel<R, 0, 1, 7, 6>(W, d); break;
+                case 1: rotate_rows<R, 0, 2>(U, d); rotate_rows_sel<R, 0, 2, 0, 6>(W, d); break;
+                default: rotate_rows_sel<R, 1, 2, 7, 0>(U, d); break;
             }
         } else {
             prn.burn();    // su3_update_cl.cl:665-668
@@ -767,8 +821,11 @@ template <typename R> __host__ __device__ constexpr uint32_t tma_slot_bytes() { 
 // per warp: kTmaK link slots, kTmaK 128-byte slots for the one wrapped-around site of a row, kTmaK mbarriers
 template <typename R> __host__ __device__ constexpr size_t tma_stage_bytes() { return size_t(kUpdateThreads / 32) * kTmaK * (tma_slot_bytes<R>() + 128 + 8); }
 
-template <typename R, int MU, bool TBC> struct Su3StageTma {
+// WS: the ring lives across the items of a persistent warp (update_kernel_rlx_ws): the mbarriers are initialised once and the
+// phase a slot waits for depends on how often it was used before (ring_par, one bit per slot).
+template <typename R, int MU, bool TBC, bool WS = false> struct Su3StageTma {
     uint32_t buf, xbuf, bar;    // shared-memory addresses of this warp's slot 0, wrapped-site slot 0 and mbarrier 0
+    uint32_t ring_par;          // WS: parity of the uses of each slot by the items before this one
     const void* tmap;           // CUtensorMap over the link table: (4 reals, ROWSIZE sites, 12 planes), box = 32 sites x 3 planes
     const void* tmap1;          // same tensor, box = 1 site x 3 planes
     const R* table;
@@ -836,7 +893,7 @@ template <typename R, int MU, bool TBC> struct Su3StageTma {
         const uint32_t gid = link_gid<L>();
         const int start = may_wrap<L>() ? __shfl_sync(0xffffffffu, int(gid), 1) - 2 : 0;
         {
-            const uint32_t b = bar + 8u * SLOT, phase = (L / kTmaK) & 1;
+            const uint32_t b = bar + 8u * SLOT, phase = ((L / kTmaK) & 1) ^ (WS ? ((ring_par >> SLOT) & 1u) : 0u);
             uint32_t done = 0;
             while (!done)
                 asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
@@ -896,6 +953,30 @@ template <typename R, int MU, bool TBC> struct Su3StageTma {
         if (QCD_TMA_PF && lane == 0) prefetch_l2_links<kTmaK, kTmaK + 6>();      // the next six links towards the L2; the rest follows one plane ahead of the ring
         __syncwarp();
     }
+    // WS: once per warp -- ring addresses and mbarriers; then begin_item() / staple_and_link() / end_item() per item
+    __device__ __forceinline__ void init_ws(uint32_t smem_warp, uint32_t xslots, uint32_t bars, const void* tm, const void* tm1, const R* tab) {
+        buf = smem_warp; xbuf = xslots; bar = bars; tmap = tm; tmap1 = tm1; table = tab; lane = threadIdx.x & 31u; ring_par = 0u;
+        if (lane == 0) {
+#pragma unroll
+            for (int k = 0; k < kTmaK; k++) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(bar + 8u * k) : "memory");
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncwarp();
+    }
+    __device__ __forceinline__ void begin_item(const Geom& g, uint32_t gi, const Coord& p) {
+        gindex = gi; px = p.x;
+        Coord pmu = nb_plus<MU>(g, p);
+        s0 = plane_sites<MU, PlaneOrder<MU>::n0>(g, p, pmu);
+        s1 = plane_sites<MU, PlaneOrder<MU>::n1>(g, p, pmu);
+        s2 = plane_sites<MU, PlaneOrder<MU>::n2>(g, p, pmu);
+        prologue<0>();
+        __syncwarp();
+    }
+    // slot s was used by the links L = s, s + K, ... <= 18 of the item
+    __device__ __forceinline__ void end_item() {
+#pragma unroll
+        for (int s = 0; s < kTmaK; s++) if (((18 - s) / kTmaK + 1) & 1) ring_par ^= 1u << s;
+    }
     template <int L> __device__ __forceinline__ void prologue() const {
         if constexpr (L < kTmaK) { issue<L>(); prologue<L + 1>(); }
     }
@@ -908,18 +989,16 @@ template <typename R, int MU, bool TBC> struct Su3StageTma {
             M3r2<R> C = take<6 * PL + 1>(g, tw);
             mul_r2_full(C, Bf, D);
             M3r2<R> A = take<6 * PL + 2>(g, tw);
-            mul_r2_dag(A, D, F);
-            if (PL == 0) S = F; else acc3(S, F);
+            if (PL == 0) { mul_r2_dag(A, D, F); S = F; } else mul_r2_dag_add(A, D, S);
         }
         {   // backward: A2^+ B2^+ C2 = (B2 A2)^+ C2
             M3r2<R> A2 = take<6 * PL + 3>(g, tw);
-            M3<R> Af = complete(A2), E, G;
+            M3<R> Af = complete(A2), E;
             M3r2<R> B2 = take<6 * PL + 4>(g, tw);
             mul_r2_full(B2, Af, E);
             M3r2<R> C2 = take<6 * PL + 5>(g, tw);
             M3<R> Cf = complete(C2);
-            mul_dag_full(E, Cf, G);
-            acc3(S, G);
+            mul_dag_full_add(E, Cf, S);
         }
     }
     __device__ __forceinline__ void staple_and_link(const Geom& g, const Twist<R>& tw, M3<R>& S, M3r2<R>& m0) const {
@@ -1156,6 +1235,252 @@ overrelax_kernel_tma(R* __restrict__ table, const __grid_constant__ Geom g, int 
     or_subgroup<R, 1, 2>(U, W);
     gram_schmidt3(U.e[0], U.e[1]);
     store3<R, MU>(table, g, site.gindex, U.e[0], U.e[1]);
+}
+
+// ---------------------------------------------------------------- warp-specialised persistent update kernel (RANLUX3, SU(3), TMA rows)
+// One block of 512 threads per SM for the whole pass: warp groups 0-2 are 12 "physics" warps (staples, Cabibbo-Marinari, store), warp
+// group 3 is four "generator" warps.  Generator warp q and the physics warps q, q + 4, q + 8 share a scheduler and form an independent
+// unit: the generator warp draws a ticket (96 consecutive update threads = three y-rows of one parity, in launch order, so the L2 window
+// of remap_gid stays), hands one row to each of its physics warps and runs the RANLUX work of the three rows as THREE instances per lane,
+// stepped together -- the three borrow chains interleave in the instruction stream and keep the integer pipe busy on their own, while the
+// physics warps keep the FP64 pipe and the memory system busy.  In the two-phase kernels a warp alternates between the two kinds of work
+// and the scheduler, three warps deep, rarely sees both at the same time (fused time = generator time + physics time).
+// setmaxnreg moves registers from the generator warp group (80) to the physics warp groups (144).  Samples travel through the same
+// shared-memory columns as in update_kernel_rlx_tma (first `keep` float4 per link, raw; rare overflow path from the state in front of the
+// pass), one buffer per physics warp: the generator parks early in its round and the physics warp consumes late in its item, so a single
+// buffer with a full / empty mbarrier pair pipelines the two.  Results are bit-identical to the other kernels.
+#ifndef QCD_WS_GEN_REGS       // 4 x gen + 12 x phys = 16 x 128 (the block's registers at launch); multiples of 8
+#define QCD_WS_GEN_REGS 104
+#define QCD_WS_PHYS_REGS 136
+#endif
+#ifdef QCD_WS_TRACE
+// diagnostic build (-DQCD_WS_TRACE): clock64 stamps of the first 64 rounds of every unit (generator warp + its three physics warps):
+// slots 0-5 generator (round start, ticket, states loaded, buffers free, samples parked, states stored), 6 + 4 c .. physics warp c
+// (ticket, staples done, samples there, link stored)
+static __device__ unsigned long long g_ws_trace[592 * 64 * 24];
+#define QCD_WS_MARK(unit, round, slot) if ((threadIdx.x & 31u) == 0 && (round) < 64u && (unit) < 592u) g_ws_trace[((unit) * 64u + (round)) * 24u + (slot)] = clock64()
+#else
+#define QCD_WS_MARK(unit, round, slot)
+#endif
+constexpr int kWsPhysWarps = 12, kWsGenWarps = 4, kWsThreads = 32 * (kWsPhysWarps + kWsGenWarps), kWsChains = kWsPhysWarps / kWsGenWarps;
+constexpr uint32_t kWsDone = 0xffffffffu;
+template <typename R> __host__ __device__ constexpr size_t ws_smem_bytes(uint32_t keep) {
+    return size_t(kWsPhysWarps) * (size_t(keep) * 32 * 16            // parked samples
+                                   + 32 * 8                          // "already converted" masks
+                                   + kTmaK * (tma_slot_bytes<R>() + 128 + 8)   // link ring, wrapped-site slots, ring mbarriers
+                                   + 2 * 8 + 2 * 8                   // item (x2), full, empty mbarriers
+                                   + 2 * 4 + 8);                     // tickets (x2), pad
+}
+__device__ __forceinline__ void mbar_init(uint32_t a, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(a), "r"(count) : "memory"); }
+__device__ __forceinline__ void mbar_arrive(uint32_t a) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(a) : "memory"); }
+__device__ __forceinline__ void mbar_wait(uint32_t a, uint32_t parity) {
+    uint32_t done = 0;
+    while (!done)
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done) : "r"(a), "r"(parity) : "memory");
+}
+// kWsChains RANLUX3 instances per lane in packed form, stepped together (same `left` for all, checked by the caller)
+struct RanluxChains {
+    RanluxPacked pk[kWsChains];
+    uint32_t carry[kWsChains];
+    __device__ __forceinline__ void skip223() {
+#pragma unroll 1
+        for (int b = 0; b < 3; b++) {
+#pragma unroll
+            for (int c = 0; c < kWsChains; c++) pk[c].rotation72(carry[c]);
+        }
+#pragma unroll
+        for (int c = 0; c < kWsChains; c++) pk[c].tail7(carry[c]);
+    }
+    // j (1..6) samples from the start of a rotation; sample number k0 + C of the pass is parked at out[c] + (k0 + C) * 32 if it is below keep
+    __device__ __forceinline__ void deliver(uint32_t j, uint32_t k0, uint32_t keep, uint4* const (&out)[kWsChains], uint32_t (&conv)[kWsChains]) {
+        if (j == 6 && k0 >= keep) {
+#pragma unroll
+            for (int c = 0; c < kWsChains; c++) pk[c].rotation24(carry[c]);
+            return;
+        }
+#pragma unroll
+        for (int C = 0; C < 6; C++) {
+            if (uint32_t(C) < j) {
+#pragma unroll
+                for (int c = 0; c < kWsChains; c++) pk[c].chunk(C, carry[c]);
+                if (k0 + C < keep) {
+#pragma unroll
+                    for (int c = 0; c < kWsChains; c++) {
+                        uint4 v;
+                        if (pk[c].sample(C, v)) conv[c] |= 1u << (k0 + C);
+                        out[c][(k0 + C) * 32] = v;
+                    }
+                }
+            }
+        }
+        // a started rotation: renumber the words so that the next chunk is chunk 0 again (one small loop: this happens once per pass)
+        if (j < 6) {
+#pragma unroll 1
+            for (uint32_t i = 0; i < j; i++) {
+#pragma unroll
+                for (int c = 0; c < kWsChains; c++) pk[c].renumber<1>();
+            }
+        }
+    }
+};
+template <typename R, int MU, bool TBC, int NSKIP>
+__global__ void __launch_bounds__(kWsThreads, 1)
+update_kernel_rlx_ws(R* __restrict__ table, const R* __restrict__ params, const __grid_constant__ Geom g, int odd,
+                     const uint32_t* rtable, uint32_t* rtable_out, uint32_t instances, uint32_t samples, uint32_t keep,
+                     const __grid_constant__ TensorMapBlob tmap, const __grid_constant__ TensorMapBlob tmap1, uint32_t* counters) {
+    static_assert(NSKIP == 223, "written for RANLUX3");
+    extern __shared__ __align__(128) uint4 ws_smem[];
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+    // carve-up: [samples 12 x keep x 32 uint4][link rings 12 x K slots][wrapped-site slots][conv masks][ring mbarriers][item/full/empty][tickets]
+    const uint32_t sm0 = (uint32_t)__cvta_generic_to_shared(ws_smem);
+    const uint32_t SAMP = keep * 32u * 16u, RING = kTmaK * tma_slot_bytes<R>();
+    const uint32_t o_ring = kWsPhysWarps * SAMP, o_x = o_ring + kWsPhysWarps * RING, o_conv = o_x + kWsPhysWarps * kTmaK * 128u,
+                   o_rbar = o_conv + kWsPhysWarps * 256u, o_bar = o_rbar + kWsPhysWarps * kTmaK * 8u, o_tick = o_bar + kWsPhysWarps * 32u;
+    // per physics warp w: item barriers at o_bar + 32 w + {0, 8}, full at + 16, empty at + 24; tickets at o_tick + 8 w + {0, 4}
+    if (threadIdx.x < kWsPhysWarps) {
+        const uint32_t b = sm0 + o_bar + 32u * threadIdx.x;
+        mbar_init(b, 1); mbar_init(b + 8, 1); mbar_init(b + 16, 32); mbar_init(b + 24, 32);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    const uint32_t nthreads = g.nthreads;                 // a multiple of 32 (launcher)
+    if (warp >= kWsPhysWarps) {
+        // ------------------------------------------------------------ generator warp
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" :: "n"(QCD_WS_GEN_REGS));
+        const uint32_t q = warp - kWsPhysWarps;
+        uint4* out[kWsChains];
+#pragma unroll
+        for (int c = 0; c < kWsChains; c++) out[c] = ws_smem + (q + 4 * c) * (SAMP / 16u) + lane;
+        for (uint32_t n = 0;; n++) {
+            QCD_WS_MARK(blockIdx.x * 4u + q, n, 0);
+            uint32_t T = 0;
+            if (lane == 0) T = atomicAdd(counters, 1u);
+            T = __shfl_sync(0xffffffffu, T, 0);
+            const uint32_t kb0 = T * (32u * kWsChains);
+            const bool any = kb0 < nthreads;
+            if (lane == 0) {
+#pragma unroll
+                for (int c = 0; c < kWsChains; c++) {
+                    const uint32_t w = q + 4 * c, kb = kb0 + 32u * c;
+                    asm volatile("st.shared.u32 [%0], %1;" :: "r"(sm0 + o_tick + 8u * w + 4u * (n & 1u)), "r"(kb < nthreads ? kb : kWsDone) : "memory");
+                    mbar_arrive(sm0 + o_bar + 32u * w + 8u * (n & 1u));
+                }
+            }
+            if (!any) break;
+            QCD_WS_MARK(blockIdx.x * 4u + q, n, 1);
+            RanluxChains G;
+            uint32_t left = 0, GID[kWsChains];
+            bool uniform = true;
+            if (g.debug_skip != 1u) {
+#pragma unroll
+                for (int c = 0; c < kWsChains; c++) {
+                    const bool valid = kb0 + 32u * c < nthreads;
+                    GID[c] = thread_site(g, valid ? kb0 + 32u * c + lane : 0u, odd != 0).GID;
+                    Ranlux r;
+                    ranlux_load(r, rtable, instances, GID[c]);
+                    G.pk[c].pack(r.s); G.carry[c] = r.carry;
+                    if (c == 0) left = __shfl_sync(0xffffffffu, r.left, 0);
+                    uniform = uniform && (!valid || r.left == left);
+                }
+                uniform = __all_sync(0xffffffffu, uniform) && g.debug_skip != 3u;      // QCDGPU_DEBUG_SKIP=3: test the general path
+            }
+            QCD_WS_MARK(blockIdx.x * 4u + q, n, 2);
+            // the buffers are free once the physics warps are through with the previous item
+            if (n > 0) {
+#pragma unroll
+                for (int c = 0; c < kWsChains; c++) if (kb0 + 32u * c < nthreads) mbar_wait(sm0 + o_bar + 32u * (q + 4 * c) + 24u, (n - 1u) & 1u);
+            }
+            QCD_WS_MARK(blockIdx.x * 4u + q, n, 3);
+            uint32_t conv[kWsChains];
+#pragma unroll
+            for (int c = 0; c < kWsChains; c++) conv[c] = 0u;
+            bool signalled = false;
+            auto signal_full = [&]() {
+#pragma unroll
+                for (int c = 0; c < kWsChains; c++) {
+                    const uint32_t w = q + 4 * c;
+                    asm volatile("st.shared.v2.u32 [%0], {%1, %2};" :: "r"(sm0 + o_conv + 256u * w + 8u * lane), "r"(conv[c]), "r"(0u) : "memory");
+                    if (kb0 + 32u * c < nthreads) mbar_arrive(sm0 + o_bar + 32u * w + 16u);
+                }
+                signalled = true;
+                QCD_WS_MARK(blockIdx.x * 4u + q, n, 4);
+            };
+            if (g.debug_skip == 1u) { signal_full(); continue; }
+            if (uniform) {
+                uint32_t k = 0;
+#pragma unroll 1
+                while (k < samples) {
+                    if (left == 0u) { G.skip223(); left = 24u; }
+                    const uint32_t j = min(left >> 2, samples - k);
+                    G.deliver(j, k, keep, out, conv);
+                    k += j; left -= 4u * j;
+                    if (!signalled && k >= keep) signal_full();
+                }
+#pragma unroll
+                for (int c = 0; c < kWsChains; c++) {
+                    if (kb0 + 32u * c < nthreads) {
+                        Ranlux r;
+                        G.pk[c].unpack(r.s); r.carry = G.carry[c]; r.left = left;
+                        ranlux_store(r, rtable_out, instances, GID[c]);
+                    }
+                }
+                QCD_WS_MARK(blockIdx.x * 4u + q, n, 5);
+            } else {
+                // instances out of step with each other (never after ranlux_init + whole passes): one chain at a time, general code
+#pragma unroll 1
+                for (int c = 0; c < kWsChains; c++) {
+                    if (kb0 + 32u * c >= nthreads) continue;
+                    const uint32_t gid = thread_site(g, kb0 + 32u * c + lane, odd != 0).GID;
+                    Ranlux r;
+                    ranlux_load(r, rtable, instances, gid);
+                    unsigned long long cv = 0ull;
+                    r.template run_pass<NSKIP>(ws_smem + (q + 4 * c) * (SAMP / 16u) + lane, 32u, keep, samples, &cv);
+                    ranlux_store(r, rtable_out, instances, gid);
+                    conv[c] = (uint32_t)cv;
+                }
+                signal_full();
+            }
+        }
+        // the last generator warp to run out of tickets re-arms the counters for the next launch
+        if (lane == 0) {
+            const uint32_t d = atomicAdd(counters + 1, 1u);
+            if (d == gridDim.x * kWsGenWarps - 1u) { counters[0] = 0u; counters[1] = 0u; __threadfence(); }
+        }
+        return;
+    }
+    // ---------------------------------------------------------------- physics warp
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" :: "n"(QCD_WS_PHYS_REGS));
+    const uint32_t w = warp;
+    Su3StageTma<R, MU, TBC, true> stage;
+    stage.init_ws(sm0 + o_ring + w * RING, sm0 + o_x + w * (kTmaK * 128u), sm0 + o_rbar + w * (kTmaK * 8u), &tmap, &tmap1, table);
+    const R beta = params[0];
+    const Twist<R> tw = make_twist<3, R, TBC>(params);
+    const uint32_t bar = sm0 + o_bar + 32u * w;
+    for (uint32_t n = 0;; n++) {
+        mbar_wait(bar + 8u * (n & 1u), (n >> 1) & 1u);
+        uint32_t kb;
+        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(kb) : "r"(sm0 + o_tick + 8u * w + 4u * (n & 1u)) : "memory");
+        if (kb == kWsDone) break;
+        QCD_WS_MARK(blockIdx.x * 4u + (w & 3u), n, 6u + 4u * (w >> 2));
+        const SiteId site = thread_site(g, kb + lane, odd != 0);
+        if (g.debug_skip == 2u) { mbar_wait(bar + 16u, n & 1u); mbar_arrive(bar + 24u); continue; }
+        stage.begin_item(g, site.gindex, site.p);
+        M3<R> S;
+        M3r2<R> m0;
+        stage.staple_and_link(g, tw, S, m0);
+        stage.end_item();
+        QCD_WS_MARK(blockIdx.x * 4u + (w & 3u), n, 7u + 4u * (w >> 2));
+        mbar_wait(bar + 16u, n & 1u);
+        QCD_WS_MARK(blockIdx.x * 4u + (w & 3u), n, 8u + 4u * (w >> 2));
+        uint32_t cv;
+        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(cv) : "r"(sm0 + o_conv + 256u * w + 8u * lane) : "memory");
+        typedef PrnSmemT<NSKIP> PrnSmem;
+        PrnSmem prn(ws_smem + w * (SAMP / 16u) + lane, 32u, (unsigned long long)cv, keep, rtable + site.GID, instances);
+        heatbath_su3<R, MU, PrnSmem>(table, g, beta, site.gindex, m0, S, prn);
+        QCD_WS_MARK(blockIdx.x * 4u + (w & 3u), n, 9u + 4u * (w >> 2));
+        mbar_arrive(bar + 24u);
+    }
 }
 
 }  // namespace qcd

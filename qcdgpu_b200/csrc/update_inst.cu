@@ -16,17 +16,38 @@ typedef double RealT;
 typedef float RealT;
 #endif
 
+// Opt-in to more than 48 KB of dynamic shared memory.  cudaFuncSetAttribute applies to the CURRENT device only, and one process may
+// drive several (BigLattice parts in one process): remember the configured size per device.
+constexpr int kMaxDevices = 64;
+struct SmemConfigured { size_t bytes[kMaxDevices] = {}; };
+template <class K>
+static cudaError_t ensure_smem(K kern, size_t bytes, SmemConfigured& done) {
+    if (bytes <= 48 * 1024) return cudaSuccess;
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (dev >= 0 && dev < kMaxDevices && bytes <= done.bytes[dev]) return cudaSuccess;
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (e != cudaSuccess) return e;
+    if (dev >= 0 && dev < kMaxDevices) done.bytes[dev] = bytes;
+    return cudaSuccess;
+}
+static int sm_count() {
+    static int n[kMaxDevices] = {};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) return 1;
+    if (n[dev] == 0 && cudaDeviceGetAttribute(&n[dev], cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) n[dev] = 1;
+    return n[dev];
+}
+static int env_int(const char* name, int dflt) { const char* e = getenv(name); return e ? atoi(e) : dflt; }
+
 template <bool TBC, class Prn>
 static cudaError_t launch_one(const UpdateArgs& a, typename Prn::Args pa, cudaStream_t st) {
     dim3 block(kUpdateThreads), grid((a.geom.nthreads + kUpdateThreads - 1) / kUpdateThreads);
     if (grid.x == 0) return cudaSuccess;
     const size_t smem = (INST_SUN == 3 && kStageK > 0) ? stage_bytes<RealT>() : 0;   // link ring (update.cuh, Su3Stage)
-    static bool configured = false;
-    if (smem > 48 * 1024 && !configured) {
-        cudaError_t e = cudaFuncSetAttribute(update_kernel<INST_SUN, RealT, INST_MU, TBC, Prn>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        configured = true;
-    }
+    static SmemConfigured configured;
+    if (cudaError_t e = ensure_smem(update_kernel<INST_SUN, RealT, INST_MU, TBC, Prn>, smem, configured); e != cudaSuccess) return e;
     update_kernel<INST_SUN, RealT, INST_MU, TBC, Prn><<<grid, block, smem, st>>>(
         static_cast<RealT*>(a.table), static_cast<const RealT*>(a.params), a.geom, a.odd, pa);
     return cudaGetLastError();
@@ -40,14 +61,14 @@ static cudaError_t launch_rlx(const UpdateArgs& a, cudaStream_t st) {
     // With a separate output table the state in front of the pass survives the launch: park `keep` samples per thread, the rest
     // is regenerated on demand (update.cuh, PrnSmemT).  In place: park everything a link can consume.
     static int keep_env = -1;
-    if (keep_env < 0) { const char* e = getenv("QCDGPU_RLX_KEEP"); keep_env = e ? atoi(e) : 12; if (keep_env < 1) keep_env = 1; if (keep_env > 64) keep_env = 64; }
+    if (keep_env < 0) { keep_env = env_int("QCDGPU_RLX_KEEP", 12); if (keep_env < 1) keep_env = 1; if (keep_env > 64) keep_env = 64; }
     uint32_t* out = a.prn_table_out ? a.prn_table_out : a.prn_table;
     uint32_t keep = need;
     if (out != a.prn_table && (uint32_t)keep_env < need) keep = (uint32_t)keep_env;
     size_t smem = size_t(keep) * kUpdateThreads * sizeof(float4);
     // diagnostic: unused shared memory per block, to measure the kernel at 2 or 1 resident blocks per SM
     static int pad_env = -1;
-    if (pad_env < 0) { const char* e = getenv("QCDGPU_SMEM_PAD_KB"); pad_env = e ? atoi(e) : 0; }
+    if (pad_env < 0) pad_env = env_int("QCDGPU_SMEM_PAD_KB", 0);
     smem += size_t(pad_env) * 1024;
     if (smem > 200 * 1024 || keep > 64) {   // does not fit (smem, or the 64-bit "already converted" mask): state-in-registers variant
         if (out != a.prn_table) return cudaErrorInvalidValue;
@@ -57,28 +78,41 @@ static cudaError_t launch_rlx(const UpdateArgs& a, cudaStream_t st) {
 #if INST_SUN == 3
     // links of the staples staged by TMA: full warps that are one y-row of one parity each (update.cuh, Su3StageTma)
     static int tma_env = -1;
-    if (tma_env < 0) { const char* e = getenv("QCDGPU_TMA"); tma_env = e ? atoi(e) : 1; }
+    if (tma_env < 0) tma_env = env_int("QCDGPU_TMA", 1);
+    // warp-specialised persistent kernel (update.cuh, update_kernel_rlx_ws): needs the second state table (rare path of the parked
+    // samples), rows of 32 update threads and room for 12 sample buffers + 12 link rings in shared memory.
+    // Measured slower than the two-phase kernel below (4.46 against 3.62 ms per 64^4 pass, DESIGN.md decision 14): opt-in, QCDGPU_WS=1.
+    // QCDGPU_WS_MIN: smallest launch (update threads) that takes it; QCDGPU_WS_BLOCKS: blocks instead of one per SM.
+    static int ws_env = -1, ws_min = 0, ws_blocks = 0;
+    if (ws_env < 0) { ws_env = env_int("QCDGPU_WS", 0); ws_min = env_int("QCDGPU_WS_MIN", 0); ws_blocks = env_int("QCDGPU_WS_BLOCKS", 0); }
+    if (ws_env && tma_env && a.tmap && a.tmap1 && a.ws_counters && out != a.prn_table && keep <= 16u && pad_env == 0 &&
+        a.geom.n2 % 64u == 0u && a.geom.nthreads % 32u == 0u && a.geom.nthreads >= (uint32_t)ws_min &&
+        ws_smem_bytes<RealT>(keep) <= 227u * 1024u) {
+        auto kw = update_kernel_rlx_ws<RealT, INST_MU, TBC, 223>;
+        const size_t smem_w = ws_smem_bytes<RealT>(keep);
+        static SmemConfigured configured_w;
+        if (cudaError_t e = ensure_smem(kw, smem_w, configured_w); e != cudaSuccess) return e;
+        const uint32_t tickets = (a.geom.nthreads + 32u * kWsChains - 1u) / (32u * kWsChains);
+        uint32_t blocks = (tickets + kWsGenWarps - 1u) / kWsGenWarps;
+        const uint32_t cap = ws_blocks > 0 ? (uint32_t)ws_blocks : (uint32_t)sm_count();
+        if (blocks > cap) blocks = cap;
+        kw<<<blocks, kWsThreads, smem_w, st>>>(static_cast<RealT*>(a.table), static_cast<const RealT*>(a.params), a.geom, a.odd,
+                                              a.prn_table, out, a.prn_instances, a.prn_samples, keep, *a.tmap, *a.tmap1, a.ws_counters);
+        return cudaGetLastError();
+    }
     if (tma_env && a.tmap && a.tmap1 && kUpdateThreads == 128 && a.geom.n2 % 64u == 0u && a.geom.nthreads % kUpdateThreads == 0u) {
         auto kt = update_kernel_rlx_tma<RealT, INST_MU, TBC, 223>;
         const size_t smem_t = smem + tma_stage_bytes<RealT>();
-        static size_t configured_t = 0;
-        if (smem_t > configured_t) {
-            cudaError_t e = cudaFuncSetAttribute(kt, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_t);
-            if (e != cudaSuccess) return e;
-            configured_t = smem_t;
-        }
+        static SmemConfigured configured_t;
+        if (cudaError_t e = ensure_smem(kt, smem_t, configured_t); e != cudaSuccess) return e;
         kt<<<a.geom.nthreads / kUpdateThreads, kUpdateThreads, smem_t, st>>>(static_cast<RealT*>(a.table), static_cast<const RealT*>(a.params), a.geom, a.odd,
                                                                            a.prn_table, out, a.prn_instances, a.prn_samples, keep, *a.tmap, *a.tmap1);
         return cudaGetLastError();
     }
 #endif
     auto kern = update_kernel_rlx<INST_SUN, RealT, INST_MU, TBC, 223>;
-    static size_t configured = 0;
-    if (smem > configured) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        configured = smem;
-    }
+    static SmemConfigured configured;
+    if (cudaError_t e = ensure_smem(kern, smem, configured); e != cudaSuccess) return e;
     dim3 block(kUpdateThreads), grid((a.geom.nthreads + kUpdateThreads - 1) / kUpdateThreads);
     if (grid.x == 0) return cudaSuccess;
     kern<<<grid, block, smem, st>>>(static_cast<RealT*>(a.table), static_cast<const RealT*>(a.params), a.geom, a.odd,
@@ -107,16 +141,12 @@ cudaError_t LAUNCH_NAME(const UpdateArgs& a, cudaStream_t st) {
     if (a.overrelax) {
 #if INST_SUN == 3
         static int or_tma_env = -1;
-        if (or_tma_env < 0) { const char* e = getenv("QCDGPU_TMA"); or_tma_env = e ? atoi(e) : 1; }
+        if (or_tma_env < 0) or_tma_env = env_int("QCDGPU_TMA", 1);
         if (or_tma_env && a.tmap && a.tmap1 && kUpdateThreads == 128 && a.geom.n2 % 64u == 0u && a.geom.nthreads > 0 && a.geom.nthreads % kUpdateThreads == 0u) {
             auto kt = overrelax_kernel_tma<RealT, INST_MU>;
             const size_t smem_t = tma_stage_bytes<RealT>();
-            static bool configured_or = false;
-            if (!configured_or) {
-                cudaError_t e = cudaFuncSetAttribute(kt, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_t);
-                if (e != cudaSuccess) return e;
-                configured_or = true;
-            }
+            static SmemConfigured configured_or;
+            if (cudaError_t e = ensure_smem(kt, smem_t, configured_or); e != cudaSuccess) return e;
             kt<<<a.geom.nthreads / kUpdateThreads, kUpdateThreads, smem_t, st>>>(static_cast<RealT*>(a.table), a.geom, a.odd, *a.tmap, *a.tmap1);
             return cudaGetLastError();
         }
@@ -157,5 +187,11 @@ int REGS_NAME(int tbc, int prn_kind) {
 // diagnostic build only: copy out the phase time stamps of the last SU(3) fp64 X-direction launch
 extern "C" int qgpu_debug_trace(unsigned long long* out, size_t n) {
     return (int)cudaMemcpyFromSymbol(out, qcd::g_trace, n * sizeof(unsigned long long));
+}
+#endif
+#if defined(QCD_WS_TRACE) && INST_SUN == 3 && INST_PREC == 1 && INST_MU == 0
+// diagnostic build only: time stamps of the last SU(3) fp64 X-direction launch of the warp-specialised kernel
+extern "C" int qgpu_debug_ws_trace(unsigned long long* out, size_t n) {
+    return (int)cudaMemcpyFromSymbol(out, qcd::g_ws_trace, n * sizeof(unsigned long long));
 }
 #endif

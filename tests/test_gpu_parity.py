@@ -361,6 +361,44 @@ def test_two_phase_kernel_overflow_path_is_bit_exact(keep, sun, prec, beta):
     assert r.returncode == 0 and "IDENTICAL" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
 
 
+_WS_SCRIPT = r"""
+import sys, numpy as np
+sys.path.insert(0, sys.argv[1])
+from test_gpu_parity import make_model
+dims, prec, phi, beta = tuple(int(x) for x in sys.argv[2].split(",")), int(sys.argv[3]), float(sys.argv[4]), float(sys.argv[5])
+tables, states = [], []
+for fused in (False, True):
+    m = make_model(3, dims, prec, ints=0, prng="RANLUX3", fused=True, iters=4, beta=beta, phi=phi)
+    if not fused:
+        m.GPU0.set_fused_prng(False)
+    m.lattice_simulate()
+    tables.append(m.table_numpy())
+    m.PRNG0.produce()
+    states.append(m.PRNG0.randoms().copy())      # the NEXT pass's numbers: the generator states must agree too
+    m.close()
+assert np.array_equal(tables[0].view(np.uint8), tables[1].view(np.uint8)), float(np.abs(tables[0] - tables[1]).max())
+assert np.array_equal(states[0].view(np.uint8), states[1].view(np.uint8))
+print("IDENTICAL")
+"""
+
+
+@pytest.mark.parametrize("env", [{}, {"QCDGPU_WS_BLOCKS": "1"}, {"QCDGPU_WS_BLOCKS": "2", "QCDGPU_DEBUG_SKIP": "3"}, {"QCDGPU_WS_BLOCKS": "1", "QCDGPU_RLX_KEEP": "3"}])  # + QCDGPU_WS=1
+@pytest.mark.parametrize("dims,prec,phi,beta", [((4, 64, 4, 4), 1, 0.0, 5.7), ((6, 64, 2, 6), 1, 3.0, 1.0), ((2, 128, 4, 6), 0, 0.0, 6.0)])
+def test_warp_specialised_kernel_is_bit_exact(env, dims, prec, phi, beta):
+    """The persistent warp-specialised update kernel (update.cuh, update_kernel_rlx_ws: generator warps with three RANLUX instances per
+    lane feeding physics warps through shared memory) against the buffered kernel fed by the stand-alone producer: lattice and generator
+    states bit for bit.  One or two blocks make every unit run many rounds (ticket hand-over, buffer reuse, mbarrier parities, a last
+    ticket with fewer than three rows); QCDGPU_DEBUG_SKIP=3 forces the general generator path (instances out of step), a small
+    QCDGPU_RLX_KEEP the regeneration of samples beyond the parked ones."""
+    import subprocess
+    import sys
+    e = dict(os.environ, QCDGPU_WS="1", **env)      # the kernel is opt-in (measured slower than the two-phase kernel)
+    here = os.path.dirname(os.path.abspath(__file__))
+    r = subprocess.run([sys.executable, "-c", _WS_SCRIPT, here, ",".join(str(d) for d in dims), str(prec), str(phi), str(beta)],
+                       env=e, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "IDENTICAL" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+
+
 # ---------------------------------------------------------------------------------- overrelaxation
 @pytest.mark.parametrize("sun,dims", [(3, (4, 4, 4, 4)), (2, (4, 4, 4, 4)), (3, (2, 64, 2, 4)), (3, (4, 128, 2, 2))])
 def test_overrelaxation(sun, dims):
