@@ -33,6 +33,20 @@ NCU_DRAM_BYTES_PER_LAUNCH = 8.151837e9 + 2.028637e9   # profiles/r01_ncu_update_
 FLOPS_PER_LINK_UPDATE = 4700
 
 
+def workload_config(n_gpus: int, dims=None) -> dict:
+    """`config` of the JSON line: the workload, named the same way by both arms (native and --impl reference) for a given N."""
+    d = tuple(dims) if dims else WORKLOAD["dims"]
+    table_gb = 4 * d[0] * d[1] * d[2] * d[3] * 96 / 1e9
+    if n_gpus <= 1:
+        w = (f"SU(3) {'x'.join(map(str, d))} fp64 heat-bath sweeps (8 passes + reunitarisation), beta={WORKLOAD['beta']}, NHIT={WORKLOAD['nhit']}, "
+             f"RANLUX3, cold start")
+    else:
+        full = (d[0] * n_gpus, d[1], d[2], d[3])
+        w = (f"SU(3) {'x'.join(map(str, full))} fp64 heat-bath sweeps (8 passes + reunitarisation), BigLattice x-slab split over {n_gpus} GPUs "
+             f"({d[0]} slices per GPU, halo exchange after each pass), beta={WORKLOAD['beta']}, NHIT={WORKLOAD['nhit']}, RANLUX3, cold start")
+    return {"workload": w, "l2_policy": f"inputs_larger_than_L2 (link table {table_gb:.2f} GB per GPU vs 126 MB L2)"}
+
+
 def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -113,28 +127,32 @@ def run_reference_cpu(n_procs: int, ls: int, sweeps: int):
 
 
 def reference_main(args):
+    """--impl reference: the reference's own CPU implementation of the path (oracle/_ref/QCDGPU_cpu = the UNMODIFIED reference built
+    in its CPU_RUN configuration), on all host cores.  One step = one bounded sample of the workload: every core runs an independent
+    SU(3) 12^4 lattice for 2 sweeps (link updates/s is volume independent to first order; 64^4 does not fit the reference's int sizes,
+    SURVEY.md 0 row 6).  W warm-up steps, then exactly K timed steps; rank 0 only."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    ls = 12
-    per_step = []
-    for _ in range(args.warmup and 1):
-        run_reference_cpu(cores, ls, 1)
-    for _ in range(max(1, min(args.steps, 3))):
-        v, dt = run_reference_cpu(cores, ls, 2)
-        if v is None:
-            print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/QCDGPU_cpu missing (run make -C oracle ref where /root/reference exists)"}))
-            return
-        per_step.append((v, dt))
-    v = sum(x[0] for x in per_step) / len(per_step)
-    dt = sum(x[1] for x in per_step) / len(per_step)
-    sample = (f"reference CPU_RUN binary, {cores} independent SU(3) {ls}^4 cold-start runs (one per core), 2 sweeps each incl. "
-              f"per-sweep plaquette+action measurement; link-updates/s is volume independent to first order")
+    ls, sweeps = 12, 2
+    if run_reference_cpu(1, 4, 1)[0] is None:
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/QCDGPU_cpu missing (run make -C oracle ref where /root/reference exists)"}))
+        return
+    for _ in range(args.warmup):
+        run_reference_cpu(cores, ls, sweeps)
+    t0 = time.time()
+    for _ in range(args.steps):
+        run_reference_cpu(cores, ls, sweeps)
+    dt = time.time() - t0
+    links_per_step = 4 * ls ** 4 * sweeps * cores
+    v = links_per_step * args.steps / dt
+    sample = (f"reference CPU_RUN binary, per step {cores} independent SU(3) {ls}^4 cold-start runs (one per core), {sweeps} sweeps each incl. "
+              f"start-up and per-sweep plaquette+action measurement; {args.steps} steps in {dt:.1f} s")
     out = {"impl": "reference", "metric": "SU(3) link updates/sec", "value": v, "unit": "link-updates/s",
-           "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3 / 2,
+           "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3 / args.steps,
            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-           "config": {"workload": "SU(3) 64^4 fp64 heat-bath sweeps, beta=6.0, NHIT=10, RANLUX3, cold start (CPU sample: 12^4 per core)"},
+           "config": workload_config(int(os.environ.get("WORLD_SIZE", str(args.gpus))), tuple(int(x) for x in args.dims.split("x")) if args.dims else None),
            "cpu_baseline": {"value": v, "unit": "link-updates/s", "cores": cores, "kind": "reference", "sample": sample},
            "e2e": {"value": v, "unit": "link-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(out))
@@ -230,16 +248,18 @@ def native_single(args):
         kname = kname.replace("update_kernel_rlx<3,", "update_kernel_rlx_tma<")      # links staged by TMA (update.cuh, Su3StageTma)
     plq_total = float(plq.sum() / (6.0 * V)) if plq is not None else None
     # ---- CPU baseline: the reference itself, 1 core, bounded sample
-    cpu_v, cpu_dt = (None, None) if args.no_cpu else run_reference_cpu(1, 12, 3)
+    cpu_v, cpu_dt = (None, None) if args.no_cpu else run_reference_cpu(1, 16, 8)
     out = {
         "metric": "SU(3) link updates/sec", "value": value, "unit": "link-updates/s", "n_gpus": 1,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64" if m.precision == 1 else "f32", "data": "synthetic",
-        "config": {"workload": f"SU({m.lattice_group}) {'x'.join(map(str, dims))} {'fp64' if m.precision == 1 else 'fp32'} heat-bath sweeps (8 passes + reunitarisation), beta={m.BETA}, "
-                               f"NHIT=10, RANLUX3 ({'fused in-register' if not args.buffered else 'buffered'}), cold start" + (f", {args.or_steps} overrelaxation sweeps after each heat-bath sweep" if args.or_steps else ""),
-                   "l2_policy": (f"inputs_larger_than_L2 (link table {4 * V * link_bytes / 1e9:.2f} GB vs 126 MB L2)" if 4 * V * link_bytes > 126e6
-                                 else f"diagnostic configuration: link table {4 * V * link_bytes / 1e6:.1f} MB fits the L2, no flush"), "sweeps_per_s": args.steps / (ms * 1e-3),
-                   "plaquette_after_run": plq_total, "update_kernel_registers": regs},
+        "config": (workload_config(1, dims) if not diag and not args.buffered and not args.materialize else
+                   {"workload": f"DIAGNOSTIC: SU({m.lattice_group}) {'x'.join(map(str, dims))} {'fp64' if m.precision == 1 else 'fp32'} heat-bath sweeps (8 passes + reunitarisation), beta={m.BETA}, "
+                                f"NHIT=10, RANLUX3 ({'fused in-register' if not args.buffered else 'buffered'}), cold start" + (f", {args.or_steps} overrelaxation sweeps after each heat-bath sweep" if args.or_steps else ""),
+                    "l2_policy": (f"inputs_larger_than_L2 (link table {4 * V * link_bytes / 1e9:.2f} GB vs 126 MB L2)" if 4 * V * link_bytes > 126e6
+                                  else f"diagnostic configuration: link table {4 * V * link_bytes / 1e6:.1f} MB fits the L2, no flush")}),
+        "details": {"sweeps_per_s": args.steps / (ms * 1e-3), "plaquette_after_run": plq_total, "update_kernel_registers": regs,
+                    "prng": "RANLUX3, one generator per update thread, run inside the update kernel (fused)" if not args.buffered else "RANLUX3, stand-alone producer + PRN buffer"},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_kind,
                      "kernel": kname,
@@ -251,7 +271,7 @@ def native_single(args):
         "gpu_launches": int(launches),
         "clocks": ck,
         "cpu_baseline": ({"value": cpu_v, "unit": "link-updates/s", "cores": 1, "kind": "reference",
-                          "sample": f"oracle/_ref/QCDGPU_cpu (unmodified reference, CPU_RUN build), SU(3) 12^4 cold start, 3 sweeps incl. measurements, {cpu_dt:.1f} s"}
+                          "sample": f"oracle/_ref/QCDGPU_cpu (unmodified reference, CPU_RUN build), SU(3) 16^4 cold start, 8 sweeps incl. start-up and per-sweep measurements, {cpu_dt:.1f} s"}
                          if cpu_v else {"value": None, "unit": "link-updates/s", "cores": 0, "kind": "reference", "sample": "oracle/_ref missing"}),
     }
     print(json.dumps(out))

@@ -118,6 +118,14 @@ void  qgpu_set_fused_prng(qgpu* h, int on);
  * 8 once three x-slices of links exceed 48 MB; env QCDGPU_TILE_X overrides the automatic choice).  Results do
  * not depend on it. */
 void  qgpu_set_tile_x(qgpu* h, int tile);
+/* Folded reunitarisation (default on; env QCDGPU_FOLD_GS=0 turns it off).  The reference's sweep ends with a lattice_GramSchmidt
+ * launch over all links (suncl.cpp:5377) although its update kernels already orthonormalise every link they write
+ * (su3_update_cl.cl:672-779).  With folding on, an SU(3) update / overrelaxation kernel applies the same Gram-Schmidt function a second
+ * time before storing the link, and a lattice_GramSchmidt kernel_run whose table was completely rewritten that way since the previous
+ * call (all 8 (parity, direction) passes, every x-slice) returns without a launch: the table already holds what it would write.
+ * Anything else that writes the table (start kernels, buffer_write, unmap) makes the next call a real launch.  During a sweep
+ * neighbours are read in their twice-orthonormalised form instead of the once-orthonormalised one: a difference of rounding errors. */
+void  qgpu_set_fold_reunitarisation(qgpu* h, int on);
 /* Run on a caller-owned cudaStream_t instead of the handle's own stream (e.g. a torch stream, so that NCCL
  * send/recv of halo buffers issued through torch.distributed is ordered with the kernels). */
 int   qgpu_set_stream(qgpu* h, void* cuda_stream);

@@ -306,7 +306,7 @@ def bench_main(args, workload):
     """bench.py --gpus N under torchrun: weak scaling, one 64-slice slab of SU(3) fp64 per GPU."""
     import torch
     import torch.distributed as dist
-    from bench import ClockSampler, measured_peaks
+    from bench import ClockSampler, measured_peaks, workload_config
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -380,11 +380,10 @@ def bench_main(args, workload):
             "metric": "SU(3) link updates/sec", "value": value, "unit": "link-updates/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"SU(3) {'x'.join(map(str, full))} fp64 heat-bath sweeps, BigLattice x-slab split over {world} GPUs "
-                                   f"({dims[0]} slices per GPU), halo exchange after each of the 8 passes (NCCL send/recv, overlapped with the "
-                                   f"interior update), beta=6.0, NHIT=10, RANLUX3, cold start",
-                       "l2_policy": "inputs_larger_than_L2", "sweeps_per_s": args.steps / (ms * 1e-3),
-                       "halo_bytes_per_pass_per_gpu": B.halo_bytes_per_pass, "plaquette_after_run": float(plq.sum() / (6.0 * V_total))},
+            "config": workload_config(world, dims),
+            "details": {"sweeps_per_s": args.steps / (ms * 1e-3), "halo_bytes_per_pass_per_gpu": B.halo_bytes_per_pass,
+                        "plaquette_after_run": float(plq.sum() / (6.0 * V_total)),
+                        "halo": "NCCL send/recv of packed boundary slices, overlapped with the interior update"},
             "roofline": {"bound": "hbm", "achieved": bytes_per_s, "peak": peak, "unit": "GB/s", "frac": bytes_per_s / peak,
                          "traffic": None, "peak_source": peak_kind, "note": "per GPU, whole sweep (update + halo + reunitarisation)"},
             "e2e": {"value": e2e, "unit": "link-updates/s", "h2d_bytes_per_step": int(params.size) * world, "d2h_bytes_per_step": 16 * world},

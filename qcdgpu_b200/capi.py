@@ -49,7 +49,7 @@ EXPORTS = [
     "qgpu_kernel_get_execution_time", "qgpu_buffer_init", "qgpu_buffer_write", "qgpu_buffer_map",
     "qgpu_buffer_map_range", "qgpu_buffer_unmap", "qgpu_buffer_kill", "qgpu_buffer_size_bytes",
     "qgpu_buffer_size_align", "qgpu_buffer_size_align_step", "qgpu_set_async", "qgpu_synchronize",
-    "qgpu_set_fused_prng", "qgpu_set_tile_x", "qgpu_set_stream", "qgpu_kernel_set_x_range", "qgpu_buffer_device_ptr", "qgpu_stream", "qgpu_timer_start",
+    "qgpu_set_fused_prng", "qgpu_set_tile_x", "qgpu_set_fold_reunitarisation", "qgpu_set_stream", "qgpu_kernel_set_x_range", "qgpu_buffer_device_ptr", "qgpu_stream", "qgpu_timer_start",
     "qgpu_timer_stop", "qgpu_launch_count", "qgpu_update_kernel_registers", "qgpu_halo_copy",
     "qgpu_halo_pack", "qgpu_halo_unpack", "qgpu_halo_bytes", "qgpu_host_srand", "qgpu_host_rand_fill",
 ]
@@ -121,6 +121,7 @@ def load(build_if_missing: bool = True):
     L.qgpu_synchronize.argtypes = [vp]
     L.qgpu_set_fused_prng.argtypes = [vp, ci]
     L.qgpu_set_tile_x.argtypes = [vp, ci]
+    L.qgpu_set_fold_reunitarisation.argtypes = [vp, ci]
     L.qgpu_set_stream.argtypes = [vp, vp]
     L.qgpu_kernel_set_x_range.argtypes = [vp, ci, ci, ci]
     L.qgpu_buffer_device_ptr.argtypes = [vp, ci]
@@ -291,6 +292,9 @@ class GPU:
 
     def set_tile_x(self, tile: int):
         self.L.qgpu_set_tile_x(self.h, int(tile))
+
+    def set_fold_reunitarisation(self, on: bool):
+        self.L.qgpu_set_fold_reunitarisation(self.h, int(on))
 
     def set_stream(self, cuda_stream: int):
         self._chk(self.L.qgpu_set_stream(self.h, C.c_void_p(cuda_stream)), "set_stream")

@@ -92,6 +92,10 @@ struct Buffer {
     int swap_seed_buf = 0;           // (on the PRN buffer) state table whose swap waits for the pass's last x-range launch
     // link table: tensor map (4 reals, ROWSIZE sites, planes) for the TMA staging of the update kernel, made on first use
     TensorMapBlob tmap, tmap1; uint32_t tmap_rowsize = 0; int tmap_prec = -1; bool tmap_failed = false;
+    // link table, folded reunitarisation (qgpu_set_fold_reunitarisation): gs_cover[(odd * 4 + dir) * nx + x] = 1 once slice x was
+    // rewritten by a (parity, dir) pass that reunitarised its links twice.  Fully covered: every link already is what
+    // lattice_GramSchmidt would make of it, and that launch is skipped.  Any other writer of the table clears it.
+    std::vector<unsigned char> gs_cover; uint32_t gs_nx = 0;
     bool alive = false;
 };
 
@@ -108,6 +112,7 @@ struct qgpu {
     qgpu_device_info info;
     bool profiling = false, brief = false, show_stage = false;
     bool return_errors = false, async = false, fused = false;
+    bool fold_gs = true;
     int tile_x = -1;
     std::string last_error;
     std::vector<ProgramCfg> programs;
@@ -116,7 +121,10 @@ struct qgpu {
     int active_program = 0;
     uint64_t launches = 0;
     uint32_t* ws_counters = nullptr;     // ticket / exit counters of the persistent update kernel (update.cuh), zeroed once: the kernel re-arms them
-    qgpu() { programs.resize(1); kernels.resize(1); buffers.resize(1); memset(&info, 0, sizeof(info)); }
+    qgpu() {
+        programs.resize(1); kernels.resize(1); buffers.resize(1); memset(&info, 0, sizeof(info));
+        if (const char* e = getenv("QCDGPU_FOLD_GS")) fold_gs = atoi(e) != 0;
+    }
 };
 
 namespace {
@@ -356,6 +364,21 @@ const TensorMapBlob* link_tensor_map(qgpu* h, int bid, const ProgramCfg& c, cons
     return &b.tmap;
 }
 
+void gs_cover_clear(qgpu* h, int bid) { if (valid_buf(h, bid)) h->buffers[bid].gs_cover.clear(); }
+void gs_cover_mark(qgpu* h, int bid, int odd, int dir, uint32_t nx, uint32_t x0, uint32_t count) {
+    if (!valid_buf(h, bid)) return;
+    Buffer& b = h->buffers[bid];
+    if (b.gs_nx != nx || b.gs_cover.size() != (size_t)8 * nx) { b.gs_cover.assign((size_t)8 * nx, 0); b.gs_nx = nx; }
+    for (uint32_t x = x0; x < x0 + count && x < nx; x++) b.gs_cover[(size_t)(odd * 4 + dir) * nx + x] = 1;
+}
+bool gs_cover_complete(qgpu* h, int bid, uint32_t nx) {
+    if (!valid_buf(h, bid)) return false;
+    const Buffer& b = h->buffers[bid];
+    if (nx == 0 || b.gs_nx != nx || b.gs_cover.size() != (size_t)8 * nx) return false;
+    for (unsigned char c : b.gs_cover) if (!c) return false;
+    return true;
+}
+
 // reduce_*_double2: partials [off, off + size) of buffer `src` summed into element `index` of buffer `dst`, both ranges checked
 // against what is allocated (a wrong host-side size or index must be a loud error, not an out-of-bounds access)
 int checked_reduce(qgpu* h, const Kernel& k, int src, int dst, size_t off, size_t size, size_t index, cudaStream_t st) {
@@ -376,6 +399,7 @@ int launch_kernel(qgpu* h, int kid) {
         case K_INIT_COLD: case K_INIT_GID: {
             if (!buf_ptr(h, k, 0)) return fail(h, "kernel %s: argument 0 (lattice_table) not set", k.name.c_str());
             Geom g = make_geom(c);
+            gs_cover_clear(h, buf_id(k, 0));
             CUDA_OK(h, k.kind == K_INIT_COLD ? launch_init_cold(c.sun, prec, buf_ptr(h, k, 0), g, st) : launch_init_gid(c.sun, prec, buf_ptr(h, k, 0), g, st));
             break;
         }
@@ -385,11 +409,18 @@ int launch_kernel(qgpu* h, int kid) {
             Geom g = make_geom(c);
             size_t need = (c.sun == 3 ? 2 * (size_t)g.rowsize : 0) + g.sites;
             if (h->buffers[buf_id(k, 1)].bytes < need * 16) return fail(h, "kernel %s: PRN buffer too small for a hot start (%zu < %zu vec4)", k.name.c_str(), h->buffers[buf_id(k, 1)].bytes / 16, need);
+            gs_cover_clear(h, buf_id(k, 0));
             CUDA_OK(h, launch_init_hot(c.sun, prec, buf_ptr(h, k, 0), g, buf_ptr(h, k, 1), k.dir, st));
             break;
         }
         case K_GRAMSCHMIDT: {
             if (!buf_ptr(h, k, 0)) return fail(h, "kernel %s: argument 0 (lattice_table) not set", k.name.c_str());
+            {   // every link rewritten since the last call by passes that already reunitarised twice: nothing left to do
+                const uint32_t nx = c.biglat ? c.n1 - 2 : c.n1;
+                const bool done = h->fold_gs && c.sun == 3 && gs_cover_complete(h, buf_id(k, 0), nx);
+                gs_cover_clear(h, buf_id(k, 0));
+                if (done) return 0;      // not a launch
+            }
             CUDA_OK(h, launch_gramschmidt(c.sun, prec, buf_ptr(h, k, 0), make_geom(c), st));
             break;
         }
@@ -399,6 +430,8 @@ int launch_kernel(qgpu* h, int kid) {
             a.table = buf_ptr(h, k, 0); a.params = buf_ptr(h, k, 1);
             if (!a.table || !a.params) return fail(h, "kernel %s: arguments (lattice_table, lattice_parameters) not set", k.name.c_str());
             a.geom = make_geom(c, h->tile_x); a.odd = k.odd; a.tbc = c.tbc ? 1 : 0;
+            a.geom.fold_gs = (h->fold_gs && c.sun == 3) ? 1u : 0u;
+            const uint32_t nx_all = a.geom.upd_nx;
             if (k.x_count >= 0) {
                 if ((uint32_t)(k.x_first + k.x_count) > a.geom.upd_nx) return fail(h, "kernel %s: x-range [%d,+%d) outside the %u updated slices", k.name.c_str(), k.x_first, k.x_count, a.geom.upd_nx);
                 a.geom.upd_x0 = (uint32_t)k.x_first; a.geom.upd_nx = (uint32_t)k.x_count;
@@ -406,6 +439,7 @@ int launch_kernel(qgpu* h, int kid) {
                 if (a.geom.tile_x >= a.geom.upd_nx) a.geom.tile_x = 0;
                 if (a.geom.nthreads == 0) break;
             }
+            if (a.geom.fold_gs) gs_cover_mark(h, buf_id(k, 0), k.odd, k.dir, nx_all, a.geom.upd_x0, a.geom.upd_nx);
             const uint32_t full_threads = (c.biglat ? c.n1 - 2 : c.n1) * (a.geom.n234 / 2);
             UpdateLaunchFn fn = get_update_launcher(c.sun, prec, k.dir);
             if (!fn) return fail(h, "kernel %s: no CUDA instantiation for SUN=%d PRECISION=%d", k.name.c_str(), c.sun, c.precision);
@@ -612,7 +646,7 @@ int launch_kernel(qgpu* h, int kid) {
         }
         case K_RANLUX_INIT: {
             if (!buf_ptr(h, k, 0) || !buf_ptr(h, k, 1)) return fail(h, "kernel %s: arguments (seeds, seedtable) not set", k.name.c_str());
-            if (h->buffers[buf_id(k, 1)].bytes < k.global[0] * 26 * 4) return fail(h, "kernel %s: seed table too small", k.name.c_str());
+            if (h->buffers[buf_id(k, 1)].bytes < k.global[0] * 20 * 4) return fail(h, "kernel %s: seed table too small (20 words per instance, prng.cuh)", k.name.c_str());
             CUDA_OK(h, launch_ranlux_init((const uint32_t*)buf_ptr(h, k, 0), (uint32_t*)buf_ptr(h, k, 1), (uint32_t)k.global[0], st));
             break;
         }
@@ -739,6 +773,10 @@ const char* qgpu_last_error(qgpu* h) { return h->last_error.c_str(); }
 void qgpu_set_async(qgpu* h, int on) { h->async = on != 0; }
 void qgpu_set_fused_prng(qgpu* h, int on) { h->fused = on != 0; }
 void qgpu_set_tile_x(qgpu* h, int tile) { h->tile_x = tile; }
+void qgpu_set_fold_reunitarisation(qgpu* h, int on) {
+    h->fold_gs = on != 0;
+    for (size_t i = 1; i < h->buffers.size(); i++) h->buffers[i].gs_cover.clear();
+}
 int qgpu_set_stream(qgpu* h, void* stream) {
     if (!h->initialized) return fail(h, "set_stream before device_initialize");
     if (h->own_stream) { cudaStreamSynchronize(h->stream); cudaStreamDestroy(h->stream); h->own_stream = false; }
@@ -942,6 +980,7 @@ int qgpu_buffer_write(qgpu* h, int bid) {
     CUDA_OK(h, cudaSetDevice(h->device));
     if (flush_pending(h, bid) < 0) return -1;
     CUDA_OK(h, cudaMemcpyAsync(b.dptr, b.host_ptr, b.bytes, cudaMemcpyHostToDevice, h->stream));
+    b.gs_cover.clear();
     if (resync_twin(h, bid) < 0) return -1;
     CUDA_OK(h, cudaStreamSynchronize(h->stream));
     return 0;
@@ -973,6 +1012,7 @@ int qgpu_buffer_unmap(qgpu* h, int bid, void* ptr) {
     CUDA_OK(h, cudaSetDevice(h->device));
     settle_state_table(h, bid);
     CUDA_OK(h, cudaMemcpyAsync((char*)b.dptr + off, ptr, b.map_len, cudaMemcpyHostToDevice, h->stream));
+    b.gs_cover.clear();
     if (resync_twin(h, bid) < 0) return -1;
     CUDA_OK(h, cudaStreamSynchronize(h->stream));
     return 0;

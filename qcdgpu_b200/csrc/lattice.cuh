@@ -33,6 +33,8 @@ struct Geom {
     uint32_t tw_lo, tw_hi;        // BIGLAT twist test: x + left_sites/n234 == tw_lo || == tw_hi
     uint32_t tile_x;              // L2 tiling of the update passes: x-chunk width (0 = reference order)
     uint32_t debug_skip;          // diagnostics (env QCDGPU_DEBUG_SKIP): 1 = skip the generator phase, 2 = skip the physics phase
+    uint32_t fold_gs;             // SU(3): reunitarise the updated link a second time before it is stored -- what the sweep's separate
+                                  // lattice_GramSchmidt pass would do to it later; the backend then skips that pass (backend.cu, gs_cover)
     uint32_t upd_x0, upd_nx;      // x-range of this launch inside the updated region (halo/interior split); nthreads = upd_nx*N4*N2/2*N3
 };
 

@@ -205,32 +205,6 @@ struct Ranlux {
         left -= 4;
         return { o[0], o[1], o[2], o[3] };
     }
-    // A whole block of 24 numbers = 6 float4 samples, written to out[q * stride], q = 0..5.  Requires left == 0 or 24
-    // on entry (block boundary).  No register rotation: after 24 steps the ring is canonical again.
-    template <int NSKIP> __device__ __forceinline__ void next24(float4* out, uint32_t stride) {
-        if (left == 0) luxury_skip<NSKIP>();
-        // the "uni < 2^-12" fix-up of number k reads seeds[8-k]: for k <= 8 that word is overwritten later in this
-        // block (step 15+k), so keep the nine old values; for k >= 9 it is s[32-k], already final when step k runs
-        uint32_t old[9];
-#pragma unroll
-        for (int k = 0; k < 9; k++) old[k] = s[k];
-        block24();
-        float o[24];
-#pragma unroll
-        for (int k = 0; k < 24; k++) {
-            const uint32_t x = s[23 - k];
-            const uint32_t nx = (k <= 8) ? old[8 - k] : s[32 - k];
-            float f = __uint2float_rn(x) * 2.3283064365386963e-10f;
-            if (x < (4096u << 8)) {
-                f = __fadd_rn(f, __fmul_rn(5.9604644775390625e-8f, __uint2float_rn(nx) * 2.3283064365386963e-10f));
-                if (f == 0.0f) f = 5.9604644775390625e-8f * 5.9604644775390625e-8f;
-            }
-            o[k] = f;
-        }
-#pragma unroll
-        for (int q = 0; q < 6; q++) out[q * stride] = make_float4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]);
-        left = 0;
-    }
     // float of the k-th number just produced (x = new seed << 8, nx = seeds[j24 after the step] << 8), reference
     // semantics incl. the "uni < 2^-12" fix-up (random.cpp:565-569)
     static __device__ __forceinline__ float to_float(uint32_t x, uint32_t nx) {
@@ -240,71 +214,6 @@ struct Ranlux {
             if (f == 0.0f) f = 5.9604644775390625e-8f * 5.9604644775390625e-8f;
         }
         return f;
-    }
-    // One pass worth of generator work in a single loop (every code piece instantiated once, to stay inside the
-    // instruction cache): advance by `samples` float4 and park the first `keep` of them at out[k * stride].
-    // Parked samples stay RAW (four seeds << 8): only the ~7 of 33 that a link really consumes get converted, by the
-    // consumer.  The exception is a sample containing a number below 2^-12, whose fix-up needs a seed that is gone
-    // later: it is converted here and flagged in `*converted` (bit k).  Whole 24-number blocks avoid the register rotation.
-    template <int NSKIP> __device__ __forceinline__ void run_pass(uint4* out, uint32_t stride, uint32_t keep, uint32_t samples,
-                                                                  unsigned long long* converted) {
-        static_assert(NSKIP == 223, "the packed period path is written for RANLUX3 (223 = 9 x 24 + 7)");
-        uint32_t k = 0;
-        unsigned long long conv = 0ull;
-#pragma unroll 1
-        while (k < samples) {
-            if (left == 0) {
-                // period boundary: whole periods (skip + 24 numbers = 6 samples), and the skip of a started one, in packed form
-                RanluxPacked pk;
-                pk.pack(s);
-#pragma unroll 1
-                do {
-                    pk.skip223(carry);
-                    if (k + 6 > samples) { left = 24; break; }
-                    if (k < keep) {
-                        // the "uni < 2^-12" fix-up of number n reads x[n-9]: for n <= 8 a limb that leaves the window in this block
-                        uint32_t old[9];
-#pragma unroll
-                        for (int i = 0; i < 9; i++) old[i] = pk.limb8(15 + i);
-                        pk.rotation24(carry);
-#pragma unroll
-                        for (int q = 0; q < 6; q++) {
-                            uint32_t w[4], nx[4];
-#pragma unroll
-                            for (int e = 0; e < 4; e++) {
-                                const int n = 4 * q + e;
-                                w[e] = pk.limb8(n);
-                                nx[e] = (n <= 8) ? old[n] : pk.limb8(n - 9);
-                            }
-                            if (min(min(w[0], w[1]), min(w[2], w[3])) < (4096u << 8)) {
-#pragma unroll
-                                for (int e = 0; e < 4; e++) w[e] = __float_as_uint(to_float(w[e], nx[e]));
-                                conv |= 1ull << (k + q);
-                            }
-                            if (k + q < keep) out[(k + q) * stride] = make_uint4(w[0], w[1], w[2], w[3]);
-                        }
-                    } else {
-                        pk.rotation24(carry);
-                    }
-                    k += 6;
-                } while (k < samples);
-                pk.unpack(s);
-                continue;
-            }
-            asm volatile(QCD_SWB_PRE QCD_SWB_4 QCD_SWB_POST : QCD_SWB_OPERANDS(s, carry));
-            if (k < keep) {
-                uint32_t w[4] = { s[23], s[22], s[21], s[20] };
-                if (min(min(w[0], w[1]), min(w[2], w[3])) < (4096u << 8)) {
-#pragma unroll
-                    for (int e = 0; e < 4; e++) w[e] = __float_as_uint(to_float(w[e], s[8 - e]));
-                    conv |= 1ull << k;
-                }
-                out[k * stride] = make_uint4(w[0], w[1], w[2], w[3]);
-            }
-            rotate<4>();
-            left -= 4; k++;
-        }
-        *converted = conv;
     }
     // advance by one float4 sample without converting
     template <int NSKIP> __device__ __forceinline__ void skip4() {
@@ -344,30 +253,139 @@ __device__ __forceinline__ bool RanluxPacked::sample(int C, uint4& out) const {
     return conv;
 }
 
-// state table layout in global memory (this backend's own; the reference's float4 x 7 table is
-// never read by the host except through PRNG::check_seeds):
-//   word w (0..25) of instance i at  table[w * instances + i]; w 0..23 seeds << 8, 24 carry, 25 left
+// State table in global memory (this backend's own; the reference's float4 x 7 table is never read by the host except through
+// PRNG::check_seeds): the generator in PACKED form, at a sample boundary (the next subtract-with-borrow step replaces
+// limb 0):  word w (0..19) of instance i at table[w * instances + i];  w 0..17 the 576-bit ring (RanluxPacked), 18 carry, 19 left.
+// 20 words instead of the 26 of the unpacked form: 0.4 GB less DRAM traffic per 64^4 pass, and the two-phase kernels need no
+// pack / unpack at all.
+constexpr int kRanluxStateWords = 20;
 __device__ __forceinline__ void ranlux_load(Ranlux& r, const uint32_t* table, uint32_t instances, uint32_t i) {
+    RanluxPacked pk;
 #pragma unroll
-    for (int w = 0; w < 24; w++) r.s[w] = table[size_t(w) * instances + i];
-    r.carry = table[size_t(24) * instances + i];
-    r.left = table[size_t(25) * instances + i];
+    for (int w = 0; w < 18; w++) pk.w[w] = table[size_t(w) * instances + i];
+    pk.unpack(r.s);
+    r.carry = table[size_t(18) * instances + i];
+    r.left = table[size_t(19) * instances + i];
 }
 __device__ __forceinline__ void ranlux_store(const Ranlux& r, uint32_t* table, uint32_t instances, uint32_t i) {
+    RanluxPacked pk;
+    pk.pack(r.s);
 #pragma unroll
-    for (int w = 0; w < 24; w++) table[size_t(w) * instances + i] = r.s[w];
-    table[size_t(24) * instances + i] = r.carry;
-    table[size_t(25) * instances + i] = r.left;
+    for (int w = 0; w < 18; w++) table[size_t(w) * instances + i] = pk.w[w];
+    table[size_t(18) * instances + i] = r.carry;
+    table[size_t(19) * instances + i] = r.left;
 }
+// NC RANLUX3 instances per thread in packed form, stepped together (the borrow chains of different instances interleave in the
+// instruction stream).  NC = 1: the generator phase of the two-phase update kernels; NC = 3: the generator warps of the
+// warp-specialised kernel, which require the same `left` for all instances.
+template <int NC> struct RanluxPk {
+    RanluxPacked pk[NC];
+    uint32_t carry[NC];
+    __device__ __forceinline__ uint32_t load(int c, const uint32_t* table, uint32_t instances, uint32_t i) {
+#pragma unroll
+        for (int w = 0; w < 18; w++) pk[c].w[w] = table[size_t(w) * instances + i];
+        carry[c] = table[size_t(18) * instances + i];
+        return table[size_t(19) * instances + i];       // left
+    }
+    __device__ __forceinline__ void store(int c, uint32_t* table, uint32_t instances, uint32_t i, uint32_t left) const {
+#pragma unroll
+        for (int w = 0; w < 18; w++) table[size_t(w) * instances + i] = pk[c].w[w];
+        table[size_t(18) * instances + i] = carry[c];
+        table[size_t(19) * instances + i] = left;
+    }
+    __device__ __forceinline__ void skip223() {
+#pragma unroll 1
+        for (int b = 0; b < 3; b++) {
+#pragma unroll
+            for (int c = 0; c < NC; c++) pk[c].rotation72(carry[c]);
+        }
+#pragma unroll
+        for (int c = 0; c < NC; c++) pk[c].tail7(carry[c]);
+    }
+    // j (1..6) samples from the start of a rotation; sample number k0 + C of the pass is parked at out[c][(k0 + C) * stride] if below keep
+    __device__ __forceinline__ void deliver(uint32_t j, uint32_t k0, uint32_t keep, uint4* const (&out)[NC], uint32_t stride,
+                                            unsigned long long (&conv)[NC]) {
+        if (j == 6 && k0 >= keep) {
+#pragma unroll
+            for (int c = 0; c < NC; c++) pk[c].rotation24(carry[c]);
+            return;
+        }
+        if (NC == 1 && j == 6) {
+            // a whole rotation in one statement (one borrow chain, no parking of the carry between the samples), then the six samples:
+            // the "uni < 2^-12" fix-up of number n reads x[n-9], for n <= 8 a limb that leaves the window in this rotation
+            uint32_t old[9];
+#pragma unroll
+            for (int i = 0; i < 9; i++) old[i] = pk[0].limb8(15 + i);
+            pk[0].rotation24(carry[0]);
+#pragma unroll
+            for (int q = 0; q < 6; q++) {
+                uint32_t v[4], nx[4];
+#pragma unroll
+                for (int e = 0; e < 4; e++) {
+                    const int n = 4 * q + e;
+                    v[e] = pk[0].limb8(n);
+                    nx[e] = (n <= 8) ? old[n] : pk[0].limb8(n - 9);
+                }
+                if (min(min(v[0], v[1]), min(v[2], v[3])) < (4096u << 8)) {
+#pragma unroll
+                    for (int e = 0; e < 4; e++) v[e] = __float_as_uint(Ranlux::to_float(v[e], nx[e]));
+                    conv[0] |= 1ull << (k0 + q);
+                }
+                if (k0 + q < keep) out[0][(k0 + q) * stride] = make_uint4(v[0], v[1], v[2], v[3]);
+            }
+            return;
+        }
+#pragma unroll
+        for (int C = 0; C < 6; C++) {
+            if (uint32_t(C) < j) {
+#pragma unroll
+                for (int c = 0; c < NC; c++) pk[c].chunk(C, carry[c]);
+                if (k0 + C < keep) {
+#pragma unroll
+                    for (int c = 0; c < NC; c++) {
+                        uint4 v;
+                        if (pk[c].sample(C, v)) conv[c] |= 1ull << (k0 + C);
+                        out[c][(k0 + C) * stride] = v;
+                    }
+                }
+            }
+        }
+        // a started rotation: renumber the words so that the next chunk is chunk 0 again (a small loop: once per pass)
+        if (j < 6) {
+#pragma unroll 1
+            for (uint32_t i = 0; i < j; i++) {
+#pragma unroll
+                for (int c = 0; c < NC; c++) pk[c].template renumber<1>();
+            }
+        }
+    }
+    // One pass of generator work: advance by `samples` float4 and park the first `keep` of them, RAW (four seeds << 8): only the ~7 of
+    // 33 that a link really consumes get converted, by the consumer.  The exception is a sample containing a number below 2^-12, whose
+    // fix-up needs a seed that is gone later: it is converted here and flagged in conv (bit k).  parked() is called once all `keep`
+    // samples are in place.  `left` (numbers left before the next luxury skip) is read and updated.
+    template <class F>
+    __device__ __forceinline__ void pass(uint32_t& left, uint32_t samples, uint32_t keep, uint4* const (&out)[NC], uint32_t stride,
+                                         unsigned long long (&conv)[NC], F parked) {
+        uint32_t k = 0;
+        bool told = false;
+#pragma unroll 1
+        while (k < samples) {
+            if (left == 0u) { skip223(); left = 24u; }
+            const uint32_t j = min(left >> 2, samples - k);
+            deliver(j, k, keep, out, stride, conv);
+            k += j; left -= 4u * j;
+            if (!told && k >= keep) { parked(); told = true; }
+        }
+        if (!told) parked();
+    }
+};
 // Rare path of the two-phase kernel: sample number `index` of the pass, regenerated from the generator state in front of
 // the pass (word w at state[w * instances]; the kernel writes the advanced state to the other table).  Not inlined: its
 // 26 state registers must not count against the physics phase.
 template <int NSKIP>
 __device__ __noinline__ float4 ranlux_overflow(const uint32_t* state, uint32_t instances, uint32_t index) {
     Ranlux r;
-#pragma unroll
-    for (int w = 0; w < 24; w++) r.s[w] = state[size_t(w) * instances];
-    r.carry = state[size_t(24) * instances]; r.left = state[size_t(25) * instances];
+    ranlux_load(r, state, instances, 0u);
     F4 v = r.template next4<NSKIP>();
 #pragma unroll 1
     for (uint32_t i = 0; i < index; i++) v = r.template next4<NSKIP>();

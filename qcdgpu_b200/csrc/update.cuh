@@ -102,7 +102,7 @@ struct PrnSmemT {
     __device__ __forceinline__ PrnSmemT(const uint4* base, uint32_t stride_, unsigned long long conv, uint32_t keep_,
                                         const uint32_t* state_, uint32_t instances_)
         : p(base), k(0), stride(stride_), keep(keep_), converted(conv), state(state_), instances(instances_) {}
-    // parked samples are raw seeds << 8 unless flagged as already converted (run_pass, prng.cuh)
+    // parked samples are raw seeds << 8 unless flagged as already converted (RanluxPk::pass, prng.cuh)
     __device__ __forceinline__ F4 get(uint32_t i) const {
         if (i >= keep) {
             float4 v = ranlux_overflow<NSKIP>(state, instances, i);
@@ -178,7 +178,23 @@ using PrnMrg = PrnSmallState<Mrg32k3a, 8>;
 // ---------------------------------------------------------------- math helpers
 template <typename R> struct Mth;
 template <> struct Mth<double> {
-    static __device__ __forceinline__ double sqrt_(double x) { return sqrt(x); }   // (seed + Newton + residual step measured slower: 3.65 vs 3.62 ms)
+#ifdef QCD_LIBDEVICE_SQRT
+    static __device__ __forceinline__ double sqrt_(double x) { return sqrt(x); }
+#else
+    // sqrt of 0 <= x <= 1 (1 - cos^2 of the Kennedy-Pendleton angles: zero or a normal number) WITHOUT a branch: reciprocal-square-root
+    // seed + two Newton steps + one residual step; zero through a select.  The library call has a slow-path branch, and a branch ends the
+    // basic block: the five independent chains of a Kennedy-Pendleton trial (two logarithms, cos, sqrt, sincos) then run one after the
+    // other instead of interleaved, which is what made the Cabibbo-Marinari section 60 % of the kernel's time (profiles/r02_*).
+    // (one Newton step leaves 1/sqrt(x) with relative error e ~ 2^-44; the residual step squares it: root error 1.5 e^2)
+    static __device__ __forceinline__ double sqrt_(double x) {
+        double y;
+        asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+        const double inv = fma(y, fma(-0.5 * x * y, y, 0.5), y);
+        const double r = x * inv;
+        const double root = fma(fma(-r, r, x), 0.5 * inv, r);
+        return (x == 0.0) ? 0.0 : root;
+    }
+#endif
     static __device__ __forceinline__ double rcp_(double x) { return fast_rcp(x); }      // positive normal arguments only
     // sqrt(x) and 1 / sqrt(x) of a positive normal x from one reciprocal-square-root (one residual step for the root)
     static __device__ __forceinline__ void sqrt_and_rcp(double x, double& root, double& inv) {
@@ -197,8 +213,10 @@ template <> struct Mth<double> {
         int hx = __double2hiint(x);
         const int lx = __double2loint(x);
         // zero (XOR128 / PM / the INTS=2 closed forms can deliver r = 1): -inf as the library; an argument 1 - r is never negative or
-        // subnormal (those, inf and nan give nan); no call into the library here -- its inlined body would cost what this function saves
-        if (hx < 0x00100000 || hx >= 0x7ff00000) return (x == 0.0) ? -CUDART_INF : CUDART_NAN;
+        // subnormal (those, inf and nan give nan).  No branch (selects at the end): the logarithms of a trial must stay in one basic
+        // block with the other chains so that ptxas interleaves them.
+        const bool special = hx < 0x00100000 || hx >= 0x7ff00000;
+        const double special_value = (x == 0.0) ? -CUDART_INF : CUDART_NAN;
         int k = (hx >> 20) - 1023;
         hx &= 0x000fffff;
         const int i = (hx + 0x95f64) & 0x100000;
@@ -218,7 +236,8 @@ template <> struct Mth<double> {
         const double t1 = w * (3.999999999940941908e-01 + w * (2.222219843214978396e-01 + w * 1.531383769920937332e-01));
         const double t2 = z * (6.666666666666735130e-01 + w * (2.857142874366239149e-01 + w * (1.818357216161805012e-01 + w * 1.479819860511658591e-01)));
         const double R = t2 + t1, hfsq = 0.5 * f * f;
-        return dk * 6.93147180369123816490e-01 - ((hfsq - (s * (hfsq + R) + dk * 1.90821492927058770002e-10)) - f);
+        const double res = dk * 6.93147180369123816490e-01 - ((hfsq - (s * (hfsq + R) + dk * 1.90821492927058770002e-10)) - f);
+        return special ? special_value : res;
     }
 #endif
 #ifdef QCD_LIBDEVICE_TRIG
@@ -234,24 +253,24 @@ template <> struct Mth<double> {
         const double qd = rint(t);
         q = int(qd);
         const double z = (t - qd) * 1.5707963267948966192;
-        const double z2 = z * z;
-        double ps = fma(z2, 2.8114572543455207632e-15, -7.6471637318198164759e-13);     // 1/17!, -1/15!
-        ps = fma(ps, z2, 1.6059043836821614599e-10);                                     //  1/13!
-        ps = fma(ps, z2, -2.5052108385441718775e-08);                                    // -1/11!
-        ps = fma(ps, z2, 2.7557319223985890653e-06);                                     //  1/9!
-        ps = fma(ps, z2, -1.9841269841269841270e-04);                                    // -1/7!
-        ps = fma(ps, z2, 8.3333333333333333333e-03);                                     //  1/5!
-        ps = fma(ps, z2, -1.6666666666666666667e-01);                                    // -1/3!
-        sn = fma(ps * z2, z, z);
-        double pc = fma(z2, -1.5619206968586226462e-16, 4.7794773323873852974e-14);      // -1/18!, 1/16!
-        pc = fma(pc, z2, -1.1470745597729724714e-11);                                    // -1/14!
-        pc = fma(pc, z2, 2.0876756987868098979e-09);                                     //  1/12!
-        pc = fma(pc, z2, -2.7557319223985890653e-07);                                    // -1/10!
-        pc = fma(pc, z2, 2.4801587301587301587e-05);                                     //  1/8!
-        pc = fma(pc, z2, -1.3888888888888888889e-03);                                    // -1/6!
-        pc = fma(pc, z2, 4.1666666666666666667e-02);                                     //  1/4!
-        pc = fma(pc, z2, -0.5);
-        cs = fma(pc, z2, 1.0);
+        // Both polynomials in Estrin form on w = z^2 (pairs, then w^2 and w^4): five dependent operations deep instead of nine -- the
+        // Kennedy-Pendleton step is a chain of dependent FP64 operations run by three warps per scheduler, its depth is its cost.
+        const double w = z * z, w2 = w * w, w4 = w2 * w2;
+        // sin z = z + z w (s0 + s1 w + ... + s7 w^7),  s_k = (-1)^(k+1) / (2k+3)!
+        const double s01 = fma(w, 8.3333333333333333333e-03, -1.6666666666666666667e-01);     //  1/5! w - 1/3!
+        const double s23 = fma(w, 2.7557319223985890653e-06, -1.9841269841269841270e-04);     //  1/9! w - 1/7!
+        const double s45 = fma(w, 1.6059043836821614599e-10, -2.5052108385441718775e-08);     //  1/13! w - 1/11!
+        const double s67 = fma(w, 2.8114572543455207632e-15, -7.6471637318198164759e-13);     //  1/17! w - 1/15!
+        const double ps = fma(w4, fma(w2, s67, s45), fma(w2, s23, s01));
+        sn = fma(ps * w, z, z);
+        // cos z = 1 + w (c0 + c1 w + ... + c8 w^8),  c_k = (-1)^(k+1) / (2k+2)!
+        const double c01 = fma(w, 4.1666666666666666667e-02, -0.5);                            //  1/4! w - 1/2!
+        const double c23 = fma(w, 2.4801587301587301587e-05, -1.3888888888888888889e-03);     //  1/8! w - 1/6!
+        const double c45 = fma(w, 2.0876756987868098979e-09, -2.7557319223985890653e-07);     //  1/12! w - 1/10!
+        const double c67 = fma(w, 4.7794773323873852974e-14, -1.1470745597729724714e-11);     //  1/16! w - 1/14!
+        const double c8 = -1.5619206968586226462e-16;                                          // -1/18!
+        const double pc = fma(w4, fma(w4, c8, fma(w2, c67, c45)), fma(w2, c23, c01));
+        cs = fma(pc, w, 1.0);
     }
     static __device__ __forceinline__ double cos2pi(double x) {
         double sn, cs; int q;
@@ -278,7 +297,7 @@ template <> struct Mth<float> {
 };
 
 // Kennedy-Pendleton sampling of the new SU(2) element (reference: lattice_heatbath2).
-// aH = (r/sqrt(det r))^+ as a 4-vector, bdet = beta*sqrt(det).  Returns false after NHIT rejections.
+// aH = (r/sqrt(det r))^+ as a 4-vector, ibdet = 1 / (beta*sqrt(det)).  Returns false after NHIT rejections.
 // direction part of the new element: uniform point on S^2 from (r.x, r.y)
 template <typename R> struct KpDir { R costh, sinth, sinphi, cosphi; };
 template <typename R> __device__ __forceinline__ KpDir<R> kp_direction(R rx, R ry) {
@@ -299,8 +318,7 @@ template <typename R> __device__ __forceinline__ V4<R> kp_compose(R delta, const
     return su2_mul(c, aH);
 }
 template <typename R, class Prn>
-__device__ __forceinline__ bool kp_heatbath(Prn& prn, const Geom& g, const V4<R>& aH, R bdet, V4<R>& out) {
-    R ibdet = Mth<R>::rcp_(bdet);
+__device__ __forceinline__ bool kp_heatbath(Prn& prn, const Geom& g, const V4<R>& aH, R ibdet, V4<R>& out) {
     if constexpr (Prn::kGid) {
         double r[4];
         prn.trial_d(r);
@@ -706,6 +724,26 @@ __device__ __forceinline__ void rotate_rows_sel(M3<R>& M, const V4<R>& d) {
         }
     }
 }
+// 1 / beta: formed once per thread at kernel entry and parked in shared memory (every thread of the block writes the same value and
+// reads it back inside the Cabibbo-Marinari loop).  Left to the compiler, beta was re-loaded from lattice_parameters and divided by
+// in every subgroup step, at the head of the step's dependency chain.
+template <typename R> struct InvBeta {
+    static __device__ __forceinline__ R* slot() { __shared__ R s; return &s; }
+    static __device__ __forceinline__ void park(const R* params) { *reinterpret_cast<volatile R*>(slot()) = R(1) / params[0]; }
+    static __device__ __forceinline__ R get() { return *reinterpret_cast<volatile R*>(slot()); }
+};
+// aH (normalised dagger of the 2x2 block (a,b) of W), its norm and the reciprocal of the norm
+template <typename R, int A, int B>
+__device__ __forceinline__ V4<R> block_dagger_inv(const M3<R>& W, R& idet) {
+    V4<R> aH;
+    aH.x =  (W.e[A][A].re + W.e[B][B].re);
+    aH.z = -(W.e[A][A].im - W.e[B][B].im);
+    aH.y = -(W.e[A][B].re - W.e[B][A].re);
+    aH.w = -(W.e[A][B].im + W.e[B][A].im);
+    idet = rsqrt_r(aH.x * aH.x + aH.y * aH.y + aH.z * aH.z + aH.w * aH.w);
+    aH.x *= idet; aH.y *= idet; aH.z *= idet; aH.w *= idet;
+    return aH;
+}
 // aH (normalised dagger of the 2x2 block (a,b) of W) and its norm
 template <typename R, int A, int B>
 __device__ __forceinline__ V4<R> block_dagger(const M3<R>& W, R& det) {
@@ -726,15 +764,15 @@ template <typename R, class Prn>
 __device__ __forceinline__ void cm_round(M3<R>& U, M3<R>& W, const Geom& g, R beta, Prn& prn) {
 #pragma unroll 1
     for (int sub = 0; sub < 3; sub++) {
-        R det;
+        R idet;
         V4<R> aH;
         switch (sub) {
-            case 0: aH = block_dagger<R, 0, 1>(W, det); break;
-            case 1: aH = block_dagger<R, 0, 2>(W, det); break;
-            default: aH = block_dagger<R, 1, 2>(W, det); break;
+            case 0: aH = block_dagger_inv<R, 0, 1>(W, idet); break;
+            case 1: aH = block_dagger_inv<R, 0, 2>(W, idet); break;
+            default: aH = block_dagger_inv<R, 1, 2>(W, idet); break;
         }
         V4<R> d;
-        if (kp_heatbath<R, Prn>(prn, g, aH, beta * det, d)) {
+        if (kp_heatbath<R, Prn>(prn, g, aH, idet * InvBeta<R>::get(), d)) {       // 1 / (beta sqrt(det))
             // Only what is read later is formed.  After the round the caller uses rows 0 and 1 of U (Gram-Schmidt, store; the
             // third row and W are rebuilt for another round): the last subgroup needs no W and no new third row of U.  Of W the
             // subgroup (0,2) reads the corners of rows 0 and 2 and rotates row 0 into row 2, (1,2) reads columns 1, 2 of rows 1, 2.
@@ -1029,17 +1067,17 @@ __device__ __forceinline__ void heatbath_su3(R* table, const Geom& g, R beta, ui
         cm_round<R, Prn>(U, W, g, beta, prn);
         gram_schmidt3(U.e[0], U.e[1]);
     }
+    if (g.fold_gs) gram_schmidt3(U.e[0], U.e[1]);      // the sweep's reunitarisation pass, applied here (same function, same values)
     store3<R, MU>(table, g, gindex, U.e[0], U.e[1]);
 }
 template <typename R, int MU, bool TBC, class Prn>
 __device__ __forceinline__ void update_site_su2(R* table, const Geom& g, R beta, const Twist<R>& tw, uint32_t gindex, const Coord& p, Prn& prn) {
     V4<R> S = staple2<R, MU, TBC>(table, g, p, gindex, tw);
     // su2_update_cl.cl:448-461: aH = S^+/|S|, det = 2|S|
-    R n = Mth<R>::sqrt_(S.x * S.x + S.y * S.y + S.z * S.z + S.w * S.w);
-    R in = R(1) / n;
+    R in = rsqrt_r(S.x * S.x + S.y * S.y + S.z * S.z + S.w * S.w);
     V4<R> aH = { S.x * in, -S.y * in, -S.z * in, -S.w * in };
     V4<R> d;
-    if (kp_heatbath<R, Prn>(prn, g, aH, beta * (R(2) * n), d))
+    if (kp_heatbath<R, Prn>(prn, g, aH, R(0.5) * in * InvBeta<R>::get(), d))       // 1 / (beta 2 |S|)
         st_plane(table, g, gindex, MU, d);
     // on NHIT rejections the old (untwisted, stored) link stays -- su2_update_cl.cl:541-548.  With TBC the
     // reference would store the twisted m0 back; that only differs on the x = N1-1 Y-links.
@@ -1060,6 +1098,7 @@ __device__ __forceinline__ void overrelax_site_su3(R* table, const Geom& g, uint
     or_subgroup<R, 0, 2>(U, W);
     or_subgroup<R, 1, 2>(U, W);
     gram_schmidt3(U.e[0], U.e[1]);
+    if (g.fold_gs) gram_schmidt3(U.e[0], U.e[1]);
     store3<R, MU>(table, g, gindex, U.e[0], U.e[1]);
 }
 template <typename R, int MU>
@@ -1101,6 +1140,7 @@ update_kernel(R* __restrict__ table, const R* __restrict__ params, const __grid_
     const SiteId site = thread_site(g, GID, odd != 0);
     GID = site.GID;
     const R beta = params[0];
+    InvBeta<R>::park(params);
     const Twist<R> tw = make_twist<SUN, R, TBC>(params);
     const uint32_t gindex = site.gindex;
     Prn prn(pargs, g, GID, gindex);
@@ -1134,9 +1174,10 @@ update_kernel_rlx(R* __restrict__ table, const R* __restrict__ params, const __g
     const bool active = GID < g.nthreads;
     const SiteId site = thread_site(g, active ? GID : 0u, odd != 0);
     GID = site.GID;
-    unsigned long long converted = 0ull;
-    Ranlux r;
-    if (active && g.debug_skip != 1u) ranlux_load(r, rtable, instances, GID);     // 26 DRAM loads in flight while the site's addresses are formed
+    unsigned long long converted[1] = { 0ull };
+    RanluxPk<1> r;
+    uint32_t left = 0;
+    if (active && g.debug_skip != 1u) left = r.load(0, rtable, instances, GID);     // 20 DRAM loads in flight while the site's addresses are formed
     // (prefetching the state of the block that will take this block's place into the L2 was measured: the 26 extra instructions
     //  per warp cost more than the shorter wait saves, 34.4 -> 35.0 ms per sweep)
     const uint32_t gindex = site.gindex;
@@ -1147,8 +1188,9 @@ update_kernel_rlx(R* __restrict__ table, const R* __restrict__ params, const __g
         //  step -- 1.17 blocks in this phase at a time, tools/trace_phases.py -- and the lock costs 4.04 -> 4.11 ms per pass.)
         QCD_TRACE_MARK(1);
         if (active) {
-            r.template run_pass<NSKIP>(prn_smem + threadIdx.x, kUpdateThreads, keep, samples, &converted);
-            ranlux_store(r, rtable_out, instances, GID);
+            uint4* const out[1] = { prn_smem + threadIdx.x };
+            r.pass(left, samples, keep, out, kUpdateThreads, converted, [] {});
+            r.store(0, rtable_out, instances, GID, left);
         }
         QCD_TRACE_MARK(2);
     }
@@ -1156,10 +1198,11 @@ update_kernel_rlx(R* __restrict__ table, const R* __restrict__ params, const __g
     if (g.debug_skip == 2u) return;
     // phase 2: the link update
     const R beta = params[0];
+    InvBeta<R>::park(params);
     const Twist<R> tw = make_twist<SUN, R, TBC>(params);
     typedef PrnSmemT<NSKIP> PrnSmem;
     // in place (rtable_out == rtable) the launcher parks every sample a link can consume, the rare path is unreachable
-    PrnSmem prn(prn_smem + threadIdx.x, kUpdateThreads, converted, (rtable_out != rtable) ? keep : 0xffffffffu, rtable + GID, instances);
+    PrnSmem prn(prn_smem + threadIdx.x, kUpdateThreads, converted[0], (rtable_out != rtable) ? keep : 0xffffffffu, rtable + GID, instances);
     if (SUN == 3) update_site_su3<R, MU, TBC, PrnSmem>(table, g, beta, tw, gindex, p, prn);
     else          update_site_su2<R, MU, TBC, PrnSmem>(table, g, beta, tw, gindex, p, prn);
     QCD_TRACE_MARK(3);
@@ -1176,9 +1219,10 @@ update_kernel_rlx_tma(R* __restrict__ table, const R* __restrict__ params, const
     extern __shared__ __align__(128) uint4 prn_smem[];
     const SiteId site = thread_site(g, blockIdx.x * blockDim.x + threadIdx.x, odd != 0);      // the launcher guarantees full blocks
     const uint32_t GID = site.GID;
-    unsigned long long converted = 0ull;
-    Ranlux r;
-    if (g.debug_skip != 1u) ranlux_load(r, rtable, instances, GID);
+    unsigned long long converted[1] = { 0ull };
+    RanluxPk<1> r;
+    uint32_t left = 0;
+    if (g.debug_skip != 1u) left = r.load(0, rtable, instances, GID);
     const uint32_t gindex = site.gindex;
     const Coord p = site.p;
     // ring of this warp behind the parked samples, mbarriers behind the rings
@@ -1189,14 +1233,16 @@ update_kernel_rlx_tma(R* __restrict__ table, const R* __restrict__ params, const
     stage.begin(base + warp * RING, base + NW * RING + warp * (kTmaK * 128u), base + NW * (RING + kTmaK * 128u) + warp * (kTmaK * 8u),
                 &tmap, &tmap1, table, g, gindex, p);
     if (g.debug_skip != 1u) {   // phase 1: the pass's whole RANLUX work (the first three links land meanwhile)
-        r.template run_pass<NSKIP>(prn_smem + threadIdx.x, kUpdateThreads, keep, samples, &converted);
-        ranlux_store(r, rtable_out, instances, GID);
+        uint4* const out[1] = { prn_smem + threadIdx.x };
+        r.pass(left, samples, keep, out, kUpdateThreads, converted, [] {});
+        r.store(0, rtable_out, instances, GID, left);
     }
     if (g.debug_skip == 2u) return;
     const R beta = params[0];
+    InvBeta<R>::park(params);
     const Twist<R> tw = make_twist<3, R, TBC>(params);
     typedef PrnSmemT<NSKIP> PrnSmem;
-    PrnSmem prn(prn_smem + threadIdx.x, kUpdateThreads, converted, (rtable_out != rtable) ? keep : 0xffffffffu, rtable + GID, instances);
+    PrnSmem prn(prn_smem + threadIdx.x, kUpdateThreads, converted[0], (rtable_out != rtable) ? keep : 0xffffffffu, rtable + GID, instances);
     update_site_su3_staged<R, MU, TBC, PrnSmem, Su3StageTma<R, MU, TBC>>(table, g, beta, tw, stage, prn);
 }
 template <int SUN, typename R, int MU>
@@ -1234,6 +1280,7 @@ overrelax_kernel_tma(R* __restrict__ table, const __grid_constant__ Geom g, int 
     or_subgroup<R, 0, 2>(U, W);
     or_subgroup<R, 1, 2>(U, W);
     gram_schmidt3(U.e[0], U.e[1]);
+    if (g.fold_gs) gram_schmidt3(U.e[0], U.e[1]);
     store3<R, MU>(table, g, site.gindex, U.e[0], U.e[1]);
 }
 
@@ -1279,51 +1326,6 @@ __device__ __forceinline__ void mbar_wait(uint32_t a, uint32_t parity) {
         asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
                      : "=r"(done) : "r"(a), "r"(parity) : "memory");
 }
-// kWsChains RANLUX3 instances per lane in packed form, stepped together (same `left` for all, checked by the caller)
-struct RanluxChains {
-    RanluxPacked pk[kWsChains];
-    uint32_t carry[kWsChains];
-    __device__ __forceinline__ void skip223() {
-#pragma unroll 1
-        for (int b = 0; b < 3; b++) {
-#pragma unroll
-            for (int c = 0; c < kWsChains; c++) pk[c].rotation72(carry[c]);
-        }
-#pragma unroll
-        for (int c = 0; c < kWsChains; c++) pk[c].tail7(carry[c]);
-    }
-    // j (1..6) samples from the start of a rotation; sample number k0 + C of the pass is parked at out[c] + (k0 + C) * 32 if it is below keep
-    __device__ __forceinline__ void deliver(uint32_t j, uint32_t k0, uint32_t keep, uint4* const (&out)[kWsChains], uint32_t (&conv)[kWsChains]) {
-        if (j == 6 && k0 >= keep) {
-#pragma unroll
-            for (int c = 0; c < kWsChains; c++) pk[c].rotation24(carry[c]);
-            return;
-        }
-#pragma unroll
-        for (int C = 0; C < 6; C++) {
-            if (uint32_t(C) < j) {
-#pragma unroll
-                for (int c = 0; c < kWsChains; c++) pk[c].chunk(C, carry[c]);
-                if (k0 + C < keep) {
-#pragma unroll
-                    for (int c = 0; c < kWsChains; c++) {
-                        uint4 v;
-                        if (pk[c].sample(C, v)) conv[c] |= 1u << (k0 + C);
-                        out[c][(k0 + C) * 32] = v;
-                    }
-                }
-            }
-        }
-        // a started rotation: renumber the words so that the next chunk is chunk 0 again (one small loop: this happens once per pass)
-        if (j < 6) {
-#pragma unroll 1
-            for (uint32_t i = 0; i < j; i++) {
-#pragma unroll
-                for (int c = 0; c < kWsChains; c++) pk[c].renumber<1>();
-            }
-        }
-    }
-};
 template <typename R, int MU, bool TBC, int NSKIP>
 __global__ void __launch_bounds__(kWsThreads, 1)
 update_kernel_rlx_ws(R* __restrict__ table, const R* __restrict__ params, const __grid_constant__ Geom g, int odd,
@@ -1369,7 +1371,7 @@ update_kernel_rlx_ws(R* __restrict__ table, const R* __restrict__ params, const 
             }
             if (!any) break;
             QCD_WS_MARK(blockIdx.x * 4u + q, n, 1);
-            RanluxChains G;
+            RanluxPk<kWsChains> G;
             uint32_t left = 0, GID[kWsChains];
             bool uniform = true;
             if (g.debug_skip != 1u) {
@@ -1377,11 +1379,9 @@ update_kernel_rlx_ws(R* __restrict__ table, const R* __restrict__ params, const 
                 for (int c = 0; c < kWsChains; c++) {
                     const bool valid = kb0 + 32u * c < nthreads;
                     GID[c] = thread_site(g, valid ? kb0 + 32u * c + lane : 0u, odd != 0).GID;
-                    Ranlux r;
-                    ranlux_load(r, rtable, instances, GID[c]);
-                    G.pk[c].pack(r.s); G.carry[c] = r.carry;
-                    if (c == 0) left = __shfl_sync(0xffffffffu, r.left, 0);
-                    uniform = uniform && (!valid || r.left == left);
+                    const uint32_t l = G.load(c, rtable, instances, GID[c]);
+                    if (c == 0) left = __shfl_sync(0xffffffffu, l, 0);
+                    uniform = uniform && (!valid || l == left);
                 }
                 uniform = __all_sync(0xffffffffu, uniform) && g.debug_skip != 3u;      // QCDGPU_DEBUG_SKIP=3: test the general path
             }
@@ -1392,52 +1392,38 @@ update_kernel_rlx_ws(R* __restrict__ table, const R* __restrict__ params, const 
                 for (int c = 0; c < kWsChains; c++) if (kb0 + 32u * c < nthreads) mbar_wait(sm0 + o_bar + 32u * (q + 4 * c) + 24u, (n - 1u) & 1u);
             }
             QCD_WS_MARK(blockIdx.x * 4u + q, n, 3);
-            uint32_t conv[kWsChains];
+            unsigned long long conv[kWsChains];
 #pragma unroll
-            for (int c = 0; c < kWsChains; c++) conv[c] = 0u;
-            bool signalled = false;
+            for (int c = 0; c < kWsChains; c++) conv[c] = 0ull;
             auto signal_full = [&]() {
 #pragma unroll
                 for (int c = 0; c < kWsChains; c++) {
                     const uint32_t w = q + 4 * c;
-                    asm volatile("st.shared.v2.u32 [%0], {%1, %2};" :: "r"(sm0 + o_conv + 256u * w + 8u * lane), "r"(conv[c]), "r"(0u) : "memory");
+                    asm volatile("st.shared.v2.u32 [%0], {%1, %2};" :: "r"(sm0 + o_conv + 256u * w + 8u * lane), "r"((uint32_t)conv[c]), "r"((uint32_t)(conv[c] >> 32)) : "memory");
                     if (kb0 + 32u * c < nthreads) mbar_arrive(sm0 + o_bar + 32u * w + 16u);
                 }
-                signalled = true;
                 QCD_WS_MARK(blockIdx.x * 4u + q, n, 4);
             };
             if (g.debug_skip == 1u) { signal_full(); continue; }
             if (uniform) {
-                uint32_t k = 0;
-#pragma unroll 1
-                while (k < samples) {
-                    if (left == 0u) { G.skip223(); left = 24u; }
-                    const uint32_t j = min(left >> 2, samples - k);
-                    G.deliver(j, k, keep, out, conv);
-                    k += j; left -= 4u * j;
-                    if (!signalled && k >= keep) signal_full();
-                }
+                G.pass(left, samples, keep, out, 32u, conv, signal_full);
 #pragma unroll
-                for (int c = 0; c < kWsChains; c++) {
-                    if (kb0 + 32u * c < nthreads) {
-                        Ranlux r;
-                        G.pk[c].unpack(r.s); r.carry = G.carry[c]; r.left = left;
-                        ranlux_store(r, rtable_out, instances, GID[c]);
-                    }
-                }
+                for (int c = 0; c < kWsChains; c++)
+                    if (kb0 + 32u * c < nthreads) G.store(c, rtable_out, instances, GID[c], left);
                 QCD_WS_MARK(blockIdx.x * 4u + q, n, 5);
             } else {
-                // instances out of step with each other (never after ranlux_init + whole passes): one chain at a time, general code
+                // instances out of step with each other (never after ranlux_init + whole passes): one instance at a time
 #pragma unroll 1
                 for (int c = 0; c < kWsChains; c++) {
                     if (kb0 + 32u * c >= nthreads) continue;
                     const uint32_t gid = thread_site(g, kb0 + 32u * c + lane, odd != 0).GID;
-                    Ranlux r;
-                    ranlux_load(r, rtable, instances, gid);
-                    unsigned long long cv = 0ull;
-                    r.template run_pass<NSKIP>(ws_smem + (q + 4 * c) * (SAMP / 16u) + lane, 32u, keep, samples, &cv);
-                    ranlux_store(r, rtable_out, instances, gid);
-                    conv[c] = (uint32_t)cv;
+                    RanluxPk<1> r;
+                    uint32_t l = r.load(0, rtable, instances, gid);
+                    unsigned long long cv[1] = { 0ull };
+                    uint4* const o1[1] = { ws_smem + (q + 4 * c) * (SAMP / 16u) + lane };
+                    r.pass(l, samples, keep, o1, 32u, cv, [] {});
+                    r.store(0, rtable_out, instances, gid, l);
+                    conv[c] = cv[0];
                 }
                 signal_full();
             }
@@ -1455,6 +1441,7 @@ update_kernel_rlx_ws(R* __restrict__ table, const R* __restrict__ params, const 
     Su3StageTma<R, MU, TBC, true> stage;
     stage.init_ws(sm0 + o_ring + w * RING, sm0 + o_x + w * (kTmaK * 128u), sm0 + o_rbar + w * (kTmaK * 8u), &tmap, &tmap1, table);
     const R beta = params[0];
+    InvBeta<R>::park(params);
     const Twist<R> tw = make_twist<3, R, TBC>(params);
     const uint32_t bar = sm0 + o_bar + 32u * w;
     for (uint32_t n = 0;; n++) {
@@ -1473,10 +1460,10 @@ update_kernel_rlx_ws(R* __restrict__ table, const R* __restrict__ params, const 
         QCD_WS_MARK(blockIdx.x * 4u + (w & 3u), n, 7u + 4u * (w >> 2));
         mbar_wait(bar + 16u, n & 1u);
         QCD_WS_MARK(blockIdx.x * 4u + (w & 3u), n, 8u + 4u * (w >> 2));
-        uint32_t cv;
-        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(cv) : "r"(sm0 + o_conv + 256u * w + 8u * lane) : "memory");
+        uint32_t cv0, cv1;
+        asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(cv0), "=r"(cv1) : "r"(sm0 + o_conv + 256u * w + 8u * lane) : "memory");
         typedef PrnSmemT<NSKIP> PrnSmem;
-        PrnSmem prn(ws_smem + w * (SAMP / 16u) + lane, 32u, (unsigned long long)cv, keep, rtable + site.GID, instances);
+        PrnSmem prn(ws_smem + w * (SAMP / 16u) + lane, 32u, ((unsigned long long)cv1 << 32) | cv0, keep, rtable + site.GID, instances);
         heatbath_su3<R, MU, PrnSmem>(table, g, beta, site.gindex, m0, S, prn);
         QCD_WS_MARK(blockIdx.x * 4u + (w & 3u), n, 9u + 4u * (w >> 2));
         mbar_arrive(bar + 24u);

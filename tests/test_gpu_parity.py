@@ -399,6 +399,36 @@ def test_warp_specialised_kernel_is_bit_exact(env, dims, prec, phi, beta):
     assert r.returncode == 0 and "IDENTICAL" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
 
 
+# ---------------------------------------------------------------------------------- folded reunitarisation
+@pytest.mark.parametrize("dims,prec,gen", [((4, 4, 4, 8), 1, "RANLUX3"), ((2, 64, 2, 4), 1, "RANLUX3"), ((4, 4, 4, 4), 0, "XOR128")])
+def test_folded_reunitarisation(dims, prec, gen):
+    """qgpu_set_fold_reunitarisation: SU(3) update kernels apply the sweep's Gram-Schmidt pass to the link they write and the
+    lattice_GramSchmidt launch is skipped once all 8 passes covered the table.  The end-of-sweep table must be what the separate pass
+    produces from the same updates: compared with folding off the lattices differ by rounding errors only (links read during the sweep are
+    orthonormalised twice instead of once), one launch per sweep disappears, and a table written by anything else (start kernels,
+    a host write) is reunitarised by a real launch."""
+    tables, launches = [], []
+    for fold in (False, True):
+        m = make_model(3, dims, prec, ints=0, prng=gen, fused=True, iters=3, beta=6.0)
+        m.GPU0.set_fold_reunitarisation(fold)
+        m.lattice_start()
+        l0 = m.GPU0.launch_count()
+        for _ in range(3):
+            m.lattice_sweep()
+        launches.append(m.GPU0.launch_count() - l0)
+        tables.append(m.table_numpy())
+        if fold:
+            # a host write of the table must bring the real launch back
+            m.GPU0.buffer_write_from(m.lattice_table, m.GPU0.buffer_map(m.lattice_table, np.uint8).copy())
+            l1 = m.GPU0.launch_count()
+            m.GPU0.kernel_run(m.sun_GramSchmidt_id)
+            assert m.GPU0.launch_count() - l1 == 1
+        m.close()
+    assert launches[0] - launches[1] == 3, launches
+    tol = 1e-12 if prec == 1 else 2e-5
+    assert float(np.abs(tables[0] - tables[1]).max()) < tol
+
+
 # ---------------------------------------------------------------------------------- overrelaxation
 @pytest.mark.parametrize("sun,dims", [(3, (4, 4, 4, 4)), (2, (4, 4, 4, 4)), (3, (2, 64, 2, 4)), (3, (4, 128, 2, 2))])
 def test_overrelaxation(sun, dims):
