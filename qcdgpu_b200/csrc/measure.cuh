@@ -10,8 +10,8 @@
 // lattice_measurement buffer (slot BID) so the host-visible buffers keep their meaning; the
 // second-stage kernel sums them in a fixed order (deterministic, no atomics).
 //
-// Roofs at SU(3) 64^4 fp64: 6.44 GB of links (1.0 ms at the measured HBM rate) and ~1800 DFMA per site (1.6 ms at the fp64
-// rate); the kernel takes 3.0 ms.  A three-threads-per-site split (two plaquettes each, 168 registers) was measured
+// Roofs at SU(3) 64^4 fp64: 6.44 GB of links (1.0 ms at the measured HBM rate) and ~1500 FP64 operations per site (two-row products
+// and the Lagrange identity for the third rows, retrace_plq3_r2; 1800 with full 3x3 products, 3.0 ms).  A three-threads-per-site split (two plaquettes each, 168 registers) was measured
 // slower (3.6 ms): the extra link loads and third-row reconstructions cost more than the occupancy gains.
 #pragma once
 #include "lattice.cuh"
@@ -64,6 +64,35 @@ __device__ __forceinline__ double retrace_plq3(const M3<double>& U1, const M3<do
         }
     return tr;
 }
+// The same trace from the two stored rows of the LEFT factors U1, U4 (no third rows for them): A = U1 U2 and B = U4 U3 are SU(3), so only
+// their rows 0, 1 are formed and the third rows enter through (a x b) . conj(c x d) = (a.c*)(b.d*) - (a.d*)(b.c*):
+//   Re Tr(A B^+) = Re[ d00 + d11 + conj(d00 d11 - d01 d10) ],  dij = A_i . conj(B_j)
+// 200 instead of 234 FP64 operations per plaquette, and four third-row reconstructions less per site.
+template <typename T1, typename T4>
+__device__ __forceinline__ double retrace_plq3_r2(const T1& U1, const M3<double>& U2, const M3<double>& U3, const T4& U4) {
+    Cx<double> A[2][3], B[2][3];
+#pragma unroll
+    for (int i = 0; i < 2; i++)
+#pragma unroll
+        for (int j = 0; j < 3; j++) {
+            Cx<double> a = cmul(U1.e[i][0], U2.e[0][j]); cfma(a, U1.e[i][1], U2.e[1][j]); cfma(a, U1.e[i][2], U2.e[2][j]);
+            Cx<double> b = cmul(U4.e[i][0], U3.e[0][j]); cfma(b, U4.e[i][1], U3.e[1][j]); cfma(b, U4.e[i][2], U3.e[2][j]);
+            A[i][j] = a; B[i][j] = b;
+        }
+    Cx<double> d00 = cmulc(A[0][0], B[0][0]), d11 = cmulc(A[1][0], B[1][0]), d01 = cmulc(A[0][0], B[1][0]), d10 = cmulc(A[1][0], B[0][0]);
+#pragma unroll
+    for (int j = 1; j < 3; j++) { cfmac(d00, A[0][j], B[0][j]); cfmac(d11, A[1][j], B[1][j]); cfmac(d01, A[0][j], B[1][j]); cfmac(d10, A[1][j], B[0][j]); }
+    return d00.re + d11.re + (d00.re * d11.re - d00.im * d11.im) - (d01.re * d10.re - d01.im * d10.im);
+}
+// the two stored rows in double (no third row)
+template <typename R> __device__ __forceinline__ M3r2<double> promote3_r2(const M3r2<R>& a) {
+    M3r2<double> m;
+#pragma unroll
+    for (int i = 0; i < 2; i++)
+#pragma unroll
+        for (int j = 0; j < 3; j++) m.e[i][j] = { double(a.e[i][j].re), double(a.e[i][j].im) };
+    return m;
+}
 __device__ __forceinline__ V4<double> promote2(const V4<float>& a) { return { double(a.x), double(a.y), double(a.z), double(a.w) }; }
 __device__ __forceinline__ V4<double> promote2(const V4<double>& a) { return a; }
 __device__ __forceinline__ double retrace_plq2(const V4<double>& U1, const V4<double>& U2, const V4<double>& U3, const V4<double>& U4) {
@@ -87,17 +116,18 @@ measure_kernel(const R* __restrict__ table, const R* __restrict__ params, const 
         uint32_t gX = coords_to_gid(g, pX), gY = coords_to_gid(g, pY), gZ = coords_to_gid(g, pZ), gT = coords_to_gid(g, pT);
         double spat, temp;
         if (SUN == 3) {
-            M3<double> ux = promote3(load3<R, 0, TBC>(table, g, gid, p.x, tw));
-            M3<double> uy = promote3(load3<R, 1, TBC>(table, g, gid, p.x, tw));
-            M3<double> uz = promote3(load3<R, 2, TBC>(table, g, gid, p.x, tw));
-            M3<double> ut = promote3(load3<R, 3, TBC>(table, g, gid, p.x, tw));
+            // the site's own links are only ever LEFT factors: two rows
+            M3r2<double> ux = promote3_r2(load3<R, 0, TBC>(table, g, gid, p.x, tw));
+            M3r2<double> uy = promote3_r2(load3<R, 1, TBC>(table, g, gid, p.x, tw));
+            M3r2<double> uz = promote3_r2(load3<R, 2, TBC>(table, g, gid, p.x, tw));
+            M3r2<double> ut = promote3_r2(load3<R, 3, TBC>(table, g, gid, p.x, tw));
             // sun_measurements_cl.cl:140-172
-            spat  = retrace_plq3(ux, promote3(load3<R, 1, TBC>(table, g, gX, pX.x, tw)), promote3(load3<R, 0, TBC>(table, g, gY, pY.x, tw)), uy);
-            spat += retrace_plq3(ux, promote3(load3<R, 2, TBC>(table, g, gX, pX.x, tw)), promote3(load3<R, 0, TBC>(table, g, gZ, pZ.x, tw)), uz);
-            temp  = retrace_plq3(ux, promote3(load3<R, 3, TBC>(table, g, gX, pX.x, tw)), promote3(load3<R, 0, TBC>(table, g, gT, pT.x, tw)), ut);
-            spat += retrace_plq3(uy, promote3(load3<R, 2, TBC>(table, g, gY, pY.x, tw)), promote3(load3<R, 1, TBC>(table, g, gZ, pZ.x, tw)), uz);
-            temp += retrace_plq3(uy, promote3(load3<R, 3, TBC>(table, g, gY, pY.x, tw)), promote3(load3<R, 1, TBC>(table, g, gT, pT.x, tw)), ut);
-            temp += retrace_plq3(uz, promote3(load3<R, 3, TBC>(table, g, gZ, pZ.x, tw)), promote3(load3<R, 2, TBC>(table, g, gT, pT.x, tw)), ut);
+            spat  = retrace_plq3_r2(ux, promote3(load3<R, 1, TBC>(table, g, gX, pX.x, tw)), promote3(load3<R, 0, TBC>(table, g, gY, pY.x, tw)), uy);
+            spat += retrace_plq3_r2(ux, promote3(load3<R, 2, TBC>(table, g, gX, pX.x, tw)), promote3(load3<R, 0, TBC>(table, g, gZ, pZ.x, tw)), uz);
+            temp  = retrace_plq3_r2(ux, promote3(load3<R, 3, TBC>(table, g, gX, pX.x, tw)), promote3(load3<R, 0, TBC>(table, g, gT, pT.x, tw)), ut);
+            spat += retrace_plq3_r2(uy, promote3(load3<R, 2, TBC>(table, g, gY, pY.x, tw)), promote3(load3<R, 1, TBC>(table, g, gZ, pZ.x, tw)), uz);
+            temp += retrace_plq3_r2(uy, promote3(load3<R, 3, TBC>(table, g, gY, pY.x, tw)), promote3(load3<R, 1, TBC>(table, g, gT, pT.x, tw)), ut);
+            temp += retrace_plq3_r2(uz, promote3(load3<R, 3, TBC>(table, g, gZ, pZ.x, tw)), promote3(load3<R, 2, TBC>(table, g, gT, pT.x, tw)), ut);
         } else {
             V4<double> ux = promote2(load2<R, 0, TBC>(table, g, gid, p.x, tw));
             V4<double> uy = promote2(load2<R, 1, TBC>(table, g, gid, p.x, tw));
