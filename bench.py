@@ -160,7 +160,7 @@ def reference_main(args):
 
 
 # ---------------------------------------------------------------------------------------------- native arm
-def build_model(dims, fused=True, device=0, group=None, precision=None, phi=0.0, or_steps=0):
+def build_model(dims, fused=True, device=0, group=None, precision=None, phi=0.0, or_steps=0, hot=False):
     from qcdgpu_b200 import Model
     m = Model()
     m.desired_device = device
@@ -171,7 +171,7 @@ def build_model(dims, fused=True, device=0, group=None, precision=None, phi=0.0,
     m.or_steps = or_steps
     if m.lattice_group == 2 and group is not None:
         m.BETA = 2.5
-    m.ints = WORKLOAD["ints"]
+    m.ints = 0 if hot else WORKLOAD["ints"]
     if not (m.lattice_group == 2 and group is not None):
         m.BETA = WORKLOAD["beta"]
     m.NHIT = WORKLOAD["nhit"]
@@ -188,8 +188,8 @@ def build_model(dims, fused=True, device=0, group=None, precision=None, phi=0.0,
 def native_single(args):
     import numpy as np
     dims = tuple(int(x) for x in args.dims.split("x")) if args.dims else WORKLOAD["dims"]
-    m = build_model(dims, fused=not args.buffered, group=args.group, precision=args.precision, phi=args.phi, or_steps=args.or_steps)
-    diag = args.group is not None or args.precision is not None or args.phi != 0.0 or args.or_steps != 0
+    m = build_model(dims, fused=not args.buffered, group=args.group, precision=args.precision, phi=args.phi, or_steps=args.or_steps, hot=args.hot)
+    diag = args.group is not None or args.precision is not None or args.phi != 0.0 or args.or_steps != 0 or args.hot
     g = m.GPU0
     if args.materialize:
         g.set_fused_prng(False)      # PRNG_instances == PRNGSTEP, but every produce() writes the PRN buffer
@@ -256,7 +256,7 @@ def native_single(args):
         "scaling": "weak", "vs_baseline": None, "dtype": "f64" if m.precision == 1 else "f32", "data": "synthetic",
         "config": (workload_config(1, dims) if not diag and not args.buffered and not args.materialize else
                    {"workload": f"DIAGNOSTIC: SU({m.lattice_group}) {'x'.join(map(str, dims))} {'fp64' if m.precision == 1 else 'fp32'} heat-bath sweeps (8 passes + reunitarisation), beta={m.BETA}, "
-                                f"NHIT=10, RANLUX3 ({'fused in-register' if not args.buffered else 'buffered'}), cold start" + (f", {args.or_steps} overrelaxation sweeps after each heat-bath sweep" if args.or_steps else ""),
+                                f"NHIT=10, RANLUX3 ({'fused in-register' if not args.buffered else 'buffered'}), {'hot' if args.hot else 'cold'} start" + (f", {args.or_steps} overrelaxation sweeps after each heat-bath sweep" if args.or_steps else ""),
                     "l2_policy": (f"inputs_larger_than_L2 (link table {4 * V * link_bytes / 1e9:.2f} GB vs 126 MB L2)" if 4 * V * link_bytes > 126e6
                                   else f"diagnostic configuration: link table {4 * V * link_bytes / 1e6:.1f} MB fits the L2, no flush")}),
         "details": {"sweeps_per_s": args.steps / (ms * 1e-3), "plaquette_after_run": plq_total, "update_kernel_registers": regs,
@@ -351,6 +351,7 @@ def main():
     ap.add_argument("--precision", type=int, default=None, help="diagnostic: 0 single, 1 double, 2 mixed")
     ap.add_argument("--phi", type=float, default=0.0, help="diagnostic: twist angle (turns -D TBC on)")
     ap.add_argument("--materialize", action="store_true", help="one generator per update thread, PRN buffer written (diagnostic)")
+    ap.add_argument("--hot", action="store_true", help="diagnostic: hot start (INTS=0: every link random) instead of the cold start of the BASELINE workload")
     ap.add_argument("--or-steps", type=int, default=0, help="diagnostic (BASELINE config 2): overrelaxation sweeps after each heat-bath sweep")
     ap.add_argument("--on", action="store_true", help="diagnostic: the O(N) scalar branch (BASELINE config 4) instead of the gauge sweep")
     ap.add_argument("--no-acc", action="store_true", help="diagnostic (--on): without the -D ACC_RATE acceptance sums")
