@@ -118,10 +118,26 @@ struct PrnSmemT {
     __device__ __forceinline__ F4 peek() const { return get(k); }
     __device__ __forceinline__ void burn() { k++; }
     __device__ __forceinline__ void finish() {}
+    // parked sample i WITHOUT a branch (selects); a caller that is past the parked samples discards the value (cm_round_pipelined)
+    __device__ __forceinline__ F4 get_parked(uint32_t i) const {
+        i = min(i, keep - 1u);
+        const uint4 r = p[i * stride];
+        const bool cv = ((converted >> i) & 1ull) != 0ull;
+        const float c = 2.3283064365386963e-10f;
+        F4 o;
+        o.x = cv ? __uint_as_float(r.x) : __uint2float_rn(r.x) * c;
+        o.y = cv ? __uint_as_float(r.y) : __uint2float_rn(r.y) * c;
+        o.z = cv ? __uint_as_float(r.z) : __uint2float_rn(r.z) * c;
+        o.w = cv ? __uint_as_float(r.w) : __uint2float_rn(r.w) * c;
+        return o;
+    }
     static constexpr bool kGid = false;
     static constexpr bool kCanPeek = true;
+    static constexpr bool kParked = true;
     static constexpr int kMinBlocks = 3;
 };
+template <class P, class = void> struct HasParked { static constexpr bool value = false; };
+template <class P> struct HasParked<P, decltype((void)P::kParked)> { static constexpr bool value = P::kParked; };
 template <class Gen, int WORDS>
 struct PrnSmallState {   // XOR128 (4 words), PM (4 words), MRG32k3a (2 x uint4 rows)
     struct Args { uint32_t* table; uint32_t instances; uint32_t samples; };
@@ -317,8 +333,22 @@ template <typename R> __device__ __forceinline__ V4<R> kp_compose(R delta, const
     c.w = sinal * d.sinth * d.cosphi;
     return su2_mul(c, aH);
 }
+// The lattice-independent part of a Kennedy-Pendleton trial with sample r, and of the direction with sample r2:
+// E = -(log(1 - r.x) + cos^2(2 pi r.y) log(1 - r.z)) (delta = E / (beta sqrt(det))), r.w^2, and the point on the sphere.
+template <typename R> struct KpTrial { R E, w2; KpDir<R> D; };
+template <typename R> __device__ __forceinline__ KpTrial<R> kp_trial_eval(const F4& r, const F4& r2) {
+    KpTrial<R> t;
+    R c = Mth<R>::cos2pi(R(r.y));
+    R l1 = Mth<R>::log_(R(1) - R(r.x)), l2 = Mth<R>::log_(R(1) - R(r.z));
+    t.D = kp_direction<R>(R(r2.x), R(r2.y));
+    t.E = -(l1 + c * c * l2);
+    t.w2 = R(r.w) * R(r.w);
+    return t;
+}
+// nhit: trials allowed (default: the run's NHIT)
 template <typename R, class Prn>
-__device__ __forceinline__ bool kp_heatbath(Prn& prn, const Geom& g, const V4<R>& aH, R ibdet, V4<R>& out) {
+__device__ __forceinline__ bool kp_heatbath(Prn& prn, const Geom& g, const V4<R>& aH, R ibdet, V4<R>& out, uint32_t nhit = 0xffffffffu) {
+    if (nhit == 0xffffffffu) nhit = g.nhit;
     if constexpr (Prn::kGid) {
         double r[4];
         prn.trial_d(r);
@@ -331,24 +361,22 @@ __device__ __forceinline__ bool kp_heatbath(Prn& prn, const Geom& g, const V4<R>
         // The slot after a trial is the direction sample if the trial is accepted and the next trial if not:
         // evaluate both roles together (five independent transcendental chains instead of one after the other).
         F4 r = prn.trial();
-        for (uint32_t i = 0; i < g.nhit; i++) {
+        for (uint32_t i = 0; i < nhit; i++) {
             F4 r2 = prn.peek();
-            R c = Mth<R>::cos2pi(R(r.y));
-            R l1 = Mth<R>::log_(R(1) - R(r.x)), l2 = Mth<R>::log_(R(1) - R(r.z));
-            KpDir<R> d = kp_direction<R>(R(r2.x), R(r2.y));
-            R delta = -(l1 + c * c * l2) * ibdet;
-            if (R(r.w) * R(r.w) <= R(1) - R(0.5) * delta) {
+            const KpTrial<R> t = kp_trial_eval<R>(r, r2);
+            R delta = t.E * ibdet;
+            if (t.w2 <= R(1) - R(0.5) * delta) {
                 prn.burn();                        // the peeked slot is consumed as the direction sample
-                out = kp_compose(delta, d, aH);
+                out = kp_compose(delta, t.D, aH);
                 return true;
             }
-            if (i + 1 < g.nhit) r = prn.trial();   // the peeked slot becomes the next trial
+            if (i + 1 < nhit) r = prn.trial();   // the peeked slot becomes the next trial
         }
         return false;
     } else {
         bool flag = false;
         R delta = R(0);
-        for (uint32_t i = 0; i < g.nhit && !flag; i++) {
+        for (uint32_t i = 0; i < nhit && !flag; i++) {
             F4 r = prn.trial();
             R c = Mth<R>::cos2pi(R(r.y));
             delta = -(Mth<R>::log_(R(1) - R(r.x)) + c * c * Mth<R>::log_(R(1) - R(r.z))) * ibdet;
@@ -786,6 +814,68 @@ __device__ __forceinline__ void cm_round(M3<R>& U, M3<R>& W, const Geom& g, R be
         }
     }
 }
+// One Cabibbo-Marinari round, software-pipelined over the three subgroups (samples parked in shared memory, PrnSmemT).  The
+// transcendental part of a Kennedy-Pendleton trial depends on the random numbers only, not on the lattice: the first trial of subgroup
+// s + 1 is evaluated in the same basic block as the composition of subgroup s's update, so two dependency chains run interleaved where
+// cm_round runs them one after the other (the section is a chain of dependent FP64 operations at three warps per scheduler: its depth
+// is its cost).  A first trial that is rejected (5 % of the lanes at beta = 6), or samples beyond the parked ones, continue in the
+// general code.  Same functions on the same values as cm_round: the lattices stay bit-identical to the other kernels'.
+// MEASURED, NOT SHIPPED (build with QCD_NVCC_EXTRA=-DQCD_CM_PIPELINE=1): the Cabibbo-Marinari section's share of the warps' life time
+// falls from 49 % to 17 %, but the pass takes 3.97 instead of 3.32 ms -- `no_instruction` stalls rise from 13 % to 30 % of all samples,
+// in every phase, the generator's small loop included.  The kernel executes ~7.6 k mostly straight-line instructions per warp (~34 B of
+// instruction fetch per clock and SM): warps that get through their straight-line code faster starve the others of instructions.
+#ifndef QCD_CM_PIPELINE
+#define QCD_CM_PIPELINE 0
+#endif
+template <typename R, int NSKIP>
+__device__ __forceinline__ void cm_round_pipelined(M3<R>& U, M3<R>& W, const Geom& g, R beta, PrnSmemT<NSKIP>& prn) {
+    typedef PrnSmemT<NSKIP> Prn;
+    if (g.nhit == 0u) { cm_round<R, Prn>(U, W, g, beta, prn); return; }
+    const R ibeta = InvBeta<R>::get();
+    uint32_t k = prn.k;
+    const uint32_t last = (prn.keep >= 2u) ? prn.keep - 2u : 0u;          // k <= last: samples k and k + 1 are parked
+    bool parked = prn.keep >= 2u && k <= last;
+    KpTrial<R> T = kp_trial_eval<R>(prn.get_parked(k), prn.get_parked(k + 1u));
+#pragma unroll 1
+    for (int sub = 0; sub < 3; sub++) {
+        R idet;
+        V4<R> aH;
+        switch (sub) {
+            case 0: aH = block_dagger_inv<R, 0, 1>(W, idet); break;
+            case 1: aH = block_dagger_inv<R, 0, 2>(W, idet); break;
+            default: aH = block_dagger_inv<R, 1, 2>(W, idet); break;
+        }
+        const R ibdet = idet * ibeta;
+        const R delta = T.E * ibdet;
+        const bool fast = parked && (T.w2 <= R(1) - R(0.5) * delta);
+        V4<R> d = { R(1), R(0), R(0), R(0) };      // the identity leaves U and W as they are (NHIT rejections, su3_update_cl.cl:665-668)
+        if (!fast) {
+            // parked: sample k was the rejected first trial, trials 2 .. NHIT follow from sample k + 1 on; otherwise (samples beyond
+            // the parked ones) the whole step by the general code
+            const uint32_t tries = parked ? g.nhit - 1u : g.nhit;
+            prn.k = parked ? k + 1u : k;
+            const bool ok = tries > 0u && kp_heatbath<R, Prn>(prn, g, aH, ibdet, d, tries);
+            if (!ok) { prn.burn(); d = { R(1), R(0), R(0), R(0) }; }
+            k = prn.k;
+        } else {
+            k += 2u;
+        }
+        // first trial of the next subgroup together with the composition of this one: independent chains in one basic block
+        KpTrial<R> Tn = T;
+        if (sub < 2) {
+            parked = prn.keep >= 2u && k <= last;
+            Tn = kp_trial_eval<R>(prn.get_parked(k), prn.get_parked(k + 1u));
+        }
+        if (fast) d = kp_compose(delta, T.D, aH);
+        switch (sub) {
+            case 0: rotate_rows<R, 0, 1>(U, d); rotate_rows_sel<R, 0, 1, 7, 6>(W, d); break;
+            case 1: rotate_rows<R, 0, 2>(U, d); rotate_rows_sel<R, 0, 2, 0, 6>(W, d); break;
+            default: rotate_rows_sel<R, 1, 2, 7, 0>(U, d); break;
+        }
+        T = Tn;
+    }
+    prn.k = k;
+}
 template <typename R, int A, int B>
 __device__ __forceinline__ void or_subgroup(M3<R>& U, M3<R>& W) {
     R det;
@@ -868,6 +958,7 @@ template <typename R, int MU, bool TBC, bool WS = false> struct Su3StageTma {
     const void* tmap1;          // same tensor, box = 1 site x 3 planes
     const R* table;
     uint32_t gindex, px, lane;
+    Coord pc;                   // the site (plane loop: the sites of a plane's links are formed when the plane comes up)
     PlaneSites s0, s1, s2;
 
     // link L of the site's read sequence (same order as Su3Stage): site and direction
@@ -887,35 +978,37 @@ template <typename R, int MU, bool TBC, bool WS = false> struct Su3StageTma {
         const int i = L % 6, NU = plane_nu<MU>(L / 6);
         return (i == 1) ? false : (i == 2) ? (MU == 1) : (i == 3) ? (MU == 1 || NU == 1) : (NU == 1);
     }
+    // One link into ring slot SLOT: the three planes of direction `dir` of the 32 sites of this warp's row, box start = lane 0's site.
+    // MW: 0 = the link's site is never a y +- 1 neighbour that wraps around, 1 = it may be, 2 = it may be if mw_rt (plane loop: NU == 1).
     // dep: a word (always 0) whose computation needed the loaded data of every lane that read the slot being refilled
-    template <int L> __device__ __forceinline__ void issue(uint32_t dep = 0u) const {
-        if constexpr (L <= 18) {
-            constexpr int SLOT = L % kTmaK, DIR = link_dir<L>();
-            uint32_t gidb = 0, wrapped = 0;
-            int start = int(link_gid<L>());     // box start = "site of lane 0" of the unwrapped row
-            if constexpr (may_wrap<L>()) {      // the first or the last lane of a row may wrap: lane 1 never does, it is the reference;
-                const int gid = start;          // the wrapped lane's site comes through a box of its own
-                start = __shfl_sync(0xffffffffu, gid, 1) - 2;
-                const uint32_t bad = __ballot_sync(0xffffffffu, gid != start + 2 * int(lane));
-                wrapped = bad;
-                gidb = uint32_t(__shfl_sync(0xffffffffu, gid, bad ? (__ffs(int(bad)) - 1) : 0));
-            }
-            if (lane == 0) {
-                const int gid0 = start + int(dep);
-                const uint32_t b = bar + 8u * SLOT, d = buf + SLOT * tma_slot_bytes<R>();
-                const uint32_t bytes = tma_slot_bytes<R>() + (wrapped ? 3u * uint32_t(sizeof(V4<R>)) : 0u);
-                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(b), "r"(bytes) : "memory");
-                // one box per link: planes DIR, DIR + 4, DIR + 8 through the traversal stride of the plane dimension
-                asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
-                             :: "r"(d), "l"(tmap), "r"(0), "r"(gid0), "r"(DIR), "r"(b) : "memory");
-                if (wrapped)
-                    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
-                                 :: "r"(xbuf + 128u * SLOT), "l"(tmap1), "r"(0), "r"(int(gidb)), "r"(DIR), "r"(b) : "memory");
-            }
-#if QCD_TMA_SYNC_AFTER_ISSUE
-            __syncwarp();
-#endif
+    template <int SLOT, int MW> __device__ __forceinline__ void issue_link(uint32_t gid_, int dir, bool mw_rt, uint32_t dep) const {
+        uint32_t gidb = 0, wrapped = 0;
+        int start = int(gid_);              // box start = "site of lane 0" of the unwrapped row
+        if (MW == 1 || (MW == 2 && mw_rt)) {    // the first or the last lane of a row may wrap: lane 1 never does, it is the reference;
+            const int gid = start;          // the wrapped lane's site comes through a box of its own
+            start = __shfl_sync(0xffffffffu, gid, 1) - 2;
+            const uint32_t bad = __ballot_sync(0xffffffffu, gid != start + 2 * int(lane));
+            wrapped = bad;
+            gidb = uint32_t(__shfl_sync(0xffffffffu, gid, bad ? (__ffs(int(bad)) - 1) : 0));
         }
+        if (lane == 0) {
+            const int gid0 = start + int(dep);
+            const uint32_t b = bar + 8u * SLOT, d = buf + SLOT * tma_slot_bytes<R>();
+            const uint32_t bytes = tma_slot_bytes<R>() + (wrapped ? 3u * uint32_t(sizeof(V4<R>)) : 0u);
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(b), "r"(bytes) : "memory");
+            // one box per link: planes dir, dir + 4, dir + 8 through the traversal stride of the plane dimension
+            asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                         :: "r"(d), "l"(tmap), "r"(0), "r"(gid0), "r"(dir), "r"(b) : "memory");
+            if (wrapped)
+                asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                             :: "r"(xbuf + 128u * SLOT), "l"(tmap1), "r"(0), "r"(int(gidb)), "r"(dir), "r"(b) : "memory");
+        }
+#if QCD_TMA_SYNC_AFTER_ISSUE
+        __syncwarp();
+#endif
+    }
+    template <int L> __device__ __forceinline__ void issue(uint32_t dep = 0u) const {
+        if constexpr (L <= 18) issue_link<L % kTmaK, may_wrap<L>() ? 1 : 0>(link_gid<L>(), link_dir<L>(), false, dep);
     }
     // lane 0: pull the three boxes of link L towards the L2 (one instruction per KB instead of one prefetch per thread and sector)
     template <int L> __device__ __forceinline__ void prefetch_l2_link() const {
@@ -926,12 +1019,14 @@ template <typename R, int MU, bool TBC, bool WS = false> struct Su3StageTma {
     template <int L0, int L1> __device__ __forceinline__ void prefetch_l2_links() const {
         if constexpr (L0 < L1) { prefetch_l2_link<L0>(); prefetch_l2_links<L0 + 1, L1>(); }
     }
-    template <int L> __device__ __forceinline__ M3r2<R> take(const Geom& g, const Twist<R>& tw) const {
-        constexpr int SLOT = L % kTmaK, DIR = link_dir<L>();
-        const uint32_t gid = link_gid<L>();
-        const int start = may_wrap<L>() ? __shfl_sync(0xffffffffu, int(gid), 1) - 2 : 0;
+    // The link in ring slot SLOT (use number 2 n + PHASE of the slot): wait for its box, read this lane's three vec4, unpack, twist.
+    // `dep` comes back as the (always zero) word that orders the slot's refill behind the reads (see below).
+    template <int SLOT, int PHASE, int MW>
+    __device__ __forceinline__ M3r2<R> take_link(const Geom& g, const Twist<R>& tw, uint32_t gid, int dir, uint32_t x, bool mw_rt, uint32_t& dep) const {
+        const bool mw = MW == 1 || (MW == 2 && mw_rt);
+        const int start = mw ? __shfl_sync(0xffffffffu, int(gid), 1) - 2 : 0;
         {
-            const uint32_t b = bar + 8u * SLOT, phase = ((L / kTmaK) & 1) ^ (WS ? ((ring_par >> SLOT) & 1u) : 0u);
+            const uint32_t b = bar + 8u * SLOT, phase = uint32_t(PHASE) ^ (WS ? ((ring_par >> SLOT) & 1u) : 0u);
             uint32_t done = 0;
             while (!done)
                 asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
@@ -940,7 +1035,7 @@ template <typename R, int MU, bool TBC, bool WS = false> struct Su3StageTma {
         V4<R> v[3];
         // this lane's vec4 of plane k: in the link slot, or (the row's wrapped-around y neighbour) in the one-site slot
         uint32_t a = buf + SLOT * tma_slot_bytes<R>() + lane * uint32_t(sizeof(V4<R>)), step = tma_plane_bytes<R>();
-        if constexpr (may_wrap<L>()) {
+        if (mw) {
             if (int(gid) != start + 2 * int(lane)) { a = xbuf + 128u * SLOT; step = uint32_t(sizeof(V4<R>)); }
         }
 #pragma unroll
@@ -953,11 +1048,8 @@ template <typename R, int MU, bool TBC, bool WS = false> struct Su3StageTma {
             }
         }
         M3r2<R> m = unpack3(v[0], v[1], v[2]);
-        if constexpr (TBC && DIR == 1) {
-            constexpr int pl = (L < 18) ? L / 6 : 0, i = L % 6;
-            const PlaneSites& s = (pl == 0) ? s0 : (pl == 1) ? s1 : s2;
-            const uint32_t x = (L == 18 || i == 1) ? px : (i == 0) ? s.x_pnu : (i == 2) ? s.x_pmu : (i == 3) ? s.x_pmnmu : s.x_pmn;
-            twist3(m, g, x, tw);
+        if (TBC) {
+            if (dir == 1) twist3(m, g, x, tw);
         }
         // The slot can be refilled once every lane's reads have RETURNED (the refill is a write through the async proxy: issuing it
         // right behind the reads let a whole warp see a half-refilled slot about once in 10^6 updates).  A vote over a word taken
@@ -969,14 +1061,22 @@ template <typename R, int MU, bool TBC, bool WS = false> struct Su3StageTma {
                              __double2hiint(v[2].x) | __double2hiint(v[2].z));
         else
             probe = __float_as_uint(float(v[0].x)) | __float_as_uint(float(v[1].x)) | __float_as_uint(float(v[2].x));
-        uint32_t dep = __ballot_sync(0xffffffffu, probe == 0x7ff5a5a5u);
+        dep = __ballot_sync(0xffffffffu, probe == 0x7ff5a5a5u);
         asm volatile("and.b32 %0, %0, 0;" : "+r"(dep));
+        return m;
+    }
+    template <int L> __device__ __forceinline__ M3r2<R> take(const Geom& g, const Twist<R>& tw) const {
+        constexpr int pl = (L < 18) ? L / 6 : 0, i = L % 6;
+        const PlaneSites& s = (pl == 0) ? s0 : (pl == 1) ? s1 : s2;
+        const uint32_t x = (L == 18 || i == 1) ? px : (i == 0) ? s.x_pnu : (i == 2) ? s.x_pmu : (i == 3) ? s.x_pmnmu : s.x_pmn;
+        uint32_t dep;
+        M3r2<R> m = take_link<L % kTmaK, (L / kTmaK) & 1, may_wrap<L>() ? 1 : 0>(g, tw, link_gid<L>(), link_dir<L>(), x, false, dep);
         issue<L + kTmaK>(dep);
         return m;
     }
     // called by all 32 lanes of a full warp; smem_warp = this warp's ring, bars = this warp's kTmaK mbarriers
     __device__ __forceinline__ void begin(uint32_t smem_warp, uint32_t xslots, uint32_t bars, const void* tm, const void* tm1, const R* tab, const Geom& g, uint32_t gi, const Coord& p) {
-        buf = smem_warp; xbuf = xslots; bar = bars; tmap = tm; tmap1 = tm1; table = tab; gindex = gi; px = p.x; lane = threadIdx.x & 31u;
+        buf = smem_warp; xbuf = xslots; bar = bars; tmap = tm; tmap1 = tm1; table = tab; gindex = gi; px = p.x; pc = p; lane = threadIdx.x & 31u;
         Coord pmu = nb_plus<MU>(g, p);
         s0 = plane_sites<MU, PlaneOrder<MU>::n0>(g, p, pmu);
         s1 = plane_sites<MU, PlaneOrder<MU>::n1>(g, p, pmu);
@@ -1002,7 +1102,7 @@ template <typename R, int MU, bool TBC, bool WS = false> struct Su3StageTma {
         __syncwarp();
     }
     __device__ __forceinline__ void begin_item(const Geom& g, uint32_t gi, const Coord& p) {
-        gindex = gi; px = p.x;
+        gindex = gi; px = p.x; pc = p;
         Coord pmu = nb_plus<MU>(g, p);
         s0 = plane_sites<MU, PlaneOrder<MU>::n0>(g, p, pmu);
         s1 = plane_sites<MU, PlaneOrder<MU>::n1>(g, p, pmu);
@@ -1039,11 +1139,74 @@ template <typename R, int MU, bool TBC, bool WS = false> struct Su3StageTma {
             mul_dag_full_add(E, Cf, S);
         }
     }
+#ifndef QCD_PLANE_LOOP     // 1: the three planes as a run-time loop (a third of the staple code: 36 KB -> 13 KB of SASS).  Measured slower
+#define QCD_PLANE_LOOP 0   // (4.20 against 3.97 ms per pass with the pipelined Cabibbo-Marinari round): the run-time plane costs 870
+#endif                     // instructions per update (sites, wrap tests, copies, spill traffic) and the fetch stalls do not go away
+    __device__ __forceinline__ PlaneSites sites_rt(const Geom& g, int nu) const {
+        const Coord pmu = nb_plus<MU>(g, pc), pnu = nb_plus_rt(g, pc, nu), pmn = nb_minus_rt(g, pc, nu), pmnmu = nb_plus<MU>(g, pmn);
+        PlaneSites s;
+        s.g_pmu = coords_to_gid(g, pmu); s.g_pnu = coords_to_gid(g, pnu);
+        s.g_pmn = coords_to_gid(g, pmn); s.g_pmnmu = coords_to_gid(g, pmnmu);
+        s.x_pmu = pmu.x; s.x_pnu = pnu.x; s.x_pmn = pmn.x; s.x_pmnmu = pmnmu.x;
+        return s;
+    }
+    // Which links of a plane can sit on a wrapped y neighbour (may_wrap above with a run-time NU): 0 never, 1 yes, 2 if NU == 1
+    template <int I> __host__ __device__ static constexpr int mw_of() {
+        return (I == 1) ? 0 : (I == 2) ? (MU == 1 ? 1 : 0) : (I == 3) ? (MU == 1 ? 1 : 2) : (MU == 1 ? 0 : 2);
+    }
+    // The same 19 reads as plane<0..2> + take<18>, the planes as a run-time loop: link 6 pl + i uses ring slot i % 3 in its use number
+    // 2 pl + i / 3, so slot and mbarrier phase do not depend on the plane; only the sites and the direction NU do.  Bit-identical
+    // to the unrolled planes (experiment, see QCD_PLANE_LOOP).
+    __device__ __forceinline__ void staple_and_link_loop(const Geom& g, const Twist<R>& tw, M3<R>& S, M3r2<R>& m0) const {
+        PlaneSites cur = s0;
+#pragma unroll 1
+        for (int pl = 0; pl < 3; pl++) {
+            const int nu = (pl == 0) ? PlaneOrder<MU>::n0 : (pl == 1) ? PlaneOrder<MU>::n1 : PlaneOrder<MU>::n2;
+            const int nun = (pl == 0) ? PlaneOrder<MU>::n1 : PlaneOrder<MU>::n2;
+            const bool mw = nu == 1, mwn = nun == 1, lastp = pl == 2;
+            PlaneSites nxt = cur;
+            if (!lastp) nxt = sites_rt(g, nun);
+            uint32_t dep;
+            __syncwarp();
+            {   // forward: A B^+ C^+ = A (C B)^+
+                M3r2<R> B = take_link<0, 0, mw_of<0>()>(g, tw, cur.g_pnu, MU, cur.x_pnu, mw, dep);
+                issue_link<0, mw_of<3>()>(cur.g_pmnmu, nu, mw, dep);
+                M3<R> Bf = complete(B), D;
+                M3r2<R> C = take_link<1, 0, 0>(g, tw, gindex, nu, px, false, dep);
+                issue_link<1, mw_of<4>()>(cur.g_pmn, MU, mw, dep);
+                mul_r2_full(C, Bf, D);
+                M3r2<R> A = take_link<2, 0, mw_of<2>()>(g, tw, cur.g_pmu, nu, cur.x_pmu, mw, dep);
+                issue_link<2, mw_of<5>()>(cur.g_pmn, nu, mw, dep);
+                if (pl == 0) { M3<R> F; mul_r2_dag(A, D, F); S = F; } else mul_r2_dag_add(A, D, S);
+            }
+            {   // backward: A2^+ B2^+ C2 = (B2 A2)^+ C2
+                M3r2<R> A2 = take_link<0, 1, mw_of<3>()>(g, tw, cur.g_pmnmu, nu, cur.x_pmnmu, mw, dep);
+                if (!lastp) issue_link<0, mw_of<0>()>(nxt.g_pnu, MU, mwn, dep);
+                else        issue_link<0, 0>(gindex, MU, false, dep);                  // the site's own link (read 18)
+                M3<R> Af = complete(A2), E;
+                M3r2<R> B2 = take_link<1, 1, mw_of<4>()>(g, tw, cur.g_pmn, MU, cur.x_pmn, mw, dep);
+                if (!lastp) issue_link<1, 0>(gindex, nun, false, dep);
+                mul_r2_full(B2, Af, E);
+                M3r2<R> C2 = take_link<2, 1, mw_of<5>()>(g, tw, cur.g_pmn, nu, cur.x_pmn, mw, dep);
+                if (!lastp) issue_link<2, mw_of<2>()>(nxt.g_pmu, nun, mwn, dep);
+                M3<R> Cf = complete(C2);
+                mul_dag_full_add(E, Cf, S);
+            }
+            cur = nxt;
+        }
+        uint32_t dep;
+        m0 = take_link<0, 0, 0>(g, tw, gindex, MU, px, false, dep);
+    }
     __device__ __forceinline__ void staple_and_link(const Geom& g, const Twist<R>& tw, M3<R>& S, M3r2<R>& m0) const {
+#if QCD_PLANE_LOOP
+        static_assert(kTmaK == 3, "the plane loop is written for a ring of three slots");
+        staple_and_link_loop(g, tw, S, m0);
+#else
         plane<0>(g, tw, S);
         plane<1>(g, tw, S);
         plane<2>(g, tw, S);
         m0 = take<18>(g, tw);
+#endif
     }
 };
 // same with the links arriving through the shared-memory ring (begin() was called earlier)
@@ -1064,6 +1227,10 @@ __device__ __forceinline__ void heatbath_su3(R* table, const Geom& g, R beta, ui
     for (uint32_t h = 0; h < g.nhitpar; h++) {
         third_row(U.e[0], U.e[1], U.e[2]);
         M3<R> W = mul_full(U, S);
+#if QCD_CM_PIPELINE
+        if constexpr (HasParked<Prn>::value) cm_round_pipelined(U, W, g, beta, prn);
+        else
+#endif
         cm_round<R, Prn>(U, W, g, beta, prn);
         gram_schmidt3(U.e[0], U.e[1]);
     }
