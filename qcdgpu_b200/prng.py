@@ -87,7 +87,7 @@ class PRNG:
         seeds[1:] = host_rand_fill(I - 1)              # the other instances: rand() (random.cpp:464-465)
         self.seeds = seeds
         gpu.program_create(None, f"-D RL_skip={self.RL_nskip}")
-        seed_table_size = I * 7                       # float4 x 7 per instance (112 B; 26 words are used)
+        seed_table_size = I * 7                       # float4 x 7 per instance (112 B; 20 words are used: the packed generator, prng.cuh)
         randoms_size = I * self.PRNG_samples
         self.PRNG_seed_id = gpu.buffer_init(GPU.buffer_type_Constant, I, seeds, 4)
         self.PRNG_seed_table_id = gpu.buffer_init(GPU.buffer_type_IO, seed_table_size, None, 16)

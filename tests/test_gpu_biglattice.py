@@ -100,6 +100,27 @@ def test_tma_staged_links_in_slabs():
         np.testing.assert_array_equal(a.view(np.uint8), b.view(np.uint8))
 
 
+def test_two_devices_in_one_process_n2_64():
+    """Several parts in ONE process on different GPUs (devices=[0, 1], P2P halo copies), N2 = 64: every device launches the kernels
+    that need more than 48 KB of dynamic shared memory (TMA-staged update, 63 KB), and the opt-in is per device
+    (update_inst.cu, ensure_smem).  Same links as with both parts on device 0."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
+    from qcdgpu_b200.biglattice import BigLattice
+    tables = []
+    for devices in ([0, 0], [0, 1], [1, 0]):
+        B = BigLattice((8, 64, 2, 2), 2, configure=_configure(3, 5.7, 0, 3, fused=True), devices=devices)
+        B.overlap = True
+        B.lattice_init()
+        B.lattice_simulate()
+        tables.append([p.table_numpy() for p in B.parts.values()])
+        B.close()
+    for t in tables[1:]:
+        for a, b in zip(tables[0], t):
+            np.testing.assert_array_equal(a.view(np.uint8), b.view(np.uint8))
+
+
 def test_partitioned_ensemble_agrees():
     """With PRNGs the parts use their own series: plaquette after thermalisation agrees statistically with the
     reference's CPU_RUN series (8^4, beta = 6)."""

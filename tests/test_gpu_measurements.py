@@ -156,3 +156,30 @@ def test_fmunu_matches_numpy(sun, dims, mode, g1, g2, phi):
                         axis1=-2, axis2=-1).real.sum() for a, b in [(0, 1), (0, 2), (1, 2)]) / (V * 3)
     assert rel(A["Plq_spat"]["data"][last], spat, 1e-11)
     m.close()
+
+
+def test_measurement_kernels_write_every_slot_their_reducer_sums():
+    """The host sizes the reducer from its own aligned grid (ceil(row size / work-group size), like the reference), which on a small
+    lattice is more slots than the sites fill (4^4: 8 against 2).  The measurement kernels must write the surplus slots too (zeros):
+    with the partial buffer full of garbage and no clear_measurement in front -- lattice_measurement has none in the run loop --
+    action and plaquette must come out as on a clean buffer."""
+    m = make_model(3, (4, 4, 4, 4), PL_level=0)
+    m.lattice_start()
+    g = m.GPU0
+    m._measure()
+    m.ITER_counter += 1
+    clean = (g.buffer_map(m.lattice_energies, np.float64).copy(), g.buffer_map(m.lattice_energies_plq, np.float64).copy())
+    junk = np.full(g.buffer_map(m.lattice_measurement, np.float64).shape, 1.0e30)
+    m.ITER_counter -= 1
+    g.buffer_write_from(m.lattice_measurement, junk)
+    g.kernel_run(m.sun_measurement_id)
+    g.kernel_init_constant_reset(m.sun_measurement_reduce_id, m.ITER_counter, m.argument_measurement_index)
+    g.kernel_run(m.sun_measurement_reduce_id)
+    g.buffer_write_from(m.lattice_measurement, junk)
+    g.kernel_run(m.sun_measurement_plq_id)
+    g.kernel_init_constant_reset(m.sun_measurement_plq_reduce_id, m.ITER_counter, m.argument_plq_index)
+    g.kernel_run(m.sun_measurement_plq_reduce_id)
+    got = (g.buffer_map(m.lattice_energies, np.float64).copy(), g.buffer_map(m.lattice_energies_plq, np.float64).copy())
+    for a, b in zip(clean, got):
+        np.testing.assert_array_equal(a, b)
+    m.close()

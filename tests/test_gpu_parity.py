@@ -399,6 +399,31 @@ def test_warp_specialised_kernel_is_bit_exact(env, dims, prec, phi, beta):
     assert r.returncode == 0 and "IDENTICAL" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
 
 
+def test_generator_state_written_by_the_host_reaches_both_tables():
+    """The two-phase kernel keeps TWO generator state tables and swaps them after each pass, writing the second one only for the
+    instances its update threads cover.  A state table written from the host (restore, re-seed) must therefore reach both, or the
+    padding instances above SITES/2 expose the old state after the next swap (backend.cu, resync_twin).  Run a fused sweep (the twin
+    exists), restore the state saved before it, run the sweep again: same lattice and the same next numbers for EVERY instance."""
+    m = make_model(3, (4, 4, 4, 6), 1, ints=0, prng="RANLUX3", fused=True, iters=2, beta=6.0)
+    m.lattice_start()
+    g, P = m.GPU0, m.PRNG0
+    m.lattice_sweep()                                   # creates the twin table
+    state = g.buffer_map(P.PRNG_seed_table_id, np.uint8).copy() if hasattr(P, "PRNG_seed_table_id") else None
+    if state is None:
+        pytest.skip("seed table id not exposed by the Python mirror")
+    table0 = m.table_numpy().copy()
+    outs = []
+    for _ in range(2):
+        g.buffer_write_from(m.lattice_table, table0)
+        g.buffer_write_from(P.PRNG_seed_table_id, state)
+        m.lattice_sweep()
+        P.produce()
+        outs.append((m.table_numpy().copy(), P.randoms().copy()))
+    np.testing.assert_array_equal(outs[0][0].view(np.uint8), outs[1][0].view(np.uint8))
+    np.testing.assert_array_equal(outs[0][1].view(np.uint8), outs[1][1].view(np.uint8))
+    m.close()
+
+
 # ---------------------------------------------------------------------------------- folded reunitarisation
 @pytest.mark.parametrize("dims,prec,gen", [((4, 4, 4, 8), 1, "RANLUX3"), ((2, 64, 2, 4), 1, "RANLUX3"), ((4, 4, 4, 4), 0, "XOR128")])
 def test_folded_reunitarisation(dims, prec, gen):
