@@ -67,6 +67,10 @@ void  qgpu_set_limit_max_workgroup_size(qgpu* h, unsigned limit);
 void  qgpu_set_max_memory_width(qgpu* h, size_t width);
 /* GPU_debug.profiling / brief_report / show_stage (clinterface.h:102-109) */
 void  qgpu_set_debug(qgpu* h, int profiling, int brief_report, int show_stage);
+/* profiling = 2 ("timeline", not in the reference): kernel_run records an event pair per launch WITHOUT waiting; qgpu_profile_collect
+ * waits for them and adds the times to the per-kernel statistics read by qgpu_kernel_get_execution_time.  Gives a kernel's duration
+ * inside a run of back-to-back launches, where profiling = 1 (GPU_debug.profiling, clinterface.cpp:1251-1278) waits after every launch. */
+int   qgpu_profile_collect(qgpu* h);
 /* 0 (default, reference behaviour OpenCL_Check_Error clinterface.cpp:225-284): print and exit(-1) on any error.
  * 1: return a negative value and keep the message for qgpu_last_error(). */
 void        qgpu_set_error_mode(qgpu* h, int return_errors);

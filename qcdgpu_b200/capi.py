@@ -49,7 +49,7 @@ EXPORTS = [
     "qgpu_kernel_get_execution_time", "qgpu_buffer_init", "qgpu_buffer_write", "qgpu_buffer_map",
     "qgpu_buffer_map_range", "qgpu_buffer_unmap", "qgpu_buffer_kill", "qgpu_buffer_size_bytes",
     "qgpu_buffer_size_align", "qgpu_buffer_size_align_step", "qgpu_set_async", "qgpu_synchronize",
-    "qgpu_set_fused_prng", "qgpu_set_tile_x", "qgpu_set_fold_reunitarisation", "qgpu_set_stream", "qgpu_kernel_set_x_range", "qgpu_buffer_device_ptr", "qgpu_stream", "qgpu_timer_start",
+    "qgpu_set_fused_prng", "qgpu_set_tile_x", "qgpu_set_fold_reunitarisation", "qgpu_profile_collect", "qgpu_set_stream", "qgpu_kernel_set_x_range", "qgpu_buffer_device_ptr", "qgpu_stream", "qgpu_timer_start",
     "qgpu_timer_stop", "qgpu_launch_count", "qgpu_update_kernel_registers", "qgpu_halo_copy",
     "qgpu_halo_pack", "qgpu_halo_unpack", "qgpu_halo_bytes", "qgpu_host_srand", "qgpu_host_rand_fill",
 ]
@@ -122,6 +122,7 @@ def load(build_if_missing: bool = True):
     L.qgpu_set_fused_prng.argtypes = [vp, ci]
     L.qgpu_set_tile_x.argtypes = [vp, ci]
     L.qgpu_set_fold_reunitarisation.argtypes = [vp, ci]
+    L.qgpu_profile_collect.argtypes = [vp]
     L.qgpu_set_stream.argtypes = [vp, vp]
     L.qgpu_kernel_set_x_range.argtypes = [vp, ci, ci, ci]
     L.qgpu_buffer_device_ptr.argtypes = [vp, ci]
@@ -198,6 +199,10 @@ class GPU:
 
     def set_debug(self, profiling=False, brief_report=False, show_stage=False):
         self.L.qgpu_set_debug(self.h, int(profiling), int(brief_report), int(show_stage))
+
+    def profile_collect(self) -> int:
+        """profiling = 2: wait for the launches recorded so far and add their times to the kernels' statistics."""
+        return self._chk(self.L.qgpu_profile_collect(self.h), "profile_collect")
 
     # -- programs
     def program_create(self, source, options: str = "") -> int:

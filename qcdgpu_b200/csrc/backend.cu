@@ -111,6 +111,12 @@ struct qgpu {
     size_t max_memory_width = 0;
     qgpu_device_info info;
     bool profiling = false, brief = false, show_stage = false;
+    // profiling == 2 ("timeline"): an event pair per launch, recorded without waiting, read back by qgpu_profile_collect -- per-kernel
+    // times INSIDE a run of back-to-back launches (the one-by-one mode above waits after every launch and lets the board cool down)
+    int profiling_mode = 0;
+    struct TimedLaunch { int kid; cudaEvent_t e0, e1; };
+    std::vector<TimedLaunch> timeline;
+    std::vector<cudaEvent_t> event_pool;
     bool return_errors = false, async = false, fused = false;
     bool fold_gs = true;
     int tile_x = -1;
@@ -767,7 +773,23 @@ void qgpu_destroy(qgpu* h) {
 }
 void qgpu_set_limit_max_workgroup_size(qgpu* h, unsigned limit) { h->limit_wg = limit; }
 void qgpu_set_max_memory_width(qgpu* h, size_t w) { h->max_memory_width = w; if (h->initialized) h->info.max_memory_width = w; }
-void qgpu_set_debug(qgpu* h, int profiling, int brief, int stage) { h->profiling = profiling != 0; h->brief = brief != 0; h->show_stage = stage != 0; }
+void qgpu_set_debug(qgpu* h, int profiling, int brief, int stage) {
+    h->profiling = profiling == 1; h->profiling_mode = profiling; h->brief = brief != 0; h->show_stage = stage != 0;
+}
+// profiling == 2: wait for the recorded launches and add their times to the kernels' statistics (qgpu_kernel_get_execution_time)
+int qgpu_profile_collect(qgpu* h) {
+    if (!h->initialized) return 0;
+    CUDA_OK(h, cudaSetDevice(h->device));
+    for (auto& t : h->timeline) {
+        CUDA_OK(h, cudaEventSynchronize(t.e1));
+        float ms = 0; CUDA_OK(h, cudaEventElapsedTime(&ms, t.e0, t.e1));
+        if (valid_kernel(h, t.kid)) { Kernel& k = h->kernels[t.kid]; double ns = (double)ms * 1e6; k.t_sum += ns; k.t_sq += ns * ns; k.starts++; }
+        h->event_pool.push_back(t.e0); h->event_pool.push_back(t.e1);
+    }
+    int n = (int)h->timeline.size();
+    h->timeline.clear();
+    return n;
+}
 void qgpu_set_error_mode(qgpu* h, int r) { h->return_errors = r != 0; }
 const char* qgpu_last_error(qgpu* h) { return h->last_error.c_str(); }
 void qgpu_set_async(qgpu* h, int on) { h->async = on != 0; }
@@ -843,6 +865,9 @@ int qgpu_device_finalize(qgpu* h, int error_code) {
         h->buffers[i] = Buffer();
     }
     if (h->ws_counters) { cudaFree(h->ws_counters); h->ws_counters = nullptr; }
+    for (auto& t : h->timeline) { cudaEventDestroy(t.e0); cudaEventDestroy(t.e1); }
+    for (cudaEvent_t e : h->event_pool) cudaEventDestroy(e);
+    h->timeline.clear(); h->event_pool.clear();
     cudaEventDestroy(h->ev0); cudaEventDestroy(h->ev1); cudaEventDestroy(h->evp0); cudaEventDestroy(h->evp1); cudaEventDestroy(h->ev_halo);
     if (h->own_stream) cudaStreamDestroy(h->stream);
     h->stream = nullptr; h->own_stream = false; h->initialized = false;
@@ -933,7 +958,16 @@ int qgpu_kernel_run(qgpu* h, int kid) {
     if (!valid_kernel(h, kid)) return fail(h, "kernel_run: bad kernel id %d", kid);
     CUDA_OK(h, cudaSetDevice(h->device));
     if (h->profiling) CUDA_OK(h, cudaEventRecord(h->evp0, h->stream));
+    qgpu::TimedLaunch tl = { kid, nullptr, nullptr };
+    if (h->profiling_mode == 2) {
+        for (cudaEvent_t* e : { &tl.e0, &tl.e1 }) {
+            if (!h->event_pool.empty()) { *e = h->event_pool.back(); h->event_pool.pop_back(); }
+            else CUDA_OK(h, cudaEventCreate(e));
+        }
+        CUDA_OK(h, cudaEventRecord(tl.e0, h->stream));
+    }
     if (launch_kernel(h, kid) < 0) return -1;
+    if (tl.e1) { CUDA_OK(h, cudaEventRecord(tl.e1, h->stream)); h->timeline.push_back(tl); }
     if (h->profiling) {
         CUDA_OK(h, cudaEventRecord(h->evp1, h->stream));
         CUDA_OK(h, cudaEventSynchronize(h->evp1));
