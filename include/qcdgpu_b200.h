@@ -164,6 +164,13 @@ size_t qgpu_halo_bytes(qgpu* h, int program, int dir);
 /* host helpers: glibc srand()/rand() in bulk (seed tables are defined through them, random.cpp:235,462-465) */
 void  qgpu_host_srand(unsigned seed);
 void  qgpu_host_rand_fill(uint32_t* out, size_t n, uint32_t modulo, uint32_t add);
+/* RANLUX skip-ahead table (host arithmetic only; csrc/ranlux_jump_host.h).  The subtract-with-borrow recurrence of prngcl_ranlux.cl:97-563
+ * / random.cpp:504-574 is a multiplication by 2^-24 mod 2^576 - 2^240 + 1 per step, so the part of a generator pass (`samples` float4)
+ * behind its first `keep` samples -- or the whole pass, from_start != 0 -- is ONE modular multiplication.  out: 7 entries (`left` = numbers
+ * to go before the next luxury skip on entry, / 4) of 20 words: 18 words of 2^-24(steps - 48), `left` after the pass, 1 if usable.
+ * The backend builds these itself (two-phase update kernels; `ranlux` kernel_runs nobody consumed, as when a resumed run replays
+ * PRNG_counter produce() calls, suncl.cpp:5350); exported so that hosts and tests can check the arithmetic. */
+void  qgpu_ranlux_jump_table(uint64_t samples, uint64_t keep, unsigned skip, int from_start, uint32_t* out);
 
 const char* qgpu_version(void);
 

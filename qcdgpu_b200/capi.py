@@ -52,6 +52,7 @@ EXPORTS = [
     "qgpu_set_fused_prng", "qgpu_set_tile_x", "qgpu_set_fold_reunitarisation", "qgpu_profile_collect", "qgpu_set_stream", "qgpu_kernel_set_x_range", "qgpu_buffer_device_ptr", "qgpu_stream", "qgpu_timer_start",
     "qgpu_timer_stop", "qgpu_launch_count", "qgpu_update_kernel_registers", "qgpu_halo_copy",
     "qgpu_halo_pack", "qgpu_halo_unpack", "qgpu_halo_bytes", "qgpu_host_srand", "qgpu_host_rand_fill",
+    "qgpu_ranlux_jump_table",
 ]
 
 
@@ -141,6 +142,8 @@ def load(build_if_missing: bool = True):
     L.qgpu_halo_bytes.restype = sz
     L.qgpu_host_srand.argtypes = [cu]
     L.qgpu_host_rand_fill.argtypes = [vp, sz, C.c_uint32, C.c_uint32]
+    L.qgpu_ranlux_jump_table.argtypes = [C.c_uint64, C.c_uint64, cu, ci, vp]
+    L.qgpu_ranlux_jump_table.restype = None
     _lib = L
     return L
 

@@ -9,6 +9,7 @@
 // PRN production can be fused into the update kernel (see qgpu_set_fused_prng).
 #include "../../include/qcdgpu_b200.h"
 #include "launch.h"
+#include "ranlux_jump_host.h"
 
 #include <cmath>
 #include <cstdarg>
@@ -85,6 +86,7 @@ struct Buffer {
     void* shadow = nullptr;          // host memory returned by buffer_map
     size_t map_off = 0, map_len = 0;
     int pending_produce = 0;         // kernel id of a deferred PRN producer writing this buffer
+    uint32_t pending_skips = 0;      // produce() calls in front of it whose numbers nobody looked at (RANLUX3: skipped in one jump)
     bool pending_partly_fused = false;   // x-range launches of the current pass already ran that generator in registers
     // RANLUX state table of the two-phase update kernel: a second table of the same size receives the advanced state and the
     // two are swapped when the pass is complete, so the state in front of a pass stays readable during it (update.cuh, PrnSmemT)
@@ -316,11 +318,26 @@ int resync_twin(qgpu* h, int bid) {
     CUDA_OK(h, cudaMemcpyAsync(b.twin, b.dptr, b.capacity, cudaMemcpyDeviceToDevice, h->stream));
     return 0;
 }
+// produce() calls that were overtaken by the next one without anybody reading their numbers (a resumed run replays PRNG_counter of
+// them back to back, suncl.cpp:5350): advance the generators past them in one jump per instance (ranlux_skip_kernel)
+int apply_pending_skips(qgpu* h, int bid) {
+    Buffer& b = h->buffers[bid];
+    if (!b.pending_skips || !b.pending_produce) { b.pending_skips = 0; return 0; }
+    Kernel& k = h->kernels[b.pending_produce];
+    int samples = 0;
+    if (!arg_int(k, 2, &samples) || !buf_ptr(h, k, 0)) return fail(h, "kernel %s: arguments (seed table, samples) not set", k.name.c_str());
+    const uint64_t total = (uint64_t)b.pending_skips * (uint64_t)samples;
+    b.pending_skips = 0;
+    CUDA_OK(h, launch_ranlux_skip((uint32_t*)buf_ptr(h, k, 0), (uint32_t)k.global[0], total, h->stream));
+    h->launches++;
+    return resync_twin(h, buf_id(k, 0));
+}
 // run a deferred PRN producer now (writes the reference-layout buffer)
 int flush_pending(qgpu* h, int bid) {
     if (!valid_buf(h, bid)) return 0;
     int kid = h->buffers[bid].pending_produce;
     if (!kid) return 0;
+    if (apply_pending_skips(h, bid) < 0) return -1;
     if (h->buffers[bid].pending_partly_fused)
         return fail(h, "PRN buffer %d is needed in memory, but x-range launches of this pass already consumed its generator in registers", bid);
     h->buffers[bid].pending_produce = 0;
@@ -469,6 +486,7 @@ int launch_kernel(qgpu* h, int kid) {
                                (pk.prn_kind == PRN_RANLUX3 || pk.prn_kind == PRN_XOR128 || pk.prn_kind == PRN_PM || pk.prn_kind == PRN_MRG32K3A) &&
                                (uint32_t)samples >= 3u * (uint32_t)(c.nhit + 1) * (uint32_t)c.nhitpar;
                 if (fusable) {
+                    if (apply_pending_skips(h, pb) < 0) return -1;
                     a.prn_kind = pk.prn_kind; a.prn_table = (uint32_t*)buf_ptr(h, pk, 0);
                     a.prn_instances = (uint32_t)pk.global[0]; a.prn_samples = (uint32_t)samples;
                     if (pk.prn_kind == PRN_RANLUX3) {      // second state table (see Buffer::twin); without it the kernel works in place
@@ -663,6 +681,10 @@ int launch_kernel(qgpu* h, int kid) {
             if (c.prng_precision == 2) return fail(h, "kernel %s: PRNG_PRECISION=2 (double PRNs) is not implemented", k.name.c_str());
             if (h->buffers[pb].bytes < (size_t)k.global[0] * samples * 16) return fail(h, "kernel %s: PRN buffer too small", k.name.c_str());
             if (h->buffers[pb].pending_partly_fused) finish_partial_pass(h, pb);   // previous pass: consumed by its x-range launches
+            if (h->fused && h->buffers[pb].pending_produce == kid && k.prn_kind == PRN_RANLUX3) {
+                h->buffers[pb].pending_skips++;        // the unconsumed earlier produce() becomes a jump (apply_pending_skips)
+                return 0;
+            }
             if (flush_pending(h, pb) < 0) return -1;   // an unconsumed earlier produce() must still advance the streams
             if (h->fused) { h->buffers[pb].pending_produce = kid; return 0; }   // decided at the consumer
             CUDA_OK(h, launch_prn_produce(k.prn_kind, (uint32_t*)buf_ptr(h, k, 0), h->buffers[pb].dptr, (uint32_t)k.global[0], (uint32_t)samples, st));
@@ -761,6 +783,11 @@ const char* qgpu_version(void) { return "qcdgpu_b200 0.1 (sm_100a)"; }
 // glibc srand()/rand() are part of the reference's stream definition (random.cpp:235, 462-465): bulk helpers so that
 // hosts written in languages with slow FFI can build seed tables of millions of instances quickly.
 void qgpu_host_srand(unsigned seed) { srand(seed); }
+void qgpu_ranlux_jump_table(uint64_t samples, uint64_t keep, unsigned skip, int from_start, uint32_t* out) {
+    uint32_t t[7 * qcd::kRanluxJumpEntryWords];
+    qcd::ranlux_jump_table(samples, keep, skip, t, from_start != 0);
+    memcpy(out, t, sizeof(t));
+}
 void qgpu_host_rand_fill(uint32_t* out, size_t n, uint32_t modulo, uint32_t add) {
     for (size_t i = 0; i < n; i++) { uint32_t r = (uint32_t)rand(); if (modulo) r %= modulo; out[i] = r + add; }
 }

@@ -1,8 +1,36 @@
 // dispatch.cu -- tables that route (SUN, precision, direction) to the separately compiled
 // instantiation units.
 #include "launch.h"
+#include "ranlux_jump_host.h"
+#include <mutex>
+#include <vector>
 
 namespace qcd {
+
+// Device copy of the RANLUX skip-ahead table (ranlux_jump_host.h) for a pass of `samples` float4 of which `keep` are parked, on the
+// current device (from_start: the whole pass is jumped over, for ranlux_skip_kernel); cached for the life of the process.  Null on any failure: the kernels then step.
+const uint32_t* ranlux_jump_table_device(uint64_t samples, uint64_t keep, uint32_t skip, bool from_start) {
+    struct Entry { int dev; uint64_t samples, keep; uint32_t skip; bool from_start; uint32_t* dptr; };
+    static std::mutex mu;
+    static std::vector<Entry> cache;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) { (void)cudaGetLastError(); return nullptr; }
+    std::lock_guard<std::mutex> lock(mu);
+    for (const Entry& e : cache)
+        if (e.dev == dev && e.samples == samples && e.keep == keep && e.skip == skip && e.from_start == from_start) return e.dptr;
+    uint32_t table[7 * kRanluxJumpEntryWords];
+    ranlux_jump_table(samples, keep, skip, table, from_start);
+    bool any = false;
+    for (int e = 0; e < 7; e++) any = any || table[e * kRanluxJumpEntryWords + 19] != 0u;
+    uint32_t* d = nullptr;
+    if (any && (cudaMalloc(&d, sizeof(table)) != cudaSuccess || cudaMemcpy(d, table, sizeof(table), cudaMemcpyHostToDevice) != cudaSuccess)) {
+        (void)cudaGetLastError();
+        if (d) cudaFree(d);
+        d = nullptr;
+    }
+    cache.push_back({ dev, samples, keep, skip, from_start, d });
+    return d;
+}
 
 #define DECL_UPD(S, P, M) cudaError_t launch_update_##S##_##P##_##M(const UpdateArgs&, cudaStream_t); int regs_update_##S##_##P##_##M(int, int);
 #define DECL_UPD4(S, P) DECL_UPD(S, P, 0) DECL_UPD(S, P, 1) DECL_UPD(S, P, 2) DECL_UPD(S, P, 3)

@@ -165,6 +165,38 @@ ranlux_produce_kernel(uint32_t* __restrict__ table, float4* __restrict__ prns, u
     }
     ranlux_store(r, table, instances, i);
 }
+// Fast-forward (a resumed run replays PRNG_counter produce() calls, suncl.cpp:5350): every instance advanced by `samples` float4
+// in one jump (ranlux_jump.cuh; table built with from_start).  An instance the table does not cover (a `left` that is no
+// multiple of four) is stepped.
+static __global__ void __launch_bounds__(128)
+ranlux_skip_kernel(uint32_t* __restrict__ table, uint32_t instances, const uint32_t* __restrict__ jump, unsigned long long samples) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= instances) return;
+    RanluxPk<1> r;
+    uint32_t left = r.load(0, table, instances, i);
+    const uint32_t* entry = (jump != nullptr && left <= 24u && (left & 3u) == 0u) ? jump + (left >> 2) * 20u : nullptr;
+    const uint32_t flags = entry ? __ldg(entry + 19) : 0u;
+    if (flags & 1u) {
+        if (!ranlux_is_fixed_point(r.pk[0].w, r.carry[0])) {
+            uint32_t A[18];
+#pragma unroll
+            for (int w = 0; w < 18; w++) A[w] = __ldg(entry + w);
+            ranlux_jump(r.pk[0].w, r.carry[0], A, flags >> 1);
+        }
+        left = __ldg(entry + 18);
+    } else {
+        Ranlux s;
+        ranlux_load(s, table, instances, i);
+        while (samples > 0ull) {
+            const uint32_t n = samples > 0x40000000ull ? 0x40000000u : (uint32_t)samples;
+            s.template skip_samples<223>(n);
+            samples -= n;
+        }
+        ranlux_store(s, table, instances, i);
+        return;
+    }
+    r.store(0, table, instances, i, left);
+}
 template <class P>
 __global__ void __launch_bounds__(128)
 small_produce_kernel(uint32_t* __restrict__ table, float4* __restrict__ prns, uint32_t instances, uint32_t samples) {

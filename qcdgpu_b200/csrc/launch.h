@@ -42,6 +42,8 @@ struct UpdateArgs {
 typedef cudaError_t (*UpdateLaunchFn)(const UpdateArgs&, cudaStream_t);
 // [sun-2][prec][mu]
 UpdateLaunchFn get_update_launcher(int sun, int prec, int mu);
+// RANLUX skip-ahead table on the current device (dispatch.cu, ranlux_jump_host.h); null: none, the kernels step through the pass
+const uint32_t* ranlux_jump_table_device(uint64_t samples, uint64_t keep, uint32_t skip, bool from_start = false);
 
 struct MeasureArgs {
     const void* table; const void* params; Geom geom; int tbc;
@@ -74,6 +76,8 @@ cudaError_t launch_gramschmidt(int sun, int prec, void* table, const Geom&, cuda
 
 cudaError_t launch_ranlux_init(const uint32_t* seeds, uint32_t* table, uint32_t instances, cudaStream_t);
 cudaError_t launch_prn_produce(int prn_kind, uint32_t* table, void* prns, uint32_t instances, uint32_t samples, cudaStream_t);
+// advance every RANLUX3 instance of a state table by `samples` float4 without producing them (one modular multiplication each)
+cudaError_t launch_ranlux_skip(uint32_t* table, uint32_t instances, uint64_t samples, cudaStream_t);
 
 // halo exchange building block (BigLattice): copy nplanes vec4 planes of one x-slice between plane-strided arrays
 cudaError_t launch_copy_planes(int prec, void* dst, size_t dst_row, uint32_t xd, int dp0, int dps,

@@ -43,6 +43,12 @@ cudaError_t launch_prn_produce(int kind, uint32_t* table, void* prns, uint32_t i
     }
     return cudaGetLastError();
 }
+cudaError_t launch_ranlux_skip(uint32_t* table, uint32_t instances, uint64_t samples, cudaStream_t st) {
+    if (samples == 0 || instances == 0) return cudaSuccess;
+    const uint32_t* jump = ranlux_jump_table_device(samples, 0, 223u, true);      // null: every instance is stepped
+    ranlux_skip_kernel<<<(instances + 127) / 128, 128, 0, st>>>(table, instances, jump, (unsigned long long)samples);
+    return cudaGetLastError();
+}
 
 // Halo exchange building block: copy `nplanes` vec4 planes of one x-slice (n234 elements each)
 // between two plane-strided arrays.  Plane k lives at (p0 + k*ps)*row_elems + x*n234.

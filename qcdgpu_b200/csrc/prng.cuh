@@ -20,6 +20,7 @@
 #pragma once
 #include <cstdint>
 #include <cuda_runtime.h>
+#include "ranlux_jump.cuh"
 
 namespace qcd {
 
@@ -363,18 +364,35 @@ template <int NC> struct RanluxPk {
     // 33 that a link really consumes get converted, by the consumer.  The exception is a sample containing a number below 2^-12, whose
     // fix-up needs a seed that is gone later: it is converted here and flagged in conv (bit k).  parked() is called once all `keep`
     // samples are in place.  `left` (numbers left before the next luxury skip) is read and updated.
+    // jump (NC = 1; may be null): the skip-ahead table of this (samples, keep) -- ranlux_jump_host.h, entry = `left` on entry / 4 --
+    // with which the rest of the pass behind the parked samples is ONE multiplication mod 2^576 - 2^240 + 1 (ranlux_jump.cuh)
+    // instead of ~1000 subtract-with-borrow steps; same state afterwards, bit for bit.
     template <class F>
     __device__ __forceinline__ void pass(uint32_t& left, uint32_t samples, uint32_t keep, uint4* const (&out)[NC], uint32_t stride,
-                                         unsigned long long (&conv)[NC], F parked) {
+                                         unsigned long long (&conv)[NC], F parked, const uint32_t* __restrict__ jump = nullptr) {
         uint32_t k = 0;
         bool told = false;
+        const uint32_t* entry = (NC == 1 && jump != nullptr && left <= 24u && (left & 3u) == 0u) ? jump + (left >> 2) * 20u : nullptr;
 #pragma unroll 1
         while (k < samples) {
             if (left == 0u) { skip223(); left = 24u; }
             const uint32_t j = min(left >> 2, samples - k);
             deliver(j, k, keep, out, stride, conv);
             k += j; left -= 4u * j;
-            if (!told && k >= keep) { parked(); told = true; }
+            if (!told && k >= keep) {
+                parked(); told = true;
+                if (NC == 1 && entry != nullptr && k < samples) {
+                    const uint32_t flags = __ldg(entry + 19);           // bit 0: entry usable; the other bits are zero
+                    if ((flags & 1u) && !ranlux_is_fixed_point(pk[0].w, carry[0])) {
+                        uint32_t A[18];
+#pragma unroll
+                        for (int w = 0; w < 18; w++) A[w] = __ldg(entry + w);
+                        ranlux_jump(pk[0].w, carry[0], A, flags >> 1);
+                        left = __ldg(entry + 18);
+                        return;
+                    }
+                }
+            }
         }
         if (!told) parked();
     }

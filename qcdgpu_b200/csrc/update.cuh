@@ -1334,7 +1334,8 @@ template <int SUN, typename R, int MU, bool TBC, int NSKIP>
 #endif
 __global__ void __launch_bounds__(kUpdateThreads, (sizeof(R) == 8 && SUN == 3) ? QCD_RLX_MINBLOCKS : (4 * 128) / kUpdateThreads)
 update_kernel_rlx(R* __restrict__ table, const R* __restrict__ params, const __grid_constant__ Geom g, int odd,
-                  const uint32_t* rtable, uint32_t* rtable_out, uint32_t instances, uint32_t samples, uint32_t keep) {
+                  const uint32_t* rtable, uint32_t* rtable_out, uint32_t instances, uint32_t samples, uint32_t keep,
+                  const uint32_t* __restrict__ jump) {
     extern __shared__ __align__(128) uint4 prn_smem[];
     QCD_TRACE_MARK(0);
     uint32_t GID = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1356,7 +1357,7 @@ update_kernel_rlx(R* __restrict__ table, const R* __restrict__ params, const __g
         QCD_TRACE_MARK(1);
         if (active) {
             uint4* const out[1] = { prn_smem + threadIdx.x };
-            r.pass(left, samples, keep, out, kUpdateThreads, converted, [] {});
+            r.pass(left, samples, keep, out, kUpdateThreads, converted, [] {}, jump);
             r.store(0, rtable_out, instances, GID, left);
         }
         QCD_TRACE_MARK(2);
@@ -1382,7 +1383,7 @@ template <typename R, int MU, bool TBC, int NSKIP>
 __global__ void __launch_bounds__(kUpdateThreads, (sizeof(R) == 8) ? QCD_RLX_MINBLOCKS : (4 * 128) / kUpdateThreads)
 update_kernel_rlx_tma(R* __restrict__ table, const R* __restrict__ params, const __grid_constant__ Geom g, int odd,
                       const uint32_t* rtable, uint32_t* rtable_out, uint32_t instances, uint32_t samples, uint32_t keep,
-                      const __grid_constant__ TensorMapBlob tmap, const __grid_constant__ TensorMapBlob tmap1) {
+                      const __grid_constant__ TensorMapBlob tmap, const __grid_constant__ TensorMapBlob tmap1, const uint32_t* __restrict__ jump) {
     extern __shared__ __align__(128) uint4 prn_smem[];
     const SiteId site = thread_site(g, blockIdx.x * blockDim.x + threadIdx.x, odd != 0);      // the launcher guarantees full blocks
     const uint32_t GID = site.GID;
@@ -1401,7 +1402,7 @@ update_kernel_rlx_tma(R* __restrict__ table, const R* __restrict__ params, const
                 &tmap, &tmap1, table, g, gindex, p);
     if (g.debug_skip != 1u) {   // phase 1: the pass's whole RANLUX work (the first three links land meanwhile)
         uint4* const out[1] = { prn_smem + threadIdx.x };
-        r.pass(left, samples, keep, out, kUpdateThreads, converted, [] {});
+        r.pass(left, samples, keep, out, kUpdateThreads, converted, [] {}, jump);
         r.store(0, rtable_out, instances, GID, left);
     }
     if (g.debug_skip == 2u) return;

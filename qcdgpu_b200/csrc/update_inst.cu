@@ -66,6 +66,10 @@ static cudaError_t launch_rlx(const UpdateArgs& a, cudaStream_t st) {
     uint32_t keep = need;
     if (out != a.prn_table && (uint32_t)keep_env < need) keep = (uint32_t)keep_env;
     size_t smem = size_t(keep) * kUpdateThreads * sizeof(float4);
+    // the rest of the pass behind the parked samples as one modular multiplication (ranlux_jump.cuh); QCDGPU_RLX_JUMP=0: stepped
+    static int jump_env = -1;
+    if (jump_env < 0) jump_env = env_int("QCDGPU_RLX_JUMP", 1);
+    const uint32_t* jump = (jump_env && keep < a.prn_samples) ? ranlux_jump_table_device(a.prn_samples, keep, 223u) : nullptr;
     // diagnostic: unused shared memory per block, to measure the kernel at 2 or 1 resident blocks per SM
     static int pad_env = -1;
     if (pad_env < 0) pad_env = env_int("QCDGPU_SMEM_PAD_KB", 0);
@@ -100,13 +104,13 @@ static cudaError_t launch_rlx(const UpdateArgs& a, cudaStream_t st) {
                                               a.prn_table, out, a.prn_instances, a.prn_samples, keep, *a.tmap, *a.tmap1, a.ws_counters);
         return cudaGetLastError();
     }
-    if (tma_env && a.tmap && a.tmap1 && kUpdateThreads == 128 && a.geom.n2 % 64u == 0u && a.geom.nthreads % kUpdateThreads == 0u) {
+    if (tma_env && a.tmap && a.tmap1 && kUpdateThreads % 32 == 0 && a.geom.n2 % 64u == 0u && a.geom.nthreads % kUpdateThreads == 0u) {
         auto kt = update_kernel_rlx_tma<RealT, INST_MU, TBC, 223>;
         const size_t smem_t = smem + tma_stage_bytes<RealT>();
         static SmemConfigured configured_t;
         if (cudaError_t e = ensure_smem(kt, smem_t, configured_t); e != cudaSuccess) return e;
         kt<<<a.geom.nthreads / kUpdateThreads, kUpdateThreads, smem_t, st>>>(static_cast<RealT*>(a.table), static_cast<const RealT*>(a.params), a.geom, a.odd,
-                                                                           a.prn_table, out, a.prn_instances, a.prn_samples, keep, *a.tmap, *a.tmap1);
+                                                                           a.prn_table, out, a.prn_instances, a.prn_samples, keep, *a.tmap, *a.tmap1, jump);
         return cudaGetLastError();
     }
 #endif
@@ -116,7 +120,7 @@ static cudaError_t launch_rlx(const UpdateArgs& a, cudaStream_t st) {
     dim3 block(kUpdateThreads), grid((a.geom.nthreads + kUpdateThreads - 1) / kUpdateThreads);
     if (grid.x == 0) return cudaSuccess;
     kern<<<grid, block, smem, st>>>(static_cast<RealT*>(a.table), static_cast<const RealT*>(a.params), a.geom, a.odd,
-                                    a.prn_table, out, a.prn_instances, a.prn_samples, keep);
+                                    a.prn_table, out, a.prn_instances, a.prn_samples, keep, jump);
     return cudaGetLastError();
 }
 template <bool TBC>

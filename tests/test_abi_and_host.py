@@ -2,6 +2,7 @@
 host logic (init.dat, option strings, sizes) behaves like the reference's, and the product fails loudly
 without a CUDA device (no CPU fallback, no oracle on the product path)."""
 import ast
+import ctypes as C
 import os
 import re
 
@@ -119,3 +120,68 @@ def test_on_model_host_logic(tmp_path):
     m.lattice_table_row_size = 32 ** 4
     o = m.options_common()
     assert "-D ON_MODEL" in o and "-D SUN=1" in o and "-D SKGROUP=4" in o and "-D N1EXACT=32" in o and "-D ACC_RATE" in o
+
+
+# ----------------------------------------------------------------------------- RANLUX skip-ahead (csrc/ranlux_jump*.{cuh,h})
+def _load_jump_generator():
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("gen_ranlux_jump", os.path.join(ROOT, "tools", "gen_ranlux_jump.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def test_ranlux_jump_header_is_what_the_checked_generator_prints():
+    """csrc/ranlux_jump.cuh is generated: tools/gen_ranlux_jump.py holds the algorithm as a list of 32-bit operations with PTX carry-flag
+    semantics, runs that list against the plain subtract-with-borrow recurrence (random.cpp:504-574) on random and degenerate states,
+    and prints the same list as CUDA.  Re-run the model here and require the committed header to be its output."""
+    gen = _load_jump_generator()
+    prog = gen.build()
+    assert gen.self_test(prog, trials=120, seed=11) == 120
+    with open(os.path.join(ROOT, "qcdgpu_b200", "csrc", "ranlux_jump.cuh")) as f:
+        assert f.read() == gen.to_cuda(prog)
+
+
+def _replay_pass(left, samples, keep, skip, from_start):
+    """RanluxPk::pass (prng.cuh) step by step: subtract-with-borrow steps behind the parked samples, `left` after the pass"""
+    k, steps, told = 0, 0, from_start
+    while k < samples:
+        if left == 0:
+            steps += skip if told else 0
+            left = 24
+        j = min(left >> 2, samples - k)
+        steps += 4 * j if told else 0
+        k += j
+        left -= 4 * j
+        if not told and k >= keep:
+            told = True
+    return steps, left
+
+
+@pytest.mark.parametrize("samples,keep,from_start", [(33, 12, 0), (33, 8, 0), (12, 12, 0), (21, 0, 0), (33, 0, 1), (6, 0, 1), (33 * 8 * 1000, 0, 1),
+                                                     (2**40 + 5, 0, 1)])
+def test_ranlux_jump_table_of_the_library(samples, keep, from_start):
+    """qgpu_ranlux_jump_table (host code of the library, no device): multipliers against python's pow(2^24, -(steps - 48), m) and the
+    pass plan against a step-by-step replay of the kernel's loop."""
+    from qcdgpu_b200 import capi
+    L = capi.load()
+    out = np.zeros(7 * 20, dtype=np.uint32)
+    L.qgpu_ranlux_jump_table(samples, keep, 223, from_start, out.ctypes.data_as(C.c_void_p))
+    b, m = 1 << 24, (1 << 576) - (1 << 240) + 1
+    for e in range(7):
+        if samples < 10**7:
+            steps, left_after = _replay_pass(4 * e, samples, keep, 223, bool(from_start))
+        else:       # closed form from a sample boundary: whole periods of 6 samples = 24 steps + a 223-step skip in front of each
+            assert from_start
+            first = min(e, samples)                  # samples before the first skip
+            rest = samples - first
+            periods, tail = divmod(rest, 6)
+            steps = 4 * first + periods * (223 + 24) + ((223 + 4 * tail) if tail else 0)
+            left_after = (4 * e - 4 * first) if rest == 0 else ((24 - 4 * tail) if tail else 0)
+        entry = out[20 * e:20 * e + 20]
+        if steps < 48:
+            assert entry[19] == 0
+            continue
+        assert entry[19] == 1 and entry[18] == left_after
+        got = sum(int(w) << (32 * i) for i, w in enumerate(entry[:18]))
+        assert got == pow(b, -(steps - 48), m), (e, steps)

@@ -510,3 +510,32 @@ def test_full_size_properties():
     assert m.Analysis["Plq_total"]["data"][0] == 3.0
     assert 1.5 < m.Analysis["Plq_total"]["data"][1] < 2.9
     m.close()
+
+
+@pytest.mark.parametrize("n", [1, 2, 9, 40])
+def test_repeated_produce_is_one_jump(n):
+    """A resumed run replays PRNG_counter produce() calls back to back (suncl.cpp:5350).  In fused mode nobody reads the numbers of
+    all but the last one, so the backend advances the generators past them in ONE modular multiplication per instance
+    (ranlux_skip_kernel, csrc/ranlux_jump.cuh) instead of n producer launches: the numbers that follow, the lattice after a sweep and
+    the state after it must equal the run in which every produce() is materialised."""
+    res = []
+    for fused in (False, True):
+        m = make_model(3, (4, 4, 4, 6), 1, ints=1, prng="RANLUX3", fused=True, iters=2, beta=5.7)
+        if not fused:
+            m.GPU0.set_fused_prng(False)
+        m.lattice_start()
+        launches = m.GPU0.launch_count()
+        for _ in range(n):
+            m.PRNG0.produce()
+        m.PRNG0.produce()
+        after_skip = m.PRNG0.randoms().copy()          # pass n + 1, materialised in both runs
+        skipped_launches = m.GPU0.launch_count() - launches
+        for _ in range(n):                             # again, this time consumed by the two-phase kernel (jump inside the kernel too)
+            m.PRNG0.produce()
+        m.lattice_sweep()
+        m.PRNG0.produce()
+        res.append((after_skip, m.table_numpy().copy(), m.PRNG0.randoms().copy(), skipped_launches))
+        m.close()
+    for a, b in zip(res[0][:3], res[1][:3]):
+        np.testing.assert_array_equal(a.view(np.uint8), b.view(np.uint8))
+    assert res[0][3] >= n + 1 and res[1][3] <= 3       # n + 1 producer launches against one jump + one producer
