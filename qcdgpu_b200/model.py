@@ -7,8 +7,9 @@ order as the reference's `lattice_init` / `lattice_simulate` / `lattice_analysis
 generator state kept in registers of the update kernel) and `or_steps` (overrelaxation passes
 after each heat-bath sweep; the reference has none).
 
-Not here (out of the hot path): Wilson loops, F_mu_nu / *_diff_* measurement
-variants, the .qcg state files, the start.txt/finish.txt handshake.
+State files (.qcg, suncl.cpp:1857-2079) are written and read in the reference's byte layout (lattice_save_state /
+lattice_load_state; INIT = 0 continues a run, fast-forwarding the generators by PRNG_counter passes).
+Not here (out of the hot path): lattice_action_diff_*, the start.txt/finish.txt handshake.
 """
 from __future__ import annotations
 
@@ -54,6 +55,15 @@ def get_init_file(path: str) -> list[tuple[str, int, float, str]]:
 
 
 MODEL_energies_size = 7     # suncl.h:222: plaquette sums + 6 Fmunu projections
+BIN_HEADER_SIZE = 64        # suncl.cpp:60: dwords in front of the data of a .qcg state file
+# PRNG::convert_generator_to_uint (random.cpp:110-122); MRG32K3A has no number there (the reference maps unknown numbers to RANLUX3)
+GENERATOR_CODES = {"XOR128": 1, "RANLUX0": 2, "RANLUX1": 3, "RANLUX2": 4, "RANLUX3": 5, "RANLUX4": 6, "RANLUX": 7, "RANMAR": 8,
+                   "PM": 9, "XOR7": 10, "RANECU": 11, "MRG32K3A": 12}
+
+
+def convert_str_uint(text: str, offset: int) -> int:
+    """model::convert_str_uint (suncl.cpp:709-716): four characters from `offset`, little end first."""
+    return sum(ord(text[offset + i]) << (8 * i) for i in range(4) if offset + i < len(text))
 
 
 def getK(n1: int, n2: int, ws: int) -> int:
@@ -107,6 +117,10 @@ class Model:
         self.get_plaquettes_avr = True
         self.path = "./"
         self.fprefix = "su3-"
+        self.fstate = ""            # state file to continue from when INIT = 0 (model::fstate, QCDGPU.cpp:234)
+        self.turnoff_config_save = True   # QCDGPU.cpp:203
+        self.PRNG_counter = 0       # produce() calls of the run that wrote the loaded state file (suncl.h:172)
+        self.LOAD_state = 0
         # BIGLAT part description (biglattice.py): this Model then owns Nx real x-slices plus one halo slice each side
         self.biglat = False
         self.Nx = 0                 # real x-slices of the part (SubLat[k].Nx, QCDGPU.cpp:117-118)
@@ -158,6 +172,10 @@ class Model:
             elif key == "NHITPAR": self.NHITPar = ival
             elif key == "FUSEDPRNG": self.fused_prng = bool(ival)
             elif key == "ORSTEPS": self.or_steps = ival
+            # state files: the reference has the fields (INIT, fstate, turnoff_config_save) but no init.dat keys for them
+            elif key == "INIT": self.INIT = ival
+            elif key == "FSTATE": self.fstate = text
+            elif key == "SAVESTATE": self.turnoff_config_save = not bool(ival)
             self.PRNG0.parameters_setup(key, ival, text)
 
     # ------------------------------------------------------------------ lattice_init (suncl.cpp:672-706)
@@ -167,6 +185,8 @@ class Model:
         g.device_initialize()
         g.set_async(self.async_run)
         g.set_fused_prng(self.fused_prng)
+        if self.INIT == 0:
+            self.lattice_load_state()      # the header: run parameters of the interrupted run (suncl.cpp:695)
         self.model_lattice_init()
 
     # model_lattice_init (suncl.cpp:2212-2384)
@@ -296,6 +316,116 @@ class Model:
             self.lattice_polyakov_loop_diff = {a: g.buffer_init(GPU.buffer_type_IO, self.size_lattice_polyakov_loop, None, 16) for a in "xyz"}
         if self.get_wilson_loop:
             self.lattice_wilson_loop = g.buffer_init(GPU.buffer_type_IO, self.lattice_energies_size, None, 8)
+        if self.INIT == 0:
+            self.lattice_load_state()      # the data (suncl.cpp:3956; the reference fills its host arrays before buffer_init copies them)
+
+    # ------------------------------------------------------------------ state files (suncl.cpp:1857-2079)
+    @property
+    def lattice_energies_size_F(self) -> int:
+        return self.lattice_energies_size * (MODEL_energies_size if (self.get_Fmunu or self.get_F0mu) else 1)   # suncl.cpp:2268, 2296-2297
+
+    def _state_sections(self):
+        """(buffer id, bytes) of the data sections of a state file, in file order (suncl.cpp:1889-1901)."""
+        double = self.precision == model_precision_double
+        sec = [(self.lattice_measurement, 16 * self.lattice_measurement_size_F),
+               (self.lattice_energies, 16 * self.lattice_energies_size)]
+        if self.get_plaquettes_avr or self.get_Fmunu or self.get_F0mu:
+            sec.append((self.lattice_energies_plq, 16 * self.lattice_energies_size_F))
+        if self.get_wilson_loop:
+            sec.append((self.lattice_wilson_loop, 8 * self.lattice_energies_size))
+        if self.PL_level > 0:
+            sec.append((self.lattice_polyakov_loop, 16 * self.lattice_polyakov_loop_size))
+        # the reference writes double4 for anything but single; mixed precision is float4 storage here (SURVEY.md section 0 row 3)
+        sec.append((self.lattice_table, (32 if double else 16) * self.lattice_table_size))
+        return sec
+
+    def lattice_make_bin_header(self) -> np.ndarray:
+        """model::lattice_make_bin_header (suncl.cpp:1939-1990): 64 dwords."""
+        head = np.zeros(BIN_HEADER_SIZE, dtype=np.uint32)
+        for i in range(2):
+            head[i] = convert_str_uint("QCDGPU", 4 * i)
+        head[2] = convert_str_uint(VERSION, 0)
+        lo_hi = lambda x: np.array([x], dtype=np.float64).view(np.uint32)       # convert_to_uint_LOW / _HIGH
+        i1, i2 = self.Fmunu_indices()
+        P = self.PRNG0
+        fields = [self.INIT, self.ints, P.PRNG_randseries, GENERATOR_CODES.get(P.PRNG_generator, 5), P.RL_nskip, P.PRNG_counter,
+                  self.NAV, self.NAV_counter, self.NITER, self.ITER, self.ITER_counter, self.NHIT, self.wilson_R, self.wilson_T,
+                  {model_precision_single: 1, model_precision_double: 2, model_precision_mixed: 3}[self.precision],
+                  *lo_hi(self.BETA), *lo_hi(self.PHI), *lo_hi(self.OMEGA),
+                  self.PL_level, i1, i2, int(self.get_Fmunu), int(self.get_actions_avr), int(self.get_plaquettes_avr), int(self.get_wilson_loop),
+                  self.lattice_measurement_size_F, self.lattice_energies_size, self.lattice_energies_size_F, self.lattice_polyakov_loop_size,
+                  self.lattice_group, self.lattice_nd, *self.lattice_full_size[:self.lattice_nd], *self.lattice_domain_size[:self.lattice_nd]]
+        head[4:4 + len(fields)] = np.array([int(f) & 0xFFFFFFFF for f in fields], dtype=np.uint32)
+        return head
+
+    def lattice_load_bin_header(self, head: np.ndarray) -> bool:
+        """model::lattice_load_bin_header (suncl.cpp:1992-2041): run parameters from a state file; False if it is not one."""
+        if [int(head[0]), int(head[1])] != [convert_str_uint("QCDGPU", 0), convert_str_uint("QCDGPU", 4)] or int(head[2]) != convert_str_uint(VERSION, 0):
+            return False
+        it = iter(int(v) for v in head[5:])            # head[4] (INIT of the writer) is skipped
+        dbl = lambda: float(np.array([next(it), next(it)], dtype=np.uint32).view(np.float64)[0])
+        P = self.PRNG0
+        v = next(it)
+        self.ints = v if v in (0, 1, 2) else model_start_hot            # convert_uint_to_start
+        P.PRNG_randseries = next(it)
+        code = next(it)
+        P.PRNG_generator = {v: k for k, v in GENERATOR_CODES.items()}.get(code, "RANLUX3")
+        P.RL_nskip = next(it)
+        self.PRNG_counter = next(it)
+        self.NAV, self.NAV_counter, self.NITER, self.ITER, self.ITER_counter, self.NHIT = (next(it) for _ in range(6))
+        self.wilson_R, self.wilson_T = next(it), next(it)
+        self.precision = {1: model_precision_single, 2: model_precision_double, 3: model_precision_mixed}.get(next(it), model_precision_single)
+        self.BETA, self.PHI, self.OMEGA = dbl(), dbl(), dbl()
+        self.PL_level = next(it)
+        i1, i2 = next(it), next(it)
+        self.get_Fmunu, self.get_actions_avr, self.get_plaquettes_avr, self.get_wilson_loop = (bool(next(it)) for _ in range(4))
+        self._loaded_sizes = [next(it) for _ in range(4)]      # recomputed by model_lattice_init; checked when the data is read
+        self.lattice_group, self.lattice_nd = next(it), next(it)
+        self.lattice_full_size = [next(it) for _ in range(self.lattice_nd)]
+        self._loaded_domain = [next(it) for _ in range(self.lattice_nd)]
+        if self.lattice_group == 3:
+            self.Fmunu_gen1, self.Fmunu_gen2 = (0 if i1 == 3 else i1), (0 if i2 == 8 else i2)
+        else:
+            self.Fmunu_gen1 = 1 if i1 == 1 else 0
+        self.fprefix = f"su{self.lattice_group}-"
+        return True
+
+    def lattice_save_state(self, filename: str | None = None) -> str:
+        """model::lattice_save_state (suncl.cpp:1857-1937): header, result buffers, link table; the reference's name
+        <path><prefix>yy-Mon-dd-hh-mm-ss.qcg unless one is given."""
+        g = self.GPU0
+        if filename is None:
+            filename = os.path.join(self.path, self.fprefix + time.strftime("%y-%b-%d-%H-%M-%S") + ".qcg")
+        with open(filename, "wb") as f:
+            f.write(self.lattice_make_bin_header().tobytes())
+            for bid, nbytes in self._state_sections():
+                f.write(g.buffer_map(bid, np.uint8)[:nbytes].tobytes())
+        return filename
+
+    def lattice_load_state(self, filename: str | None = None):
+        """model::lattice_load_state (suncl.cpp:2043-2079): first call = header (before the sizes are computed), second call = data
+        (once the buffers exist)."""
+        g = self.GPU0
+        if filename is None:
+            filename = self.fstate if os.path.isabs(self.fstate) else os.path.join(self.path, self.fstate)
+        with open(filename, "rb") as f:
+            head = np.frombuffer(f.read(4 * BIN_HEADER_SIZE), dtype=np.uint32)
+            if self.LOAD_state == 0:
+                if head.size != BIN_HEADER_SIZE or not self.lattice_load_bin_header(head):
+                    raise QcdGpuError(f"{filename}: not a QCDGPU {VERSION} state file")
+            elif self.LOAD_state == 1:
+                sizes = [self.lattice_measurement_size_F, self.lattice_energies_size, self.lattice_energies_size_F, self.lattice_polyakov_loop_size]
+                if sizes != self._loaded_sizes:
+                    raise QcdGpuError(f"{filename}: buffer sizes {self._loaded_sizes} of the writer differ from {sizes} here "
+                                      "(other work-group size or alignment)")
+                for bid, nbytes in self._state_sections():
+                    data = np.frombuffer(f.read(nbytes), dtype=np.uint8)
+                    if data.size != nbytes:
+                        raise QcdGpuError(f"{filename}: truncated")
+                    cur = g.buffer_map(bid, np.uint8).copy()
+                    cur[:nbytes] = data
+                    g.buffer_write_from(bid, cur)
+        self.LOAD_state += 1
 
     # ------------------------------------------------------------------ lattice_make_programs (suncl.cpp:3265-3648)
     def options_common(self) -> str:
@@ -478,6 +608,12 @@ class Model:
         self.lattice_make_programs()
         if self.ints == model_start_hot:
             P.produce()
+        if self.INIT == 0:
+            # continue from a state file (suncl.cpp:5349-5354): the generators were re-seeded from RANDSERIES; replay the produce() calls
+            # of the interrupted run.  Back-to-back produce() calls nobody consumes cost one jump per generator in fused mode.
+            while self.PRNG_counter > P.PRNG_counter:
+                P.produce()
+            return
         if self.ints == model_start_hot:
             for i, k in enumerate(self.sun_init_hot_id):
                 g.kernel_run(k)
@@ -502,6 +638,8 @@ class Model:
             self.ITER_counter += 1
         g.synchronize()
         self.elapsed = time.time() - t0
+        if not self.turnoff_config_save:
+            self.lattice_save_state()      # suncl.cpp:5498-5500
 
     # ------------------------------------------------------------------ analysis (suncl.cpp:1328-1675, data_analysis.cpp:107-135)
     @staticmethod
