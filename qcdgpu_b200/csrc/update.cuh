@@ -1385,7 +1385,8 @@ update_kernel_rlx_tma(R* __restrict__ table, const R* __restrict__ params, const
                       const uint32_t* rtable, uint32_t* rtable_out, uint32_t instances, uint32_t samples, uint32_t keep,
                       const __grid_constant__ TensorMapBlob tmap, const __grid_constant__ TensorMapBlob tmap1, const uint32_t* __restrict__ jump) {
     extern __shared__ __align__(128) uint4 prn_smem[];
-    const SiteId site = thread_site(g, blockIdx.x * blockDim.x + threadIdx.x, odd != 0);      // the launcher guarantees full blocks
+    if (blockIdx.x * blockDim.x + threadIdx.x >= g.nthreads) return;                          // whole warps (the launcher guarantees full warps)
+    const SiteId site = thread_site(g, blockIdx.x * blockDim.x + threadIdx.x, odd != 0);
     const uint32_t GID = site.GID;
     unsigned long long converted[1] = { 0ull };
     RanluxPk<1> r;

@@ -104,12 +104,12 @@ static cudaError_t launch_rlx(const UpdateArgs& a, cudaStream_t st) {
                                               a.prn_table, out, a.prn_instances, a.prn_samples, keep, *a.tmap, *a.tmap1, a.ws_counters);
         return cudaGetLastError();
     }
-    if (tma_env && a.tmap && a.tmap1 && kUpdateThreads % 32 == 0 && a.geom.n2 % 64u == 0u && a.geom.nthreads % kUpdateThreads == 0u) {
+    if (tma_env && a.tmap && a.tmap1 && kUpdateThreads % 32 == 0 && a.geom.n2 % 64u == 0u && a.geom.nthreads % 32u == 0u && a.geom.nthreads > 0u) {
         auto kt = update_kernel_rlx_tma<RealT, INST_MU, TBC, 223>;
         const size_t smem_t = smem + tma_stage_bytes<RealT>();
         static SmemConfigured configured_t;
         if (cudaError_t e = ensure_smem(kt, smem_t, configured_t); e != cudaSuccess) return e;
-        kt<<<a.geom.nthreads / kUpdateThreads, kUpdateThreads, smem_t, st>>>(static_cast<RealT*>(a.table), static_cast<const RealT*>(a.params), a.geom, a.odd,
+        kt<<<(a.geom.nthreads + kUpdateThreads - 1) / kUpdateThreads, kUpdateThreads, smem_t, st>>>(static_cast<RealT*>(a.table), static_cast<const RealT*>(a.params), a.geom, a.odd,
                                                                            a.prn_table, out, a.prn_instances, a.prn_samples, keep, *a.tmap, *a.tmap1, jump);
         return cudaGetLastError();
     }

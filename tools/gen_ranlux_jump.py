@@ -29,7 +29,7 @@ import random
 import sys
 
 B = 1 << 24
-LAG = 2            # multiplication carry chains in flight (see build)
+LAG = 3            # multiplication carry chains in flight (see build)
 M = B**24 - B**10 + 1
 MASK32 = 0xFFFFFFFF
 W576 = (1 << 576) - 1
