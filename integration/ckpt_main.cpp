@@ -6,6 +6,7 @@
 // the reference's code compiled from where it lies, over integration/clinterface_cuda.cpp + libqcdgpu_b200.so.
 //
 //   QCDGPU_b200_ckpt init.dat [state.qcg]        writes <OUTPUTPATH>/su3-<date>.qcg at the end of the run
+//   QCDGPU_ACTIONS_DIFF=1 in the environment switches on model::get_actions_diff (action per x / y / z slice)
 #include "QCDGPU.h"
 
 #include <cstdio>
@@ -61,7 +62,7 @@ int main(int argc, char** argv) {
     m->get_Fmunu1 = false;
     m->get_Fmunu5 = false;
     m->write_lattice_state_every_secs = 1.0e9;       // one file, at the end of the run (suncl.cpp:5498-5500)
-    m->get_actions_diff = false;
+    m->get_actions_diff = getenv("QCDGPU_ACTIONS_DIFF") != NULL;     // another switch without an init.dat key (QCDGPU.cpp:218)
     m->check_prngs = true;
     m->finishpath = dup_str("./");
     m->path = dup_str("./");

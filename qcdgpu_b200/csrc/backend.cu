@@ -49,7 +49,7 @@ struct ProgramCfg {
 enum KernelKind {
     K_NONE = 0, K_INIT_COLD, K_INIT_GID, K_INIT_HOT, K_GRAMSCHMIDT, K_UPDATE, K_OVERRELAX, K_CLEAR,
     K_MEASURE, K_REDUCE_MEAS, K_MEASURE_PLQ, K_REDUCE_PLQ, K_POLYAKOV, K_REDUCE_POLYAKOV,
-    K_POLYAKOV_DIFF, K_REDUCE_POLYAKOV_DIFF, K_WILSON, K_REDUCE_WILSON,
+    K_POLYAKOV_DIFF, K_REDUCE_POLYAKOV_DIFF, K_WILSON, K_REDUCE_WILSON, K_ACTION_DIFF, K_REDUCE_ACTION_DIFF,
     K_RANLUX_INIT, K_PRODUCE,
     K_ON_INIT_COLD, K_ON_INIT_HOT, K_ON_UPDATE, K_ON_MEASURE, K_ON_REDUCE
 };
@@ -259,6 +259,9 @@ const NameMap kNames[] = {
     { "reduce_polyakov_diff_x_double2", K_REDUCE_POLYAKOV_DIFF, 0, 0, 0 }, { "reduce_polyakov_diff_y_double2", K_REDUCE_POLYAKOV_DIFF, 1, 0, 0 },
     { "reduce_polyakov_diff_z_double2", K_REDUCE_POLYAKOV_DIFF, 2, 0, 0 },
     { "lattice_measurement_wilson", K_WILSON, 0, 0, 0 }, { "reduce_wilson_double2", K_REDUCE_WILSON, 0, 0, 0 },
+    { "lattice_action_diff_x", K_ACTION_DIFF, 0, 0, 0 }, { "lattice_action_diff_y", K_ACTION_DIFF, 1, 0, 0 }, { "lattice_action_diff_z", K_ACTION_DIFF, 2, 0, 0 },
+    { "reduce_action_diff_x_double2", K_REDUCE_ACTION_DIFF, 0, 0, 0 }, { "reduce_action_diff_y_double2", K_REDUCE_ACTION_DIFF, 1, 0, 0 },
+    { "reduce_action_diff_z_double2", K_REDUCE_ACTION_DIFF, 2, 0, 0 },
     { "ranlux_init", K_RANLUX_INIT, 0, 0, 0 },
     { "ranlux", K_PRODUCE, 0, 0, -1 }, { "xor128", K_PRODUCE, 0, 0, PRN_XOR128 }, { "pm", K_PRODUCE, 0, 0, PRN_PM }, { "mrg32k3a", K_PRODUCE, 0, 0, PRN_MRG32K3A },
 };
@@ -529,6 +532,7 @@ int launch_kernel(qgpu* h, int kid) {
         case K_MEASURE: case K_MEASURE_PLQ: {
             MeasureArgs a;
             memset(&a, 0, sizeof(a));
+            a.diff_axis = -1;
             a.table = buf_ptr(h, k, 0); a.params = buf_ptr(h, k, 2);
             double2* out = (double2*)buf_ptr(h, k, 1);
             if (!a.table || !a.params || !out) return fail(h, "kernel %s: arguments (table, measurement, parameters) not set", k.name.c_str());
@@ -580,6 +584,7 @@ int launch_kernel(qgpu* h, int kid) {
         case K_WILSON: {
             MeasureArgs a;
             memset(&a, 0, sizeof(a));
+            a.diff_axis = -1;
             a.table = buf_ptr(h, k, 0); a.params = buf_ptr(h, k, 2);
             a.out_plq = (double2*)buf_ptr(h, k, 1);
             if (!a.table || !a.params || !a.out_plq) return fail(h, "kernel %s: arguments (table, measurement, parameters) not set", k.name.c_str());
@@ -600,6 +605,41 @@ int launch_kernel(qgpu* h, int kid) {
             if (!buf_ptr(h, k, 0) || !buf_ptr(h, k, 1)) return fail(h, "kernel %s: buffers not set", k.name.c_str());
             if (h->buffers[buf_id(k, 1)].capacity < ((size_t)index + 1) * 8) return fail(h, "kernel %s: result buffer too small", k.name.c_str());
             CUDA_OK(h, launch_reduce_double_x((const double2*)buf_ptr(h, k, 0), (uint32_t)size, (double*)buf_ptr(h, k, 1), (uint32_t)index, st));
+            break;
+        }
+        // slice-resolved action (sun_measurements_cl.cl:186-706; no init.dat key of the reference switches it on: model::get_actions_diff)
+        case K_ACTION_DIFF: {
+            MeasureArgs a;
+            memset(&a, 0, sizeof(a));
+            a.table = buf_ptr(h, k, 0); a.out_action = (double2*)buf_ptr(h, k, 1); a.params = buf_ptr(h, k, 2);
+            if (!a.table || !a.out_action || !a.params) return fail(h, "kernel %s: arguments (table, measurement, parameters) not set", k.name.c_str());
+            if (c.biglat) return fail(h, "kernel %s: the BIGLAT slice-resolved action kernels are not implemented in qcdgpu_b200", k.name.c_str());
+            a.geom = make_geom(c); a.tbc = c.tbc ? 1 : 0; a.diff_axis = k.dir;
+            a.plk = c.plk_axis[k.dir] ? c.plk_axis[k.dir] : c.plk;
+            if (!a.plk) return fail(h, "kernel %s: the program was created without -D PLK", k.name.c_str());
+            a.block = (uint32_t)k.local0;
+            if (a.block == 0 || a.block > 256) return fail(h, "kernel %s: work-group size %u not supported (1..256)", k.name.c_str(), a.block);
+            a.min_blocks = (uint32_t)((k.global[0] + a.block - 1) / a.block);
+            {   // every site must have a thread: slices of N_a x PLK x N4 (x, y) or N1 x PLK x N4 (z) padded sites
+                const uint64_t per = (uint64_t)(k.dir == 0 ? c.n2 : c.n1) * a.plk * c.n4, nsl = (k.dir == 0) ? c.n1 : (k.dir == 1) ? c.n2 : c.n3;
+                const uint32_t padded = (k.dir == 2) ? c.n2 : c.n3;
+                if (a.plk < padded || (uint64_t)a.min_blocks * a.block < per * nsl)
+                    return fail(h, "kernel %s: grid of %zu threads does not cover the %llu padded sites (PLK = %u)", k.name.c_str(), (size_t)k.global[0], (unsigned long long)(per * nsl), a.plk);
+            }
+            if (h->buffers[buf_id(k, 1)].capacity < (size_t)a.min_blocks * 16) return fail(h, "kernel %s: measurement buffer too small", k.name.c_str());
+            CUDA_OK(h, launch_measure(c.sun, prec, a, st));
+            break;
+        }
+        case K_REDUCE_ACTION_DIFF: {
+            int index = 0;
+            if (k.args.size() < 5 || k.args[3].type != Arg::U32X4 || !arg_int(k, 4, &index)) return fail(h, "kernel %s: arguments (param, index) not set", k.name.c_str());
+            if (!buf_ptr(h, k, 0) || !buf_ptr(h, k, 1)) return fail(h, "kernel %s: buffers not set", k.name.c_str());
+            const uint32_t* p = k.args[3].u4;                              // total partials, result stride
+            const uint32_t n = (k.dir == 0) ? c.n1 : (k.dir == 1) ? c.n2 : c.n3;
+            const uint32_t size = p[0] / n;
+            if (index < 0 || h->buffers[buf_id(k, 1)].capacity < ((size_t)index + (size_t)p[1] * (n - 1) + 1) * 16) return fail(h, "kernel %s: result buffer too small", k.name.c_str());
+            if (h->buffers[buf_id(k, 0)].capacity / 16 < (size_t)size * n) return fail(h, "kernel %s: measurement buffer too small", k.name.c_str());
+            CUDA_OK(h, launch_reduce_slices((const double2*)buf_ptr(h, k, 0), size, n, (double2*)buf_ptr(h, k, 1), (uint32_t)index, p[1], 0u, 0u, false, st));
             break;
         }
         case K_POLYAKOV_DIFF: {

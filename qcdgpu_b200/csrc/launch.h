@@ -53,6 +53,7 @@ struct MeasureArgs {
     int fmode, gen1, gen2; uint32_t offset;
     int wilson;                                 // 1: Wilson loop W(R,T) into out_plq[BID].x instead of the plaquettes
     uint32_t min_blocks;                        // the host's grid: every partial slot its reducer will sum must be written (zeros beyond the sites)
+    int diff_axis; uint32_t plk;                // diff_axis >= 0: lattice_action_diff_{x,y,z} on the index space padded to PLK (memset gives 0: set -1!)
 };
 cudaError_t launch_measure(int sun, int prec, const MeasureArgs&, cudaStream_t);   // dispatch.cu
 

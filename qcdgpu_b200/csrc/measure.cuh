@@ -100,17 +100,54 @@ __device__ __forceinline__ double retrace_plq2(const V4<double>& U1, const V4<do
     return 2.0 * p.x;
 }
 
+// Thread index on the padded 4D index space of the slice-resolved action kernels -> site index, or g.sites if the thread has no site
+// (lattice_gidK_{x,y,z}_to_gid, sun_common.cl:222-349): the slices of `axis` lie `per-slice size` apart, one transverse extent is
+// padded to PLK so that the host's work-groups stay inside a slice.
+__device__ __forceinline__ uint32_t gidk_to_gid(const Geom& g, int axis, uint32_t plk, uint32_t k) {
+    uint32_t x, y, z, t;
+    if (axis == 0) {            // k = t + y N4 + z N2 N4 + x N2 PLK N4
+        const uint32_t per = g.n2 * plk * g.n4, z4 = k / per;
+        uint32_t z1 = k - z4 * per;
+        const uint32_t z3 = z1 / (g.n2 * g.n4); z1 -= z3 * g.n2 * g.n4;
+        const uint32_t z2 = z1 / g.n4; z1 -= z2 * g.n4;
+        if (!(z1 < g.n4 && z2 < g.n2 && z3 < g.n3 && z4 < g.n1)) return g.sites;
+        x = z4; y = z2; z = z3; t = z1;
+    } else if (axis == 1) {     // k = t + x N4 + z N1 N4 + y N1 PLK N4
+        const uint32_t per = g.n1 * plk * g.n4, z4 = k / per;
+        uint32_t z1 = k - z4 * per;
+        const uint32_t z3 = z1 / (g.n1 * g.n4); z1 -= z3 * g.n1 * g.n4;
+        const uint32_t z2 = z1 / g.n4; z1 -= z2 * g.n4;
+        if (!(z1 < g.n4 && z2 < g.n1 && z3 < g.n3 && z4 < g.n2)) return g.sites;
+        x = z2; y = z4; z = z3; t = z1;
+    } else {                    // k = t + y N4 + x PLK N4 + z N1 PLK N4
+        const uint32_t per = g.n1 * plk * g.n4, z4 = k / per;
+        uint32_t z1 = k - z4 * per;
+        const uint32_t z3 = z1 / (plk * g.n4); z1 -= z3 * plk * g.n4;
+        const uint32_t z2 = z1 / g.n4; z1 -= z2 * g.n4;
+        if (!(z1 < g.n4 && z2 < g.n2 && z3 < g.n1 && z4 < g.n3)) return g.sites;
+        x = z3; y = z2; z = z4; t = z1;
+    }
+    Coord c; c.x = x; c.y = y; c.z = z; c.t = t;
+    return coords_to_gid(g, c);
+}
+
 // out layout: measurement[BID] = (S_spat, S_temp) partial; measurement[BID + offset] = (Plq_spat, Plq_temp) partial
-template <int SUN, typename R, bool TBC>
+// DIFF: lattice_action_diff_{x,y,z} (sun_measurements_cl.cl:186-615): the same site action on the padded index space of `axis`
+template <int SUN, typename R, bool TBC, bool DIFF = false>
 __global__ void __launch_bounds__(kMeasThreads)
 measure_kernel(const R* __restrict__ table, const R* __restrict__ params, const __grid_constant__ Geom g,
-               double2* __restrict__ out_action, double2* __restrict__ out_plq, uint32_t first_site, uint32_t nsites) {
+               double2* __restrict__ out_action, double2* __restrict__ out_plq, uint32_t first_site, uint32_t nsites,
+               int axis = 0, uint32_t plk = 0) {
     const R beta = params[0];
     const Twist<R> tw = make_twist<SUN, R, TBC>(params);
     uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
-    double v[2] = { 0.0, 0.0 };
-    if (k < nsites) {
-        uint32_t gid = first_site + k;
+    double v[3] = { 0.0, 0.0, 0.0 };
+    uint32_t site = g.sites;
+    if (DIFF) site = gidk_to_gid(g, axis, plk, k);
+    else if (k < nsites) site = first_site + k;
+    if (site < g.sites) {
+        uint32_t gid = site;
+        v[2] = 1.0;
         Coord p = gid_to_coords(g, gid);
         Coord pX = nb_plus<0>(g, p), pY = nb_plus<1>(g, p), pZ = nb_plus<2>(g, p), pT = nb_plus<3>(g, p);
         uint32_t gX = coords_to_gid(g, pX), gY = coords_to_gid(g, pY), gZ = coords_to_gid(g, pZ), gT = coords_to_gid(g, pT);
@@ -142,12 +179,13 @@ measure_kernel(const R* __restrict__ table, const R* __restrict__ params, const 
         }
         v[0] = spat; v[1] = temp;
     }
-    block_sum<2>(v);
+    block_sum<3>(v);
     if (threadIdx.x == 0) {
         const double trN = (SUN == 3) ? 9.0 : 6.0;
         // number of active sites in this block (the reference adds bet*(9 - retr) per active thread)
         uint32_t base = blockIdx.x * blockDim.x;
-        uint32_t act = (base < nsites) ? min(uint32_t(blockDim.x), nsites - base) : 0u;
+        double act = (base < nsites) ? double(min(uint32_t(blockDim.x), nsites - base)) : 0.0;
+        if (DIFF) act = v[2];
         if (out_plq) out_plq[blockIdx.x] = make_double2(v[0], v[1]);
         if (out_action) {
             double b = double(beta);

@@ -37,6 +37,12 @@ cudaError_t NAME(launch_measure)(const MeasureArgs& a, cudaStream_t st) {
         else       measure_f_kernel<INST_SUN, RealT, false><<<grid, block, 0, st>>>(t, p, a.geom, a.out_plq, a.offset, a.fmode, a.gen1, a.gen2, a.first_site, a.nsites);
         return cudaGetLastError();
     }
+    if (a.diff_axis >= 0) {    // slice-resolved action: the host's grid and work-group size define the partial layout
+        if (a.min_blocks == 0 || a.block == 0 || a.block > (uint32_t)kMeasThreads || a.plk == 0) return cudaErrorInvalidValue;
+        if (a.tbc) measure_kernel<INST_SUN, RealT, true, true><<<a.min_blocks, a.block, 0, st>>>(t, p, a.geom, a.out_action, nullptr, 0u, 0u, a.diff_axis, a.plk);
+        else       measure_kernel<INST_SUN, RealT, false, true><<<a.min_blocks, a.block, 0, st>>>(t, p, a.geom, a.out_action, nullptr, 0u, 0u, a.diff_axis, a.plk);
+        return cudaGetLastError();
+    }
     if (a.tbc) measure_kernel<INST_SUN, RealT, true><<<grid, block, 0, st>>>(t, p, a.geom, a.out_action, a.out_plq, a.first_site, a.nsites);
     else       measure_kernel<INST_SUN, RealT, false><<<grid, block, 0, st>>>(t, p, a.geom, a.out_action, a.out_plq, a.first_site, a.nsites);
     return cudaGetLastError();

@@ -115,10 +115,12 @@ class Model:
         self.turnoff_gramschmidt = False
         self.get_actions_avr = True
         self.get_plaquettes_avr = True
+        self.get_actions_diff = False     # action per x / y / z slice (model::get_actions_diff: QCDGPU.cpp:218, no init.dat key in the reference)
         self.path = "./"
         self.fprefix = "su3-"
         self.fstate = ""            # state file to continue from when INIT = 0 (model::fstate, QCDGPU.cpp:234)
         self.turnoff_config_save = True   # QCDGPU.cpp:203
+        self.write_lattice_state_every_secs = 2.0     # QCDGPU.cpp:215
         self.PRNG_counter = 0       # produce() calls of the run that wrote the loaded state file (suncl.h:172)
         self.LOAD_state = 0
         # BIGLAT part description (biglattice.py): this Model then owns Nx real x-slices plus one halo slice each side
@@ -173,6 +175,7 @@ class Model:
             elif key == "FUSEDPRNG": self.fused_prng = bool(ival)
             elif key == "ORSTEPS": self.or_steps = ival
             # state files: the reference has the fields (INIT, fstate, turnoff_config_save) but no init.dat keys for them
+            elif key == "ACTIONSDIFF": self.get_actions_diff = bool(ival)      # model::get_actions_diff has no key in the reference
             elif key == "INIT": self.INIT = ival
             elif key == "FSTATE": self.fstate = text
             elif key == "SAVESTATE": self.turnoff_config_save = not bool(ival)
@@ -194,8 +197,8 @@ class Model:
         g = self.GPU0
         if self.lattice_group not in (2, 3):
             raise QcdGpuError("GROUP must be 2 or 3")
-        if self.biglat and (self.PL_level > 2 or self.get_wilson_loop or self.get_Fmunu or self.get_F0mu):
-            raise QcdGpuError("PL_LEVEL 3, Wilson loops and Fmunu are implemented for the single-lattice build only")
+        if self.biglat and (self.PL_level > 2 or self.get_wilson_loop or self.get_Fmunu or self.get_F0mu or self.get_actions_diff):
+            raise QcdGpuError("PL_LEVEL 3, Wilson loops, Fmunu and the slice-resolved action are implemented for the single-lattice build only")
         full = self.lattice_full_size
         if self.biglat:
             # suncl.cpp:2388-2446: the part is stored with N1 = Nx + 2 (one halo slice on each side)
@@ -238,7 +241,13 @@ class Model:
             self.lattice_polyakov_size = al(self.lattice_domain_exact_n1n2n3)
         self.lattice_polyakov_loop_size = al(self.ITER)
         self.lattice_polyakov_loop_offset = al(int(math.ceil(self.lattice_polyakov_size / workgroup_factor)))
-        self.lattice_action_size = self.lattice_table_exact_row_size
+        if self.get_actions_diff:  # suncl.cpp:2291-2294: grid of all action kernels = the index space padded to PLK
+            self.lattice_action_size = al(self.lattice_domain_n2n3n4 * getK(n[0], n[1], local_size_intel))
+            # (the reference warns "buffer plattice_measurement should be resized" instead, suncl.cpp:3511-3515)
+            self.lattice_measurement_size = max(self.lattice_measurement_size, al(int(math.ceil(self.lattice_action_size / workgroup_factor))))
+            self.lattice_measurement_size_F = self.lattice_measurement_size * (MODEL_energies_size if fm else 1)
+        else:
+            self.lattice_action_size = self.lattice_table_exact_row_size
         # PRNG preparation (suncl.cpp:2301-2311)
         P = self.PRNG0
         half = self.lattice_table_row_size_half
@@ -292,6 +301,8 @@ class Model:
         self.size_lattice_measurement = max(self.lattice_measurement_size_F,
                                             2 * self.lattice_polyakov_loop_offset if self.PL_level > 1 else 0)
         self.size_lattice_energies = self.lattice_energies_size
+        if self.get_actions_diff:  # suncl.cpp:3892-3896
+            self.size_lattice_energies *= 2 * getK(self.lattice_domain_n1, self.lattice_domain_size[1], g.GPU_limit_max_workgroup_size or 0)
         self.size_lattice_energies_plq = self.lattice_energies_offset * MODEL_energies_size      # suncl.cpp:3890
         if self.PL_level > 2:      # suncl.cpp:3898-3901
             self.size_lattice_polyakov_loop = (self.lattice_domain_n1 + 1) * self.lattice_polyakov_loop_size * max(self.PLK, 1)
@@ -310,6 +321,8 @@ class Model:
         self.lattice_lds = g.buffer_init(GPU.buffer_type_LDS, lds_size, None, 16)
         self.lattice_energies = g.buffer_init(GPU.buffer_type_IO, self.size_lattice_energies, None, 16)
         self.lattice_energies_plq = g.buffer_init(GPU.buffer_type_IO, self.size_lattice_energies_plq, None, 16)
+        if self.get_actions_diff:  # suncl.cpp:3973-3978
+            self.lattice_action_diff = {a: g.buffer_init(GPU.buffer_type_IO, self.size_lattice_energies, None, 16) for a in "xyz"}
         if self.PL_level > 0:
             self.lattice_polyakov_loop = g.buffer_init(GPU.buffer_type_IO, self.size_lattice_polyakov_loop, None, 16)
         if self.PL_level > 2:
@@ -540,6 +553,18 @@ class Model:
                 g.kernel_init_buffer(self.sun_polyakov_reduce_id, b)
             self.argument_polyakov_index = g.kernel_init_constant(
                 self.sun_polyakov_reduce_id, [size_p, offset_p, self.lattice_polyakov_loop_size, 0])
+        if self.get_actions_diff:  # suncl.cpp:3440-3490
+            self.sun_action_diff_id, self.sun_action_diff_reduce_id, self.argument_action_diff_index = {}, {}, {}
+            for a in "xyz":
+                k = g.kernel_init(f"lattice_action_diff_{a}", 1, [self.lattice_action_size], [wg])
+                for b in (self.lattice_table, self.lattice_measurement, self.lattice_parameters, self.lattice_lds):
+                    g.kernel_init_buffer(k, b)
+                r = g.kernel_init(f"reduce_action_diff_{a}_double2", 1, [wg], [wg])
+                for b in (self.lattice_measurement, self.lattice_action_diff[a], self.lattice_lds):
+                    g.kernel_init_buffer(r, b)
+                sparam = [int(math.ceil(self.lattice_action_size / g.kernel_get_worksize(self.sun_measurement_id))), self.lattice_energies_size, 0, 0]
+                self.argument_action_diff_index[a] = g.kernel_init_constant(r, sparam)
+                self.sun_action_diff_id[a], self.sun_action_diff_reduce_id[a] = k, r
         if self.PL_level > 2:      # suncl.cpp:3590-3644
             self.sun_polyakov_diff_id, self.sun_polyakov_diff_reduce_id, self.argument_polyakov_diff_index = {}, {}, {}
             for a in "xyz":
@@ -568,6 +593,11 @@ class Model:
             g.kernel_run(self.sun_measurement_id)
             g.kernel_init_constant_reset(self.sun_measurement_reduce_id, self.ITER_counter, self.argument_measurement_index)
             g.kernel_run(self.sun_measurement_reduce_id)
+        if self.get_actions_diff:  # suncl.cpp:5284-5310
+            for a in "xyz":
+                g.kernel_run(self.sun_action_diff_id[a])
+                g.kernel_init_constant_reset(self.sun_action_diff_reduce_id[a], self.ITER_counter, self.argument_action_diff_index[a])
+                g.kernel_run(self.sun_action_diff_reduce_id[a])
         if self.PL_level > 0:
             g.kernel_run(self.sun_clear_measurement_id)
             g.kernel_run(self.sun_polyakov_id)
@@ -623,19 +653,29 @@ class Model:
             g.kernel_run(self.sun_init_id)
         self._measure()
         self.ITER_counter += 1
+        if not self.turnoff_config_save:
+            self.lattice_save_state()      # suncl.cpp:5342
+
+    def _timed_save(self):
+        """suncl.cpp:5383-5387, 5488-5492: a state file every write_lattice_state_every_secs seconds"""
+        if not self.turnoff_config_save and time.time() - self._last_save > self.write_lattice_state_every_secs:
+            self.lattice_save_state()
+            self._last_save = time.time()
 
     def lattice_simulate(self):
         g = self.GPU0
-        t0 = time.time()
+        t0 = self._last_save = time.time()
         self.lattice_start()
         for _ in range(self.NAV_counter, self.NAV):
             self.lattice_sweep()
             self.NAV_counter += 1
+            self._timed_save()
         for _ in range(self.ITER_counter, self.ITER):
             for _ in range(self.NITER):
                 self.lattice_sweep()
             self._measure()
             self.ITER_counter += 1
+            self._timed_save()
         g.synchronize()
         self.elapsed = time.time() - t0
         if not self.turnoff_config_save:
@@ -690,6 +730,16 @@ class Model:
                 o = self.lattice_polyakov_loop_size
                 A[f"PL_{a.upper()}"] = [self._series(e[i * o: i * o + self.ITER, 0].copy(), pden_slice(n)) for i in range(n)]
                 A[f"PL_{a.upper()}_im"] = [self._series(e[i * o: i * o + self.ITER, 1].copy(), pden_slice(n)) for i in range(n)]
+        if self.get_actions_diff:  # suncl.cpp:1376-1481: slice i of an axis at [i * lattice_energies_size + iteration], / (transverse volume * 3)
+            full = self.lattice_full_size
+            vol = full[0] * full[1] * full[2] * full[3]
+            for ax, a in enumerate("xyz"):
+                e = g.buffer_map(self.lattice_action_diff[a], np.float64).reshape(-1, 2)
+                o, den_a = self.lattice_energies_size, float(vol // full[ax] * 3)
+                s_ = [self._series(e[i * o: i * o + self.ITER, 0].copy(), den_a) for i in range(full[ax])]
+                t_ = [self._series(e[i * o: i * o + self.ITER, 1].copy(), den_a) for i in range(full[ax])]
+                A[f"S_diff_{a.upper()}_s"], A[f"S_diff_{a.upper()}_t"] = s_, t_
+                A[f"S_diff_{a.upper()}"] = [self._joint(x, y) for x, y in zip(s_, t_)]
         if self.get_wilson_loop:   # suncl.cpp:1606-1612
             w = g.buffer_map(self.lattice_wilson_loop, np.float64)[: self.ITER]
             A["Wilson_loop"] = self._series(w.copy(), den)
@@ -739,6 +789,14 @@ class Model:
                 if c in A:
                     f.write(f" Mean {c:20s}: {A[c]['mean_value']: 16.13e}\n")
                     f.write(f" Variance {c:16s}: {A[c]['variance']: 16.13e}\n")
+            if self.get_actions_diff:      # suncl.cpp:1753-1791
+                f.write(" ***************************************************\n")
+                f.write("Differentiated S data (#, S_total, S_variance):\n")
+                for ax, a in enumerate("XYZ"):
+                    n = self.lattice_full_size[ax]
+                    f.write(f"\n{a}              " + "".join(f"{i:2d}                   " for i in range(n)))
+                    f.write("\nS             " + "".join(f"{A[f'S_diff_{a}'][i]['mean_value']: 16.13e} " for i in range(n)))
+                    f.write("\nS_variance    " + "".join(f"{A[f'S_diff_{a}'][i]['variance']: 16.13e} " for i in range(n)) + "\n")
             f.write(" ***************************************************\n")
             f.write(" Data fields:\n")
             f.write("    #,  " + "".join(f"{c:<21s} " for c in cols) + "\n")

@@ -48,9 +48,11 @@ def reference_run(tmp, cfg, state=None):
     args = [BIN, "init.dat"] + ([state] if state else [])
     r = subprocess.run(args, cwd=tmp, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and "state driver completed" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
-    files = [f for f in glob.glob(os.path.join(tmp, "su*-*.qcg")) if os.path.basename(f) != (state or "")]
-    assert len(files) == 1, files
-    return np.fromfile(files[0], dtype=np.uint8)
+    # the reference saves after every iteration (suncl.cpp:5342) under a name with one-second resolution: the newest file is the final state
+    files = sorted((f for f in glob.glob(os.path.join(tmp, "su*-*.qcg")) if os.path.basename(f) != (state or "")),
+                   key=lambda f: (os.path.getmtime(f), f))
+    assert files, os.listdir(tmp)
+    return np.fromfile(files[-1], dtype=np.uint8)
 
 
 def mirror_model(cfg, fused=False):
@@ -132,3 +134,38 @@ def test_continued_run_equals_uninterrupted_run(tmp_path, group, ints, prng, bet
             with_iter(part, 9, str(d / "state.qcg"))
             mcont, _ = mirror_run(str(d), cfg, state=str(d / "state.qcg"))
             same_but_init_word(full, mcont)
+
+
+def test_action_slices_through_the_reference_host(tmp_path):
+    """model::get_actions_diff is one more switch of the reference without an init.dat key (QCDGPU.cpp:218); the state driver sets it from
+    the environment.  The reference's host code then sizes the buffers, launches lattice_action_diff_{x,y,z} / reduce_action_diff_* and
+    prints "Differentiated S data" with its own analysis (suncl.cpp:1376-1481, 1753-1791): its per-slice means must be the mirror's."""
+    import re
+    if not os.path.exists(BIN):
+        pytest.skip("integration/_build/QCDGPU_b200_ckpt not built")
+    cfg = dict(group=3, ls=8, lt=4, iter=5, beta=6.0, nav=1, ints=0, prng="RANLUX3", phi=0.0, pl=1)
+    d = tmp_path / "ref"
+    os.makedirs(d)
+    (d / "init.dat").write_text(INIT.format(**cfg))
+    r = subprocess.run([BIN, "init.dat"], cwd=d, capture_output=True, text=True, timeout=600, env=dict(os.environ, QCDGPU_ACTIONS_DIFF="1"))
+    assert r.returncode == 0 and "state driver completed" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
+    out = sorted(glob.glob(str(d / "su3-*.txt")))
+    assert out
+    text = open(out[-1]).read()
+    block = text[text.index("Differentiated S data"):]
+    ref = {}
+    for axis in "XYZ":
+        mm = re.search(rf"\n{axis} .*\nS\s+(.*)\nS_variance\s+(.*)\n", block)
+        ref[axis] = (np.array(mm.group(1).split(), dtype=float), np.array(mm.group(2).split(), dtype=float))
+    m = mirror_model(cfg)
+    m.get_actions_diff = True
+    m.lattice_init()
+    m.lattice_simulate()
+    A = m.lattice_analysis()
+    for axis in "XYZ":
+        mean = np.array([x["mean_value"] for x in A[f"S_diff_{axis}"]])
+        var = np.array([x["variance"] for x in A[f"S_diff_{axis}"]])
+        assert ref[axis][0].size == 8
+        np.testing.assert_allclose(mean, ref[axis][0], rtol=1e-11)
+        np.testing.assert_allclose(var, ref[axis][1], rtol=1e-7, atol=1e-16)
+    m.close()

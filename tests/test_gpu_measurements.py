@@ -183,3 +183,40 @@ def test_measurement_kernels_write_every_slot_their_reducer_sums():
     for a, b in zip(clean, got):
         np.testing.assert_array_equal(a, b)
     m.close()
+
+
+@pytest.mark.parametrize("sun,dims,precision,phi,omega", [
+    (3, (8, 8, 8, 4), 1, 0.0, 0.0), (3, (6, 6, 6, 4), 1, 0.7, 0.3), (2, (8, 8, 8, 6), 1, 3.0, 0.0), (3, (4, 4, 4, 4), 0, 0.0, 0.0)])
+def test_action_slices_match_numpy(sun, dims, precision, phi, omega):
+    """lattice_action_diff_{x,y,z} + reduce_action_diff_*_double2 (sun_measurements_cl.cl:186-706): the site action
+    beta/N (N - Re Tr plaquette) of the six plaquettes that start at a site, summed per x / y / z slice, against numpy on the same links;
+    6^3 x 4 pads a transverse extent from 6 to PLK = 32."""
+    m = make_model(sun, dims, precision, phi, omega, PL_level=0, get_actions_diff=True)
+    m.lattice_simulate()
+    A = m.lattice_analysis()
+    U = links(m)
+    N, bet = sun, m.BETA / sun
+    s_spat = np.zeros(dims)
+    s_temp = np.zeros(dims)
+    for a in range(4):
+        for b in range(a + 1, 4):
+            P = U[..., a, :, :] @ shift(U[..., b, :, :], a) @ dag(shift(U[..., a, :, :], b)) @ dag(U[..., b, :, :])
+            s = bet * (N - np.trace(P, axis1=-2, axis2=-1).real)
+            if b == 3:
+                s_temp += s
+            else:
+                s_spat += s
+    tol = 1e-11 if precision == 1 else 5e-5
+    last = m.ITER - 1
+    vol = dims[0] * dims[1] * dims[2] * dims[3]
+    for ax, name in enumerate("XYZ"):
+        den = vol // dims[ax] * 3
+        other = tuple(a for a in range(4) if a != ax)
+        for kind, field in (("s", s_spat), ("t", s_temp)):
+            per = field.sum(axis=other) / den
+            got = np.array([x["data"][last] for x in A[f"S_diff_{name}_{kind}"]])
+            assert np.abs(got - per).max() <= 10 * tol * np.abs(per).max(), (name, kind, got, per)
+        # the slices add up to the plain action of the same configuration (lattice_measurement, denominator full_site * 3)
+        total = sum(x["data"][last] for x in A[f"S_diff_{name}_s"]) * den
+        assert rel(total, A["S_spat"]["data"][last] * vol * 3, 100 * tol)
+    m.close()
