@@ -58,7 +58,7 @@ def test_program_options_are_validated_like_compile_errors():
     with pytest.raises(QcdGpuError, match="SUN=4"):
         g.program_create(None, "-D SUN=4 -D ND=4 -D N1=4 -D N2=4 -D N3=4 -D N4=4")
     with pytest.raises(QcdGpuError, match="not implemented"):
-        g.kernel_init("lattice_action_diff_x", 1, [64], None)
+        g.kernel_init("lattice_measurement_WLx0", 1, [64], None)      # BIGLAT Wilson-loop family
     with pytest.raises(QcdGpuError, match="RL_skip=100"):
         g.program_create(None, "-D RL_skip=100")
         g.kernel_init("ranlux", 1, [64], None)
