@@ -539,3 +539,29 @@ def test_repeated_produce_is_one_jump(n):
     for a, b in zip(res[0][:3], res[1][:3]):
         np.testing.assert_array_equal(a.view(np.uint8), b.view(np.uint8))
     assert res[0][3] >= n + 1 and res[1][3] <= 3       # n + 1 producer launches against one jump + one producer
+
+
+def test_mixed_precision_is_single_storage_with_double_sums():
+    """BASELINE config 3 (finite temperature, twist, mixed precision) at test size.  PRECISION = 2 in the reference's kernels is float4
+    links and float update arithmetic with the measurement sums in double (model.cl / complex.h typedefs),
+    which is what PRECISION = 0 computes too: the two runs must agree bit for bit, lattice and observables, and the observables must be
+    the fp64 re-measurement of the fp32 table (checker) to fp64 accuracy."""
+    runs = []
+    for prec in (0, 2):
+        m = make_model(3, (8, 8, 8, 4), prec, ints=0, prng="RANLUX3", fused=True, iters=3, beta=5.7, phi=3.0, pl=2)
+        m.lattice_simulate()
+        A = m.lattice_analysis()
+        runs.append((m.table_numpy(), {k: np.array(A[k]["data"]) for k in ("Plq_spat", "Plq_temp", "S_total", "Polyakov_loop", "Polyakov_loop_im")}))
+        if prec == 2:
+            L = make_oracle(m)
+            L.table[:] = m.table_numpy()
+            ps, pt = L.measure_plq()
+            re, im, _, _ = L.polyakov()
+            V = L.sites
+            np.testing.assert_allclose([A["Plq_spat"]["data"][-1], A["Plq_temp"]["data"][-1]], [ps / (3 * V), pt / (3 * V)], rtol=5e-5)
+            np.testing.assert_allclose(A["Polyakov_loop"]["data"][-1], re / (8 * 8 * 8 * 3), rtol=5e-5, atol=1e-7)
+        m.close()
+    assert runs[0][0].dtype == np.float32 and runs[1][0].dtype == np.float32
+    np.testing.assert_array_equal(runs[0][0].view(np.uint8), runs[1][0].view(np.uint8))
+    for k in runs[0][1]:
+        np.testing.assert_array_equal(runs[0][1][k], runs[1][1][k])
