@@ -161,7 +161,10 @@ B.close(); dist.destroy_process_group()
 '''
 
 
-def test_nccl_two_gpus_gid(tmp_path):
+@pytest.mark.parametrize("direct", ["1", "0"])
+def test_nccl_two_gpus_gid(tmp_path, direct):
+    """Two processes, NCCL send/recv of the boundary slices after every pass -- straight from / into the link tables (direct) or
+    staged through packed buffers -- against the reference's CPU_RUN table of the same deterministic (INTS = 2) run."""
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
@@ -170,7 +173,7 @@ def test_nccl_two_gpus_gid(tmp_path):
     script.write_text(NCCL_WORKER)
     s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
-                        "--master-port", str(port), str(script)], capture_output=True, text=True, env=dict(os.environ, QCD_ROOT=ROOT), timeout=600)
+                        "--master-port", str(port), str(script)], capture_output=True, text=True, env=dict(os.environ, QCD_ROOT=ROOT, QCDGPU_HALO_DIRECT=direct), timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
     rows = json.loads([l for l in r.stdout.splitlines() if l.startswith("ROWS ")][0][5:])
     np.testing.assert_allclose(np.array(rows), np.array(gold["rows"]), rtol=5e-6)
