@@ -137,6 +137,9 @@ int   qgpu_set_stream(qgpu* h, void* cuda_stream);
  * Used by the BigLattice path to update the two boundary slices first and the interior while halos travel.
  * A restricted launch always reads the PRN buffer (the generators advance once per pass, for all sites). */
 int   qgpu_kernel_set_x_range(qgpu* h, int kernel_id, int x_first, int x_count);
+/* The same with the slices x_first + i * x_stride, i < x_count: x_stride = Nx - 1, x_count = 2 updates BOTH boundary slices of a part in
+ * one launch (two one-slice launches cost about 0.1 ms of ramp-up and tail each at 64^3 sites per slice). */
+int   qgpu_kernel_set_x_range_strided(qgpu* h, int kernel_id, int x_first, int x_count, int x_stride);
 /* raw device pointer of a buffer (halo exchange, interop) and raw stream handle (cudaStream_t) */
 void* qgpu_buffer_device_ptr(qgpu* h, int buffer_id);
 void* qgpu_stream(qgpu* h);

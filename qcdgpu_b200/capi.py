@@ -49,7 +49,7 @@ EXPORTS = [
     "qgpu_kernel_get_execution_time", "qgpu_buffer_init", "qgpu_buffer_write", "qgpu_buffer_map",
     "qgpu_buffer_map_range", "qgpu_buffer_unmap", "qgpu_buffer_kill", "qgpu_buffer_size_bytes",
     "qgpu_buffer_size_align", "qgpu_buffer_size_align_step", "qgpu_set_async", "qgpu_synchronize",
-    "qgpu_set_fused_prng", "qgpu_set_tile_x", "qgpu_set_fold_reunitarisation", "qgpu_profile_collect", "qgpu_set_stream", "qgpu_kernel_set_x_range", "qgpu_buffer_device_ptr", "qgpu_stream", "qgpu_timer_start",
+    "qgpu_set_fused_prng", "qgpu_set_tile_x", "qgpu_set_fold_reunitarisation", "qgpu_profile_collect", "qgpu_set_stream", "qgpu_kernel_set_x_range", "qgpu_kernel_set_x_range_strided", "qgpu_buffer_device_ptr", "qgpu_stream", "qgpu_timer_start",
     "qgpu_timer_stop", "qgpu_launch_count", "qgpu_update_kernel_registers", "qgpu_halo_copy",
     "qgpu_halo_pack", "qgpu_halo_unpack", "qgpu_halo_bytes", "qgpu_host_srand", "qgpu_host_rand_fill",
     "qgpu_ranlux_jump_table",
@@ -126,6 +126,7 @@ def load(build_if_missing: bool = True):
     L.qgpu_profile_collect.argtypes = [vp]
     L.qgpu_set_stream.argtypes = [vp, vp]
     L.qgpu_kernel_set_x_range.argtypes = [vp, ci, ci, ci]
+    L.qgpu_kernel_set_x_range_strided.argtypes = [vp, ci, ci, ci, ci]
     L.qgpu_buffer_device_ptr.argtypes = [vp, ci]
     L.qgpu_buffer_device_ptr.restype = vp
     L.qgpu_stream.argtypes = [vp]
@@ -307,8 +308,8 @@ class GPU:
     def set_stream(self, cuda_stream: int):
         self._chk(self.L.qgpu_set_stream(self.h, C.c_void_p(cuda_stream)), "set_stream")
 
-    def kernel_set_x_range(self, kid: int, x_first: int, x_count: int):
-        self._chk(self.L.qgpu_kernel_set_x_range(self.h, kid, x_first, x_count), "kernel_set_x_range")
+    def kernel_set_x_range(self, kid: int, x_first: int, x_count: int, x_stride: int = 1):
+        self._chk(self.L.qgpu_kernel_set_x_range_strided(self.h, kid, x_first, x_count, x_stride), "kernel_set_x_range")
 
     def synchronize(self):
         self._chk(self.L.qgpu_synchronize(self.h), "synchronize")

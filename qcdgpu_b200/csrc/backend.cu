@@ -72,6 +72,7 @@ struct Kernel {
     size_t local0 = 0;
     bool local_given = false;
     int x_first = 0, x_count = -1;   // update kernels: x-range of the launch inside the updated region (-1 = all)
+    int x_stride = 1;                // distance between the slices of the range
     std::vector<Arg> args;
     // profiling (GPU_debug.profiling)
     double t_sum = 0, t_sq = 0; int starts = 0;
@@ -219,7 +220,7 @@ Geom make_geom(const ProgramCfg& c, int tile_override = -1) {
     g.prngstep = c.prngstep ? c.prngstep : g.sites / 2;                     // model.cl:126-128
     g.left_sites = c.left_sites; g.full_sites = c.full_sites;
     g.nhit = (uint32_t)c.nhit; g.nhitpar = (uint32_t)c.nhitpar;
-    g.upd_x0 = 0; g.upd_nx = c.biglat ? c.n1 - 2 : c.n1;
+    g.upd_x0 = 0; g.upd_nx = c.biglat ? c.n1 - 2 : c.n1; g.upd_xstride = 1;
     if (c.biglat && g.n234) { g.tw_lo = c.left_sites / g.n234; g.tw_hi = c.full_sites / g.n234; }
     { static int dbg = -1; if (dbg < 0) { const char* e = getenv("QCDGPU_DEBUG_SKIP"); dbg = e ? atoi(e) : 0; } g.debug_skip = (uint32_t)dbg; }
     // L2 tiling (lattice.cuh remap_gid): worthwhile once three x-slices of all links no longer fit the L2
@@ -459,13 +460,19 @@ int launch_kernel(qgpu* h, int kid) {
             a.geom.fold_gs = (h->fold_gs && c.sun == 3) ? 1u : 0u;
             const uint32_t nx_all = a.geom.upd_nx;
             if (k.x_count >= 0) {
-                if ((uint32_t)(k.x_first + k.x_count) > a.geom.upd_nx) return fail(h, "kernel %s: x-range [%d,+%d) outside the %u updated slices", k.name.c_str(), k.x_first, k.x_count, a.geom.upd_nx);
+                if (k.x_stride < 1 || (k.x_count > 0 && (uint64_t)k.x_first + (uint64_t)(k.x_count - 1) * k.x_stride >= a.geom.upd_nx) || k.x_first < 0)
+                    return fail(h, "kernel %s: x-slices %d + i * %d, i < %d, outside the %u updated slices", k.name.c_str(), k.x_first, k.x_stride, k.x_count, a.geom.upd_nx);
+                if (k.x_stride == 1 && (uint32_t)(k.x_first + k.x_count) > a.geom.upd_nx) return fail(h, "kernel %s: x-range [%d,+%d) outside the %u updated slices", k.name.c_str(), k.x_first, k.x_count, a.geom.upd_nx);
                 a.geom.upd_x0 = (uint32_t)k.x_first; a.geom.upd_nx = (uint32_t)k.x_count;
                 a.geom.nthreads = a.geom.upd_nx * (a.geom.n234 / 2);
-                if (a.geom.tile_x >= a.geom.upd_nx) a.geom.tile_x = 0;
+                a.geom.upd_xstride = (uint32_t)k.x_stride;
+                if (a.geom.tile_x >= a.geom.upd_nx || k.x_stride != 1) a.geom.tile_x = 0;
                 if (a.geom.nthreads == 0) break;
             }
-            if (a.geom.fold_gs) gs_cover_mark(h, buf_id(k, 0), k.odd, k.dir, nx_all, a.geom.upd_x0, a.geom.upd_nx);
+            if (a.geom.fold_gs) {
+                if (a.geom.upd_xstride == 1u) gs_cover_mark(h, buf_id(k, 0), k.odd, k.dir, nx_all, a.geom.upd_x0, a.geom.upd_nx);
+                else for (uint32_t i = 0; i < a.geom.upd_nx; i++) gs_cover_mark(h, buf_id(k, 0), k.odd, k.dir, nx_all, a.geom.upd_x0 + i * a.geom.upd_xstride, 1u);
+            }
             const uint32_t full_threads = (c.biglat ? c.n1 - 2 : c.n1) * (a.geom.n234 / 2);
             UpdateLaunchFn fn = get_update_launcher(c.sun, prec, k.dir);
             if (!fn) return fail(h, "kernel %s: no CUDA instantiation for SUN=%d PRECISION=%d", k.name.c_str(), c.sun, c.precision);
@@ -872,13 +879,15 @@ int qgpu_set_stream(qgpu* h, void* stream) {
     h->stream = (cudaStream_t)stream;
     return 0;
 }
-int qgpu_kernel_set_x_range(qgpu* h, int kid, int x_first, int x_count) {
+int qgpu_kernel_set_x_range_strided(qgpu* h, int kid, int x_first, int x_count, int x_stride) {
     if (!valid_kernel(h, kid)) return fail(h, "bad kernel id %d", kid);
     Kernel& k = h->kernels[kid];
     if (k.kind != K_UPDATE && k.kind != K_OVERRELAX) return fail(h, "kernel %s has no x-range", k.name.c_str());
-    k.x_first = x_first; k.x_count = x_count;
+    if (x_stride < 1) return fail(h, "kernel %s: x-stride %d", k.name.c_str(), x_stride);
+    k.x_first = x_first; k.x_count = x_count; k.x_stride = x_stride;
     return 0;
 }
+int qgpu_kernel_set_x_range(qgpu* h, int kid, int x_first, int x_count) { return qgpu_kernel_set_x_range_strided(h, kid, x_first, x_count, 1); }
 uint64_t qgpu_launch_count(qgpu* h) { return h->launches; }
 void* qgpu_stream(qgpu* h) { return (void*)h->stream; }
 

@@ -36,6 +36,7 @@ struct Geom {
     uint32_t fold_gs;             // SU(3): reunitarise the updated link a second time before it is stored -- what the sweep's separate
                                   // lattice_GramSchmidt pass would do to it later; the backend then skips that pass (backend.cu, gs_cover)
     uint32_t upd_x0, upd_nx;      // x-range of this launch inside the updated region (halo/interior split); nthreads = upd_nx*N4*N2/2*N3
+    uint32_t upd_xstride;         // distance between the launch's slices (1; Nx - 1 for the two boundary slices in one launch; tile_x == 0 then)
 };
 
 struct Coord { uint32_t x, y, z, t; };
@@ -73,7 +74,11 @@ __device__ __forceinline__ uint32_t parity_gid(const Geom& g, uint32_t GID, bool
 // changes, the site's GID (hence its PRNG instance / PRN slots) does not.
 __device__ __forceinline__ uint32_t remap_gid(const Geom& g, uint32_t k) {
     const uint32_t P = (g.n2 >> 1) * g.n3;                 // threads per (x,t) plane
-    if (g.tile_x == 0) return k + g.upd_x0 * g.n4 * P;     // reference order, shifted to the launch's x-range
+    if (g.tile_x == 0) {                                   // reference order, shifted to the launch's x-range
+        if (g.upd_xstride == 1u) return k + g.upd_x0 * g.n4 * P;
+        const uint32_t XP = g.n4 * P, xi = k / XP;
+        return (k - xi * XP) + (g.upd_x0 + xi * g.upd_xstride) * XP;
+    }
     const uint32_t chunk = g.tile_x * g.n4 * P;
     const uint32_t xc = k / chunk;
     uint32_t r = k - xc * chunk;
@@ -94,9 +99,9 @@ __device__ __forceinline__ SiteId thread_site(const Geom& g, uint32_t k, bool od
     const uint32_t H = g.n2 >> 1, P = H * g.n3;              // threads per y-row, per (x,t) plane
     uint32_t x, t, yz;
     if (g.tile_x == 0) {
-        const uint32_t G0 = k + g.upd_x0 * g.n4 * P, XP = g.n4 * P;
-        x = G0 / XP;
-        const uint32_t r = G0 - x * XP;
+        const uint32_t XP = g.n4 * P, xi = k / XP;
+        x = g.upd_x0 + xi * g.upd_xstride;
+        const uint32_t r = k - xi * XP;
         t = r / P;
         yz = r - t * P;
     } else {
