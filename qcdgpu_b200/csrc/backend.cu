@@ -129,6 +129,7 @@ struct qgpu {
     std::vector<Buffer> buffers;
     int active_program = 0;
     uint64_t launches = 0;
+    void* split_scratch = nullptr; size_t split_scratch_bytes = 0;   // QCDGPU_SPLIT=1 (experiment): staple sums between the two kernels of a pass
     uint32_t* ws_counters = nullptr;     // ticket / exit counters of the persistent update kernel (update.cuh), zeroed once: the kernel re-arms them
     qgpu() {
         programs.resize(1); kernels.resize(1); buffers.resize(1); memset(&info, 0, sizeof(info));
@@ -513,6 +514,19 @@ int launch_kernel(qgpu* h, int kid) {
                             else { h->ws_counters = nullptr; (void)cudaGetLastError(); }
                         }
                         a.ws_counters = h->ws_counters;
+                        {   // QCDGPU_SPLIT=1 (experiment): scratch for the staple sums and links of this launch
+                            static int split_env = -1;
+                            if (split_env < 0) { const char* e = getenv("QCDGPU_SPLIT"); split_env = e ? atoi(e) : 0; }
+                            if (split_env) {
+                                const size_t need = (size_t)a.geom.nthreads * 9 * 2 * (prec ? 8 : 4);
+                                if (h->split_scratch_bytes < need) {
+                                    if (h->split_scratch) cudaFree(h->split_scratch);
+                                    h->split_scratch = nullptr; h->split_scratch_bytes = 0;
+                                    if (cudaMalloc(&h->split_scratch, need) == cudaSuccess) h->split_scratch_bytes = need; else (void)cudaGetLastError();
+                                }
+                                a.split_scratch = h->split_scratch; a.split_scratch_bytes = h->split_scratch_bytes;
+                            }
+                        }
                     }
                     if (k.x_count < 0) { pbuf.pending_produce = 0; pbuf.pending_partly_fused = false; }
                     else { pbuf.pending_partly_fused = true; pbuf.swap_seed_buf = swap_seed; swap_seed = 0; }   // the other x-ranges of this pass follow
@@ -941,6 +955,7 @@ int qgpu_device_finalize(qgpu* h, int error_code) {
         h->buffers[i] = Buffer();
     }
     if (h->ws_counters) { cudaFree(h->ws_counters); h->ws_counters = nullptr; }
+    if (h->split_scratch) { cudaFree(h->split_scratch); h->split_scratch = nullptr; h->split_scratch_bytes = 0; }
     for (auto& t : h->timeline) { cudaEventDestroy(t.e0); cudaEventDestroy(t.e1); }
     for (cudaEvent_t e : h->event_pool) cudaEventDestroy(e);
     h->timeline.clear(); h->event_pool.clear();

@@ -38,6 +38,7 @@ struct UpdateArgs {
     const TensorMapBlob* tmap;   // tensor maps over the link table (4 reals, ROWSIZE sites, planes), or null: TMA staging of the staple links;
     const TensorMapBlob* tmap1;  // box = 32 sites of one parity x 3 planes, and 1 site x 3 planes
     uint32_t* ws_counters;       // two zeroed words owned by the handle: ticket and exit counters of the persistent kernel (it re-arms them itself)
+    void* split_scratch; size_t split_scratch_bytes;   // QCDGPU_SPLIT=1: staple sums + links between staple_kernel_tma and heatbath_kernel_rlx
 };
 typedef cudaError_t (*UpdateLaunchFn)(const UpdateArgs&, cudaStream_t);
 // [sun-2][prec][mu]

@@ -1453,6 +1453,91 @@ overrelax_kernel_tma(R* __restrict__ table, const __grid_constant__ Geom g, int 
     store3<R, MU>(table, g, site.gindex, U.e[0], U.e[1]);
 }
 
+// ---------------------------------------------------------------- EXPERIMENT: the pass as two kernels (build with -DQCD_SPLIT_EXPERIMENT, run with QCDGPU_SPLIT=1)
+// A warp of the fused kernel is bound by its own dependent chains at three warps per scheduler, and 168 registers allow no more.  Cut
+// between staples and heat bath, each half needs fewer: staple_kernel_tma (TMA-staged links -> the staple sum S of every updated link,
+// 9 complex numbers, to a scratch buffer: plane e of launch thread k at scratch[e * nthreads + k]) and heatbath_kernel_rlx (generator
+// phase as in update_kernel_rlx, then S from the scratch buffer and the link itself from the table, Cabibbo-Marinari, store).  Same functions on the same values:
+// bit-identical lattices.  Costs 288 B of extra traffic per update.
+// MEASURED, NOT SHIPPED (64^4 fp64): 32.7-33.3 against 28.1 ms per sweep.  staple_kernel_tma 1.87 ms at 4 blocks per SM with the issue
+// slots 31 % busy and 8.8 GB of DRAM traffic = 4.7 TB/s, 73 % of the measured copy bandwidth: the staple phase on its own is bound by
+// HBM; heatbath_kernel_rlx 2.10 ms (128 registers, 184 B of spills; 168 registers / 3 blocks per SM: the same).  The fused kernel's
+// 3.43 ms is less than the sum because its generator and Cabibbo-Marinari phases run under the staple phase's memory traffic.
+#ifdef QCD_SPLIT_EXPERIMENT
+#ifndef QCD_SPLIT_MINBLOCKS
+#define QCD_SPLIT_MINBLOCKS 4
+#endif
+#ifndef QCD_SPLIT_B_MINBLOCKS
+#define QCD_SPLIT_B_MINBLOCKS 4
+#endif
+template <typename R> struct Pair { R a, b; };
+template <typename R> __device__ __forceinline__ void st_pair(R* p, R a, R b);
+template <> __device__ __forceinline__ void st_pair<double>(double* p, double a, double b) { asm volatile("st.global.v2.f64 [%0], {%1, %2};" :: "l"(p), "d"(a), "d"(b) : "memory"); }
+template <> __device__ __forceinline__ void st_pair<float>(float* p, float a, float b) { asm volatile("st.global.v2.f32 [%0], {%1, %2};" :: "l"(p), "f"(a), "f"(b) : "memory"); }
+template <typename R> __device__ __forceinline__ Cx<R> ld_pair(const R* p);
+template <> __device__ __forceinline__ Cx<double> ld_pair<double>(const double* p) { Cx<double> c; asm volatile("ld.global.nc.v2.f64 {%0, %1}, [%2];" : "=d"(c.re), "=d"(c.im) : "l"(p)); return c; }
+template <> __device__ __forceinline__ Cx<float> ld_pair<float>(const float* p) { Cx<float> c; asm volatile("ld.global.nc.v2.f32 {%0, %1}, [%2];" : "=f"(c.re), "=f"(c.im) : "l"(p)); return c; }
+
+template <typename R, int MU, bool TBC>
+__global__ void __launch_bounds__(kUpdateThreads, (QCD_SPLIT_MINBLOCKS * 128) / kUpdateThreads)
+staple_kernel_tma(const R* __restrict__ table, const R* __restrict__ params, const __grid_constant__ Geom g, int odd,
+                  const __grid_constant__ TensorMapBlob tmap, const __grid_constant__ TensorMapBlob tmap1, R* __restrict__ scratch) {
+    extern __shared__ __align__(128) uint4 prn_smem[];
+    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= g.nthreads) return;
+    const SiteId site = thread_site(g, k, odd != 0);
+    const uint32_t base = (uint32_t)__cvta_generic_to_shared(prn_smem), warp = threadIdx.x >> 5;
+    constexpr uint32_t NW = kUpdateThreads / 32, RING = kTmaK * tma_slot_bytes<R>();
+    Su3StageTma<R, MU, TBC> stage;
+    stage.begin(base + warp * RING, base + NW * RING + warp * (kTmaK * 128u), base + NW * (RING + kTmaK * 128u) + warp * (kTmaK * 8u),
+                &tmap, &tmap1, table, g, site.gindex, site.p);
+    const Twist<R> tw = make_twist<3, R, TBC>(params);
+    M3<R> S;
+    M3r2<R> m0;
+    stage.staple_and_link(g, tw, S, m0);
+    R* out = scratch + 2 * size_t(k);
+    const size_t plane = 2 * size_t(g.nthreads);
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+#pragma unroll
+        for (int j = 0; j < 3; j++) st_pair<R>(out + (3 * i + j) * plane, S.e[i][j].re, S.e[i][j].im);
+}
+template <typename R, int MU, bool TBC, int NSKIP>
+__global__ void __launch_bounds__(kUpdateThreads, (QCD_SPLIT_B_MINBLOCKS * 128) / kUpdateThreads)
+heatbath_kernel_rlx(R* __restrict__ table, const R* __restrict__ params, const __grid_constant__ Geom g, int odd,
+                    const uint32_t* rtable, uint32_t* rtable_out, uint32_t instances, uint32_t samples, uint32_t keep,
+                    const uint32_t* __restrict__ jump, const R* __restrict__ scratch) {
+    extern __shared__ __align__(128) uint4 prn_smem[];
+    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= g.nthreads) return;
+    const SiteId site = thread_site(g, k, odd != 0);
+    const uint32_t GID = site.GID;
+    unsigned long long converted[1] = { 0ull };
+    RanluxPk<1> r;
+    uint32_t left = r.load(0, rtable, instances, GID);
+    {
+        uint4* const out[1] = { prn_smem + threadIdx.x };
+        r.pass(left, samples, keep, out, kUpdateThreads, converted, [] {}, jump);
+        r.store(0, rtable_out, instances, GID, left);
+    }
+    const R beta = params[0];
+    InvBeta<R>::park(params);
+    typedef PrnSmemT<NSKIP> PrnSmem;
+    PrnSmem prn(prn_smem + threadIdx.x, kUpdateThreads, converted[0], (rtable_out != rtable) ? keep : 0xffffffffu, rtable + GID, instances);
+    const R* in = scratch + 2 * size_t(k);
+    const size_t plane = 2 * size_t(g.nthreads);
+    M3<R> S;
+    M3r2<R> m0;
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+#pragma unroll
+        for (int j = 0; j < 3; j++) S.e[i][j] = ld_pair<R>(in + (3 * i + j) * plane);
+    const Twist<R> tw = make_twist<3, R, TBC>(params);
+    m0 = load3<R, MU, TBC>(table, g, site.gindex, site.p.x, tw);
+    heatbath_su3<R, MU, PrnSmem>(table, g, beta, site.gindex, m0, S, prn);
+}
+#endif  // QCD_SPLIT_EXPERIMENT
+
 // ---------------------------------------------------------------- warp-specialised persistent update kernel (RANLUX3, SU(3), TMA rows)
 // One block of 512 threads per SM for the whole pass: warp groups 0-2 are 12 "physics" warps (staples, Cabibbo-Marinari, store), warp
 // group 3 is four "generator" warps.  Generator warp q and the physics warps q, q + 4, q + 8 share a scheduler and form an independent

@@ -104,6 +104,27 @@ static cudaError_t launch_rlx(const UpdateArgs& a, cudaStream_t st) {
                                               a.prn_table, out, a.prn_instances, a.prn_samples, keep, *a.tmap, *a.tmap1, a.ws_counters);
         return cudaGetLastError();
     }
+#ifdef QCD_SPLIT_EXPERIMENT
+    // experiment (update.cuh): the pass as a staple kernel + a heat-bath kernel with the staple sums in a scratch buffer
+    static int split_env = -1;
+    if (split_env < 0) split_env = env_int("QCDGPU_SPLIT", 0);
+    if (split_env && tma_env && a.tmap && a.tmap1 && a.geom.n2 % 64u == 0u && a.geom.nthreads % 32u == 0u && a.geom.nthreads > 0u &&
+        a.split_scratch && a.split_scratch_bytes >= size_t(a.geom.nthreads) * 9 * 2 * sizeof(RealT) && out != a.prn_table) {
+        auto ka = staple_kernel_tma<RealT, INST_MU, TBC>;
+        auto kb = heatbath_kernel_rlx<RealT, INST_MU, TBC, 223>;
+        const size_t smem_a = tma_stage_bytes<RealT>();
+        static SmemConfigured configured_a, configured_b;
+        if (cudaError_t e = ensure_smem(ka, smem_a, configured_a); e != cudaSuccess) return e;
+        if (cudaError_t e = ensure_smem(kb, smem, configured_b); e != cudaSuccess) return e;
+        const uint32_t blocks = (a.geom.nthreads + kUpdateThreads - 1) / kUpdateThreads;
+        ka<<<blocks, kUpdateThreads, smem_a, st>>>(static_cast<const RealT*>(a.table), static_cast<const RealT*>(a.params), a.geom, a.odd, *a.tmap, *a.tmap1,
+                                                  static_cast<RealT*>(a.split_scratch));
+        if (cudaError_t e = cudaGetLastError(); e != cudaSuccess) return e;
+        kb<<<blocks, kUpdateThreads, smem, st>>>(static_cast<RealT*>(a.table), static_cast<const RealT*>(a.params), a.geom, a.odd, a.prn_table, out,
+                                                 a.prn_instances, a.prn_samples, keep, jump, static_cast<const RealT*>(a.split_scratch));
+        return cudaGetLastError();
+    }
+#endif
     if (tma_env && a.tmap && a.tmap1 && kUpdateThreads % 32 == 0 && a.geom.n2 % 64u == 0u && a.geom.nthreads % 32u == 0u && a.geom.nthreads > 0u) {
         auto kt = update_kernel_rlx_tma<RealT, INST_MU, TBC, 223>;
         const size_t smem_t = smem + tma_stage_bytes<RealT>();
