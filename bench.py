@@ -202,7 +202,10 @@ def native_single(args):
     clocks = ClockSampler(0)
     clocks.start()
     l0 = g.launch_count()
-    g.set_debug(profiling=2)          # an event pair per launch, recorded without waiting: per-kernel times INSIDE the timed region
+    # an event pair per launch, recorded without waiting: per-kernel times INSIDE the timed region.  Only where a launch is long against
+    # the two event records (64^4: 3.5 ms); on the small diagnostic lattices (16^4: 13 us per pass) they would be half of what is timed.
+    if V >= (1 << 20):
+        g.set_debug(profiling=2)
     g.timer_start()
     for _ in range(args.steps):
         m.lattice_sweep()
