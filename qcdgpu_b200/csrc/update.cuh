@@ -1379,8 +1379,13 @@ update_kernel_rlx(R* __restrict__ table, const R* __restrict__ params, const __g
 #endif
 }
 // update_kernel_rlx with the links of the staples staged by TMA (SU(3), full warps, N2 a multiple of 64; chosen by the launcher)
+#ifdef QCD_RLX_MAXNREG        // experiment knob: register cap of the TMA-staged kernel below what three blocks per SM allow (168)
+#define QCD_RLX_MAXNREG_ATTR __maxnreg__(QCD_RLX_MAXNREG)
+#else
+#define QCD_RLX_MAXNREG_ATTR __launch_bounds__(kUpdateThreads, (sizeof(R) == 8) ? QCD_RLX_MINBLOCKS : (4 * 128) / kUpdateThreads)
+#endif
 template <typename R, int MU, bool TBC, int NSKIP>
-__global__ void __launch_bounds__(kUpdateThreads, (sizeof(R) == 8) ? QCD_RLX_MINBLOCKS : (4 * 128) / kUpdateThreads)
+__global__ void QCD_RLX_MAXNREG_ATTR
 update_kernel_rlx_tma(R* __restrict__ table, const R* __restrict__ params, const __grid_constant__ Geom g, int odd,
                       const uint32_t* rtable, uint32_t* rtable_out, uint32_t instances, uint32_t samples, uint32_t keep,
                       const __grid_constant__ TensorMapBlob tmap, const __grid_constant__ TensorMapBlob tmap1, const uint32_t* __restrict__ jump) {
@@ -1723,5 +1728,93 @@ update_kernel_rlx_ws(R* __restrict__ table, const R* __restrict__ params, const 
         mbar_arrive(bar + 24u);
     }
 }
+
+
+// ---------------------------------------------------------------- EXPERIMENT: persistent kernel, symmetric warp groups, registers on loan
+// (build with -DQCD_SYM_EXPERIMENT, run with QCDGPU_SYM=1).  The fused kernel's time is generator phase + physics phase because a block keeps its 168 registers per thread while
+// it runs the generator, which needs 50.  Here one block of 512 threads per SM holds the whole register file and its four warp groups
+// (4 warps = 128 update threads = four y-rows) each loop over tickets on their own: generator phase at QCD_SYM_GEN_REGS registers
+// (setmaxnreg.dec), physics phase at QCD_SYM_PHYS_REGS (setmaxnreg.inc, which waits until another warp group has given registers back):
+// 3 x 136 + 104 = 512 = the launch's 128 per thread, so three warp groups can be in their physics phase while the fourth generates --
+// sixteen warps per SM instead of twelve, the generator phase under the physics phases.  Unlike update_kernel_rlx_ws no warp works for
+// another one: samples stay in the warp's own shared-memory columns, links in its own TMA ring.  Bit-identical to the other kernels.
+// MEASURED, NOT SHIPPED (64^4 fp64): 36.1-36.4 against 27.9 ms per sweep (with the jump in the generator phase 36.8).  The plan needs a
+// generator phase that takes a third of a physics phase (5 us); a warp's generator phase is one dependent chain (state load, two
+// luxury skips, the tail) of ~10 k cycles even undisturbed, and sharing a scheduler with three physics warps it takes ~10 us: the one
+// generating warp group is the bottleneck (443 tickets x 10 us = 4.4 ms per pass), as in update_kernel_rlx_ws.  Also: the four warps
+// of a group wait for each other at every setmaxnreg, physics at 136 registers is 4 % slower, 8 parked samples 2 %.
+#ifdef QCD_SYM_EXPERIMENT
+#ifndef QCD_SYM_GEN_REGS
+#define QCD_SYM_GEN_REGS 104
+#define QCD_SYM_PHYS_REGS 136
+#endif
+constexpr int kSymWarps = 16, kSymThreads = 32 * kSymWarps;
+template <typename R> __host__ __device__ constexpr size_t sym_smem_bytes(uint32_t keep) {
+    return size_t(kSymWarps) * (size_t(keep) * 32 * 16 + kTmaK * (tma_slot_bytes<R>() + 128 + 8)) + 64;
+}
+template <typename R, int MU, bool TBC, int NSKIP>
+__global__ void __launch_bounds__(kSymThreads, 1)
+update_kernel_rlx_sym(R* __restrict__ table, const R* __restrict__ params, const __grid_constant__ Geom g, int odd,
+                      const uint32_t* rtable, uint32_t* rtable_out, uint32_t instances, uint32_t samples, uint32_t keep,
+                      const __grid_constant__ TensorMapBlob tmap, const __grid_constant__ TensorMapBlob tmap1,
+                      const uint32_t* __restrict__ jump, uint32_t* counters) {
+    static_assert(NSKIP == 223, "written for RANLUX3");
+    extern __shared__ __align__(128) uint4 sym_smem[];
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u, wg = warp >> 2;
+    const uint32_t sm0 = (uint32_t)__cvta_generic_to_shared(sym_smem);
+    const uint32_t SAMP = keep * 32u * 16u, RING = kTmaK * tma_slot_bytes<R>();
+    const uint32_t o_ring = kSymWarps * SAMP, o_x = o_ring + kSymWarps * RING, o_rbar = o_x + kSymWarps * kTmaK * 128u,
+                   o_tick = o_rbar + kSymWarps * kTmaK * 8u;
+    Su3StageTma<R, MU, TBC, true> stage;
+    stage.init_ws(sm0 + o_ring + warp * RING, sm0 + o_x + warp * (kTmaK * 128u), sm0 + o_rbar + warp * (kTmaK * 8u), &tmap, &tmap1, table);
+    const R beta = params[0];
+    InvBeta<R>::park(params);
+    const Twist<R> tw = make_twist<3, R, TBC>(params);
+    const uint32_t nthreads = g.nthreads;                 // a multiple of 32 (launcher)
+    uint4* const column = sym_smem + warp * (SAMP / 16u) + lane;
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" :: "n"(QCD_SYM_GEN_REGS));
+    for (uint32_t n = 0;; n++) {
+        // the warp group's ticket: 128 consecutive update threads in launch order (so the L2 window of remap_gid stays)
+        const uint32_t slot = sm0 + o_tick + 16u * wg + 4u * (n & 1u);
+        if ((threadIdx.x & 127u) == 0u) {
+            const uint32_t t = atomicAdd(counters, 1u);
+            asm volatile("st.shared.u32 [%0], %1;" :: "r"(slot), "r"(t) : "memory");
+        }
+        asm volatile("bar.sync %0, 128;" :: "r"(1u + wg) : "memory");
+        uint32_t T;
+        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(T) : "r"(slot) : "memory");
+        if (T * 128u >= nthreads || T >= 0x01000000u) break;
+        const uint32_t kb = T * 128u + (warp & 3u) * 32u;
+        const bool active = kb < nthreads;
+        SiteId site = {};
+        unsigned long long conv[1] = { 0ull };
+        if (active) {
+            site = thread_site(g, kb + lane, odd != 0);
+            RanluxPk<1> r;
+            uint32_t left = r.load(0, rtable, instances, site.GID);
+            stage.begin_item(g, site.gindex, site.p);          // the first links travel during the generator phase
+            uint4* const out[1] = { column };
+            r.pass(left, samples, keep, out, 32u, conv, [] {}, jump);
+            r.store(0, rtable_out, instances, site.GID, left);
+        }
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" :: "n"(QCD_SYM_PHYS_REGS));
+        if (active) {
+            M3<R> S;
+            M3r2<R> m0;
+            stage.staple_and_link(g, tw, S, m0);
+            stage.end_item();
+            typedef PrnSmemT<NSKIP> PrnSmem;
+            PrnSmem prn(column, 32u, conv[0], keep, rtable + site.GID, instances);
+            heatbath_su3<R, MU, PrnSmem>(table, g, beta, site.gindex, m0, S, prn);
+        }
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" :: "n"(QCD_SYM_GEN_REGS));
+    }
+    // the last warp group to run out of tickets re-arms the counters for the next launch
+    if ((threadIdx.x & 127u) == 0u) {
+        const uint32_t d = atomicAdd(counters + 1, 1u);
+        if (d == gridDim.x * 4u - 1u) { counters[0] = 0u; counters[1] = 0u; __threadfence(); }
+    }
+}
+#endif  // QCD_SYM_EXPERIMENT
 
 }  // namespace qcd

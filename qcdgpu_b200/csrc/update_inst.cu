@@ -65,6 +65,17 @@ static cudaError_t launch_rlx(const UpdateArgs& a, cudaStream_t st) {
     uint32_t* out = a.prn_table_out ? a.prn_table_out : a.prn_table;
     uint32_t keep = need;
     if (out != a.prn_table && (uint32_t)keep_env < need) keep = (uint32_t)keep_env;
+#if INST_SUN == 3 && defined(QCD_SYM_EXPERIMENT)
+    // experiment: persistent kernel with symmetric warp groups and registers on loan (update.cuh, update_kernel_rlx_sym); 16 warps per SM
+    // leave room for 8 parked samples per thread
+    static int sym_env = -1;
+    if (sym_env < 0) sym_env = env_int("QCDGPU_SYM", 0);
+    const bool sym = sym_env && a.tmap && a.tmap1 && a.ws_counters && out != a.prn_table && a.geom.n2 % 64u == 0u && a.geom.nthreads % 32u == 0u &&
+                     a.geom.nthreads > 0u;
+    if (sym && keep > 8u) keep = 8u;
+#else
+    const bool sym = false; (void)sym;
+#endif
     size_t smem = size_t(keep) * kUpdateThreads * sizeof(float4);
     // the rest of the pass behind the parked samples as one modular multiplication (ranlux_jump.cuh); QCDGPU_RLX_JUMP=0: stepped
     static int jump_env = -1;
@@ -87,6 +98,22 @@ static cudaError_t launch_rlx(const UpdateArgs& a, cudaStream_t st) {
     // samples), rows of 32 update threads and room for 12 sample buffers + 12 link rings in shared memory.
     // Measured slower than the two-phase kernel below (4.46 against 3.62 ms per 64^4 pass, DESIGN.md decision 14): opt-in, QCDGPU_WS=1.
     // QCDGPU_WS_MIN: smallest launch (update threads) that takes it; QCDGPU_WS_BLOCKS: blocks instead of one per SM.
+#ifdef QCD_SYM_EXPERIMENT
+    if (sym && sym_smem_bytes<RealT>(keep) <= 227u * 1024u) {
+        auto ks = update_kernel_rlx_sym<RealT, INST_MU, TBC, 223>;
+        const size_t smem_s = sym_smem_bytes<RealT>(keep);
+        static SmemConfigured configured_s;
+        if (cudaError_t e = ensure_smem(ks, smem_s, configured_s); e != cudaSuccess) return e;
+        static int sym_jump = -1;
+        if (sym_jump < 0) sym_jump = env_int("QCDGPU_SYM_JUMP", 0);
+        const uint32_t tickets = (a.geom.nthreads + 127u) / 128u;
+        uint32_t blocks = (tickets + 3u) / 4u;
+        if (blocks > (uint32_t)sm_count()) blocks = (uint32_t)sm_count();
+        ks<<<blocks, kSymThreads, smem_s, st>>>(static_cast<RealT*>(a.table), static_cast<const RealT*>(a.params), a.geom, a.odd,
+                                               a.prn_table, out, a.prn_instances, a.prn_samples, keep, *a.tmap, *a.tmap1, sym_jump ? jump : nullptr, a.ws_counters);
+        return cudaGetLastError();
+    }
+#endif
     static int ws_env = -1, ws_min = 0, ws_blocks = 0;
     if (ws_env < 0) { ws_env = env_int("QCDGPU_WS", 0); ws_min = env_int("QCDGPU_WS_MIN", 0); ws_blocks = env_int("QCDGPU_WS_BLOCKS", 0); }
     if (ws_env && tma_env && a.tmap && a.tmap1 && a.ws_counters && out != a.prn_table && keep <= 16u && pad_env == 0 &&
