@@ -1790,21 +1790,23 @@ update_kernel_rlx_sym(R* __restrict__ table, const R* __restrict__ params, const
         unsigned long long conv[1] = { 0ull };
         if (active) {
             site = thread_site(g, kb + lane, odd != 0);
-            RanluxPk<1> r;
-            uint32_t left = r.load(0, rtable, instances, site.GID);
             stage.begin_item(g, site.gindex, site.p);          // the first links travel during the generator phase
-            uint4* const out[1] = { column };
-            r.pass(left, samples, keep, out, 32u, conv, [] {}, jump);
-            r.store(0, rtable_out, instances, site.GID, left);
+            if (g.debug_skip != 1u) {                          // QCDGPU_DEBUG_SKIP=1: physics only (diagnostic: stale samples)
+                RanluxPk<1> r;
+                uint32_t left = r.load(0, rtable, instances, site.GID);
+                uint4* const out[1] = { column };
+                r.pass(left, samples, keep, out, 32u, conv, [] {}, jump);
+                r.store(0, rtable_out, instances, site.GID, left);
+            }
         }
         asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" :: "n"(QCD_SYM_PHYS_REGS));
-        if (active) {
+        if (active && g.debug_skip != 2u) {                    // QCDGPU_DEBUG_SKIP=2: generator only
             M3<R> S;
             M3r2<R> m0;
             stage.staple_and_link(g, tw, S, m0);
             stage.end_item();
             typedef PrnSmemT<NSKIP> PrnSmem;
-            PrnSmem prn(column, 32u, conv[0], keep, rtable + site.GID, instances);
+            PrnSmem prn(column, 32u, conv[0], g.debug_skip == 1u ? 0xffffffffu : keep, rtable + site.GID, instances);
             heatbath_su3<R, MU, PrnSmem>(table, g, beta, site.gindex, m0, S, prn);
         }
         asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" :: "n"(QCD_SYM_GEN_REGS));
