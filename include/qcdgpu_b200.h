@@ -113,10 +113,10 @@ unsigned qgpu_buffer_size_align_step(qgpu* h, unsigned size, unsigned step);
  * qgpu_synchronize wait.  (The reference blocks in every kernel_run, clinterface.cpp:1251-1278.) */
 void  qgpu_set_async(qgpu* h, int on);
 int   qgpu_synchronize(qgpu* h);
-/* Fused PRNG: a `ranlux`/`xor128`/`pm`/`mrg32k3a` kernel_run is deferred; if the next consumer of its PRN
+/* Fused PRNG: a `ranlux`/`xor128`/`pm`/`mrg32k3a`/`xor7`/`ranecu` kernel_run is deferred; if the next consumer of its PRN
  * buffer is an update kernel and PRNG_instances == PRNGSTEP, the generator runs inside the update kernel
  * with its state in registers and the buffer is never written.  Any other access materialises it first.
- * Streams and results are identical either way. */
+ * Streams are identical either way; results too (xor7 / ranecu on SU(3) fp64: to rounding). */
 void  qgpu_set_fused_prng(qgpu* h, int on);
 /* L2 tiling of the update passes: x-chunk width of the launch order (0 = the reference's order, -1 = automatic:
  * 8 once three x-slices of links exceed 48 MB; env QCDGPU_TILE_X overrides the automatic choice).  Results do

@@ -162,6 +162,66 @@ static inline float mrg_step(uint32_t s1[3], uint32_t s2[3]) {
     return (float)((double)(x1n - x2n + 4294967087LL) * m);
 }
 
+/* XOR7 -- prngcl_xor7.cl:59-75 (device: two uint4 shifting by one word per step) == random.cpp:975-986
+ * (host: ring of eight words with a moving index).  s[0] oldest, s[7] newest. */
+static inline uint32_t xor7_step(uint32_t s[8]) {
+    uint32_t t, y;
+    t = s[7]; t = t ^ (t << 13); y = t ^ (t << 9);
+    t = s[4]; y ^= t ^ (t << 7);
+    t = s[3]; y ^= t ^ (t >> 3);
+    t = s[1]; y ^= t ^ (t >> 10);
+    t = s[0]; t = t ^ (t >> 7); y ^= t ^ (t << 24);
+    for (int k = 0; k < 7; k++) s[k] = s[k + 1];
+    s[7] = y;
+    return y;
+}
+/* RANECU, one lane: prngcl_ranecu.cl:77-103 (device, unsigned compares) */
+static inline uint32_t ranecu_step(uint32_t* a, uint32_t* b) {
+    uint32_t q = *a / 53668u;
+    uint32_t t1 = 40014u * (*a - q * 53668u), t2 = q * 12211u;
+    *a = (t1 > t2) ? (t1 - t2) : (t1 - t2 + 2147483563u);
+    q = *b / 52774u;
+    t1 = 40692u * (*b - q * 52774u); t2 = q * 3791u;
+    *b = (t1 > t2) ? (t1 - t2) : (t1 - t2 + 2147483399u);
+    return (*a > *b) ? (*a - *b) : (*a - *b + 2147483562u);
+}
+/* RANMAR: seeds of one lane (ranmar_init, prngcl_ranmar.cl:65-101 == RANMAR_initialize_CPU, random.cpp:773-799) */
+static void ranmar_seed_lane(uint32_t seed1, uint32_t seed2, float out[97]) {
+    uint32_t i = ((seed1 / 177u) % 177u) + 2u, j = (seed1 % 177u) + 2u, k = ((seed2 / 169u) % 178u) + 1u, l = seed2 % 169u;
+    for (int n = 0; n < 97; n++) {
+        uint32_t sv = 0u, t = 8388608u;
+        for (int m = 0; m < 24; m++) {
+            uint32_t u = (i * j) % 179u;
+            u = (u * k) % 179u;
+            i = j; j = k; k = u;
+            l = (53u * l + 1u) % 169u;
+            if (((l * u) % 64u) >= 32u) sv += t;
+            t >>= 1;
+        }
+        out[n] = ((float)sv) / 16777216.0f;
+    }
+}
+/* one RANMAR instance: 97 seeds x 4 lanes, the two indices and the arithmetic-sequence value (prngcl_ranmar.cl:103-133) */
+typedef struct { float u[97][4]; uint32_t i97, j97; float c; } rm_state;
+static void ranmar_step4(rm_state* r, float o[4]) {
+    const float CD = 7654321.0f / 16777216.0f, CM = 16777213.0f / 16777216.0f;
+    for (int k = 0; k < 4; k++) {
+        float uni = r->u[r->i97][k] - r->u[r->j97][k];
+        if (uni < 0.0f) uni = uni + 1.0f;
+        r->u[r->i97][k] = uni;
+        o[k] = uni;
+    }
+    if (r->i97 == 0) r->i97 = 97;
+    if (r->j97 == 0) r->j97 = 97;
+    r->i97--; r->j97--;
+    r->c -= CD;
+    if (r->c < 0.0f) r->c += CM;
+    for (int k = 0; k < 4; k++) {
+        o[k] = o[k] - r->c;
+        if (o[k] < 0.0f) o[k] = o[k] + 1.0f;
+    }
+}
+
 struct orc_prng {
     int generator;
     uint32_t instances;
@@ -171,6 +231,7 @@ struct orc_prng {
     uint32_t* seeds;     /* raw words handed to the device */
     uint32_t n_seed_words;
     uint32_t* st;        /* xor128/pm: 4 words per instance; mrg: 8 words per instance */
+    rm_state* rm;        /* ranmar */
 };
 
 static int rl_nskip_of(int generator) {
@@ -221,6 +282,44 @@ orc_prng* orc_prng_create(int generator, uint32_t randseries, uint32_t instances
         for (uint32_t i = 0; i < 8 * instances; i++) p->seeds[i] = (uint32_t)(rand() % 2147483647) + 1u;
         p->st = (uint32_t*)malloc(p->n_seed_words * sizeof(uint32_t));
         memcpy(p->st, p->seeds, p->n_seed_words * sizeof(uint32_t));
+    } else if (generator == ORC_PRNG_XOR7) {
+        /* random.cpp:967-974 (eight words of the host replica), then 934-950: rows 1 .. 2I-1 drawn, rows 0 and I = the replica's state */
+        uint32_t st8[8];
+        for (int k = 0; k < 8; k++) st8[k] = (uint32_t)rand();
+        p->n_seed_words = 8 * instances;
+        p->seeds = (uint32_t*)calloc(p->n_seed_words, sizeof(uint32_t));
+        for (uint32_t i = 4; i < 8 * instances; i++) p->seeds[i] = (uint32_t)rand();
+        for (int k = 0; k < 4; k++) { p->seeds[k] = st8[k]; p->seeds[4 * (size_t)instances + k] = st8[4 + k]; }
+        p->st = (uint32_t*)malloc(p->n_seed_words * sizeof(uint32_t));
+        memcpy(p->st, p->seeds, p->n_seed_words * sizeof(uint32_t));
+    } else if (generator == ORC_PRNG_RANECU) {
+        /* random.cpp:1044-1048, then 1017-1027 */
+        uint32_t j1 = (uint32_t)(rand() % 2147483647), j2 = (uint32_t)(rand() % 2147483647);
+        p->n_seed_words = 8 * instances;
+        p->seeds = (uint32_t*)calloc(p->n_seed_words, sizeof(uint32_t));
+        for (uint32_t i = 0; i < 8 * instances; i++) p->seeds[i] = (uint32_t)(rand() % 2147483647);
+        p->seeds[0] = j1; p->seeds[4 * (size_t)instances] = j2;
+        p->st = (uint32_t*)malloc(p->n_seed_words * sizeof(uint32_t));
+        memcpy(p->st, p->seeds, p->n_seed_words * sizeof(uint32_t));
+    } else if (generator == ORC_PRNG_RANMAR) {
+        /* random.cpp:776-777, then 726-744: seeds4[0] / seeds4[I] = the replica's pair in all four lanes */
+        uint32_t s1 = (uint32_t)(rand() % 31328), s2 = (uint32_t)(rand() % 30081);
+        p->n_seed_words = 8 * instances;
+        p->seeds = (uint32_t*)calloc(p->n_seed_words, sizeof(uint32_t));
+        for (int k = 0; k < 4; k++) { p->seeds[k] = s1; p->seeds[4 * (size_t)instances + k] = s2; }
+        for (uint32_t i = 1; i < instances; i++) {
+            for (int k = 0; k < 4; k++) p->seeds[4 * (size_t)i + k] = (uint32_t)(rand() % 31328);
+            for (int k = 0; k < 4; k++) p->seeds[4 * ((size_t)instances + i) + k] = (uint32_t)(rand() % 30081);
+        }
+        p->rm = (rm_state*)calloc(instances, sizeof(rm_state));
+        for (uint32_t i = 0; i < instances; i++) {
+            float lane[97];
+            for (int k = 0; k < 4; k++) {
+                ranmar_seed_lane(p->seeds[4 * (size_t)i + k], p->seeds[4 * ((size_t)instances + i) + k], lane);
+                for (int n = 0; n < 97; n++) p->rm[i].u[n][k] = lane[n];
+            }
+            p->rm[i].i97 = 96; p->rm[i].j97 = 32; p->rm[i].c = 362436.0f / 16777216.0f;
+        }
     } else {
         free(p); return NULL;
     }
@@ -228,7 +327,7 @@ orc_prng* orc_prng_create(int generator, uint32_t randseries, uint32_t instances
 }
 void orc_prng_destroy(orc_prng* p) {
     if (!p) return;
-    free(p->rl); free(p->seeds); free(p->st); free(p);
+    free(p->rl); free(p->seeds); free(p->st); free(p->rm); free(p);
 }
 const uint32_t* orc_prng_seeds(const orc_prng* p, uint32_t* n_words) {
     if (n_words) *n_words = p->n_seed_words;
@@ -248,6 +347,17 @@ void orc_prng_produce(orc_prng* p, uint32_t samples, float* out) {
             } else if (p->generator == ORC_PRNG_PM) {
                 uint32_t* s = p->st + 4 * g;
                 for (int k = 0; k < 4; k++) { s[k] = pm_step(s[k]); o[k] = ((float)s[k]) / 2147483648.0f; }
+            } else if (p->generator == ORC_PRNG_XOR7) {
+                uint32_t s8[8];
+                memcpy(s8, p->st + 4 * g, 16); memcpy(s8 + 4, p->st + 4 * ((size_t)I + g), 16);
+                for (int k = 0; k < 4; k++) o[k] = ((float)xor7_step(s8)) / 4294967296.0f;
+                memcpy(p->st + 4 * g, s8, 16); memcpy(p->st + 4 * ((size_t)I + g), s8 + 4, 16);
+            } else if (p->generator == ORC_PRNG_RANECU) {
+                uint32_t* a = p->st + 4 * g;
+                uint32_t* b = p->st + 4 * ((size_t)I + g);
+                for (int k = 0; k < 4; k++) o[k] = ((float)ranecu_step(a + k, b + k)) / 2147483648.0f;
+            } else if (p->generator == ORC_PRNG_RANMAR) {
+                ranmar_step4(&p->rm[g], o);
             } else {
                 uint32_t* s1 = p->st + 4 * g;
                 uint32_t* s2 = p->st + 4 * ((size_t)I + g);
@@ -275,6 +385,44 @@ void orc_prng_host_stream(int generator, uint32_t randseries, uint32_t n, float*
             int test = (int)(16807u * lo - 2836u * hi);
             seed = (test > 0) ? test : test + 2147483647;
             out[i] = (float)(((double)seed) / 2147483647.0);
+        }
+    } else if (generator == ORC_PRNG_XOR7) {
+        /* random.cpp:965-986 */
+        uint32_t s8[8]; for (int k = 0; k < 8; k++) s8[k] = (uint32_t)rand();
+        for (uint32_t i = 0; i < n; i++) out[i] = (float)((float)xor7_step(s8) / 4294967296.0);
+    } else if (generator == ORC_PRNG_RANECU) {
+        /* random.cpp:1044-1068: signed arithmetic */
+        int j1 = rand() % 2147483647, j2 = rand() % 2147483647;
+        for (uint32_t i = 0; i < n; i++) {
+            int k = j1 / 53668;
+            j1 = 40014 * (j1 - k * 53668) - k * 12211;
+            if (j1 < 0) j1 += 2147483563;
+            k = j2 / 52774;
+            j2 = 40692 * (j2 - k * 52774) - k * 3791;
+            if (j2 < 0) j2 += 2147483399;
+            int z = j1 - j2;
+            if (z < 1) z += 2147483562;
+            out[i] = (float)((float)z) / ((float)2147483648.0);
+        }
+    } else if (generator == ORC_PRNG_RANMAR) {
+        /* random.cpp:773-816: one lane */
+        uint32_t s1 = (uint32_t)(rand() % 31328), s2 = (uint32_t)(rand() % 30081);
+        float u[97];
+        ranmar_seed_lane(s1, s2, u);
+        int i97 = 96, j97 = 32;
+        float c = (float)(362436.0 / 16777216.0);
+        for (uint32_t i = 0; i < n; i++) {
+            float uni = u[i97] - u[j97];
+            if (uni < 0.0) uni = uni + 1.0f;
+            u[i97] = uni;
+            if (i97 == 0) i97 = 97;
+            if (j97 == 0) j97 = 97;
+            i97--; j97--;
+            c = (float)c - (float)(7654321.0 / 16777216.0);
+            if (c < 0.0) c = (float)c + (float)(16777213.0 / 16777216.0);
+            uni = uni - c;
+            if (uni < 0.0) uni = uni + 1.0f;
+            out[i] = uni;
         }
     }
 }

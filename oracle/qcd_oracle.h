@@ -84,7 +84,8 @@ uint32_t orc_neighbour(const orc_cfg*, uint32_t gindex, int dir, int sign);
 
 /* ---- PRNG host logic + streams */
 enum { ORC_PRNG_XOR128 = 1, ORC_PRNG_RANLUX0 = 2, ORC_PRNG_RANLUX1 = 3, ORC_PRNG_RANLUX2 = 4,
-       ORC_PRNG_RANLUX3 = 5, ORC_PRNG_RANLUX4 = 6, ORC_PRNG_PM = 9, ORC_PRNG_MRG32K3A = 12 };
+       ORC_PRNG_RANLUX3 = 5, ORC_PRNG_RANLUX4 = 6, ORC_PRNG_RANMAR = 8, ORC_PRNG_PM = 9, ORC_PRNG_XOR7 = 10, ORC_PRNG_RANECU = 11,
+       ORC_PRNG_MRG32K3A = 12 };   /* convert_generator_to_uint, random.cpp:108-121 */
 
 typedef struct orc_prng orc_prng;
 /* PRNG::initialize (random.cpp:216-277): srand(randseries), per-generator seed

@@ -4,7 +4,7 @@
 // as raw IEEE-754 words, so that tests/golden/ref_prng_*.json can pin the oracle
 // and the CUDA producers bit for bit.
 //
-//   prng_dump <RANLUX0..4|PM> <randseries> <count>
+//   prng_dump <RANLUX0..4|PM|XOR7|RANECU|RANMAR> <randseries> <count>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>

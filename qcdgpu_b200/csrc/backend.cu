@@ -50,7 +50,7 @@ enum KernelKind {
     K_NONE = 0, K_INIT_COLD, K_INIT_GID, K_INIT_HOT, K_GRAMSCHMIDT, K_UPDATE, K_OVERRELAX, K_CLEAR,
     K_MEASURE, K_REDUCE_MEAS, K_MEASURE_PLQ, K_REDUCE_PLQ, K_POLYAKOV, K_REDUCE_POLYAKOV,
     K_POLYAKOV_DIFF, K_REDUCE_POLYAKOV_DIFF, K_WILSON, K_REDUCE_WILSON, K_ACTION_DIFF, K_REDUCE_ACTION_DIFF,
-    K_RANLUX_INIT, K_PRODUCE,
+    K_RANLUX_INIT, K_RANMAR_INIT, K_PRODUCE,
     K_ON_INIT_COLD, K_ON_INIT_HOT, K_ON_UPDATE, K_ON_MEASURE, K_ON_REDUCE
 };
 
@@ -266,6 +266,10 @@ const NameMap kNames[] = {
     { "reduce_action_diff_z_double2", K_REDUCE_ACTION_DIFF, 2, 0, 0 },
     { "ranlux_init", K_RANLUX_INIT, 0, 0, 0 },
     { "ranlux", K_PRODUCE, 0, 0, -1 }, { "xor128", K_PRODUCE, 0, 0, PRN_XOR128 }, { "pm", K_PRODUCE, 0, 0, PRN_PM }, { "mrg32k3a", K_PRODUCE, 0, 0, PRN_MRG32K3A },
+    { "xor7", K_PRODUCE, 0, 0, PRN_XOR7 }, { "ranecu", K_PRODUCE, 0, 0, PRN_RANECU },
+    // RANMAR: the kernels are ranmar_init / ranmar in prngcl_ranmar.cl:65,159, the reference's host asks for "rmseed" / "rmproduce" (random.cpp:757,763)
+    { "ranmar_init", K_RANMAR_INIT, 0, 0, 0 }, { "rmseed", K_RANMAR_INIT, 0, 0, 0 },
+    { "ranmar", K_PRODUCE, 0, 0, PRN_RANMAR }, { "rmproduce", K_PRODUCE, 0, 0, PRN_RANMAR },
 };
 
 // kernel names of a program created with -D ON_MODEL (O(N)/oncl/oncl.cl, on_measurements_cl.cl); dir = what is measured
@@ -494,7 +498,8 @@ int launch_kernel(qgpu* h, int kid) {
                 Kernel& pk = h->kernels[pbuf.pending_produce];
                 int samples = 0; arg_int(pk, 2, &samples);
                 bool fusable = h->fused && (uint32_t)pk.global[0] == a.geom.prngstep && full_threads <= a.geom.prngstep &&
-                               (pk.prn_kind == PRN_RANLUX3 || pk.prn_kind == PRN_XOR128 || pk.prn_kind == PRN_PM || pk.prn_kind == PRN_MRG32K3A) &&
+                               (pk.prn_kind == PRN_RANLUX3 || pk.prn_kind == PRN_XOR128 || pk.prn_kind == PRN_PM || pk.prn_kind == PRN_MRG32K3A ||
+                                pk.prn_kind == PRN_XOR7 || pk.prn_kind == PRN_RANECU) &&
                                (uint32_t)samples >= 3u * (uint32_t)(c.nhit + 1) * (uint32_t)c.nhitpar;
                 if (fusable) {
                     if (apply_pending_skips(h, pb) < 0) return -1;
@@ -735,10 +740,22 @@ int launch_kernel(qgpu* h, int kid) {
             CUDA_OK(h, launch_ranlux_init((const uint32_t*)buf_ptr(h, k, 0), (uint32_t*)buf_ptr(h, k, 1), (uint32_t)k.global[0], st));
             break;
         }
+        case K_RANMAR_INIT: {
+            if (!buf_ptr(h, k, 0) || !buf_ptr(h, k, 1)) return fail(h, "kernel %s: arguments (seeds, seedtable) not set", k.name.c_str());
+            if (h->buffers[buf_id(k, 0)].bytes < k.global[0] * 2 * 16) return fail(h, "kernel %s: seeds must hold 2 uint4 per instance", k.name.c_str());
+            if (h->buffers[buf_id(k, 1)].bytes < k.global[0] * 98 * 16) return fail(h, "kernel %s: seed table too small (97 + 1 float4 per instance, prngcl_ranmar.cl)", k.name.c_str());
+            CUDA_OK(h, launch_ranmar_init((const uint32_t*)buf_ptr(h, k, 0), (float*)buf_ptr(h, k, 1), (uint32_t)k.global[0], st));
+            break;
+        }
         case K_PRODUCE: {
             int pb = buf_id(k, 1);
             int samples = 0;
             if (!buf_ptr(h, k, 0) || !valid_buf(h, pb) || !arg_int(k, 2, &samples)) return fail(h, "kernel %s: arguments (seed table, prns, samples) not set", k.name.c_str());
+            {   // float4 / uint4 elements of generator state per instance
+                const size_t per = (k.prn_kind == PRN_RANMAR) ? 98 : (k.prn_kind == PRN_XOR7 || k.prn_kind == PRN_RANECU || k.prn_kind == PRN_MRG32K3A) ? 2 : 0;
+                if (per && h->buffers[buf_id(k, 0)].bytes < k.global[0] * per * 16)
+                    return fail(h, "kernel %s: seed table too small (%zu vec4 per instance)", k.name.c_str(), per);
+            }
             if (c.prng_precision == 2) return fail(h, "kernel %s: PRNG_PRECISION=2 (double PRNs) is not implemented", k.name.c_str());
             if (h->buffers[pb].bytes < (size_t)k.global[0] * samples * 16) return fail(h, "kernel %s: PRN buffer too small", k.name.c_str());
             if (h->buffers[pb].pending_partly_fused) finish_partial_pass(h, pb);   // previous pass: consumed by its x-range launches
@@ -788,7 +805,7 @@ int launch_kernel(qgpu* h, int kid) {
                 Kernel& pk = h->kernels[pbuf.pending_produce];
                 int samples = 0; arg_int(pk, 2, &samples);
                 if (h->fused && (uint32_t)pk.global[0] == a.geom.prngstep && a.geom.nthreads <= a.geom.prngstep &&
-                    (pk.prn_kind == PRN_XOR128 || pk.prn_kind == PRN_PM || pk.prn_kind == PRN_MRG32K3A) && (uint32_t)samples >= need) {
+                    (pk.prn_kind == PRN_XOR128 || pk.prn_kind == PRN_PM || pk.prn_kind == PRN_MRG32K3A || pk.prn_kind == PRN_XOR7 || pk.prn_kind == PRN_RANECU) && (uint32_t)samples >= need) {
                     a.prn_kind = pk.prn_kind; a.prn_table = (uint32_t*)buf_ptr(h, pk, 0);
                     a.prn_instances = (uint32_t)pk.global[0]; a.prn_samples = (uint32_t)samples;
                     pbuf.pending_produce = 0; fused = true;

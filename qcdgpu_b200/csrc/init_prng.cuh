@@ -2,7 +2,7 @@
 //
 // Replaces lattice_init_{cold,gid,hot_X..T}, lattice_GramSchmidt (SU(N)/suncl/suncl.cl:55-396;
 // lattice_random{2,3}: su2_update_cl.cl:110-147, su3_update_cl.cl:165-225) and the producer
-// kernels ranlux_init / ranlux / xor128 / pm / mrg32k3a (SU(N)/random/prngcl_*.cl).
+// kernels ranlux_init / ranlux / xor128 / pm / mrg32k3a / xor7 / ranecu / ranmar_init / ranmar (SU(N)/random/prngcl_*.cl).
 // The producers fill the reference-layout buffer prns[GID + i*instances] so that any
 // PRNG_instances configuration of the reference can be replayed bit for bit; the fused
 // update kernels (update.cuh) use the same generator structs from registers instead.
@@ -196,6 +196,52 @@ ranlux_skip_kernel(uint32_t* __restrict__ table, uint32_t instances, const uint3
         return;
     }
     r.store(0, table, instances, i, left);
+}
+// RANMAR (prngcl_ranmar.cl:65-191; the reference's host asks for the kernels as "rmseed" / "rmproduce", random.cpp:757-763).
+// seeds: uint4[2 x instances] (first seeds, then second seeds); table: float4[98 x instances].  One thread per (instance, lane).
+static __global__ void __launch_bounds__(128)
+ranmar_init_kernel(const uint32_t* __restrict__ seeds, float* __restrict__ table, uint32_t instances) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= 4u * instances) return;
+    const uint32_t i = t >> 2, lane = t & 3u;
+    RanmarLane4::seed(seeds[4u * i + lane], seeds[4u * (size_t(instances) + i) + lane], table + 4u * size_t(i) + lane, 4u * size_t(instances));
+    if (lane == 0u)
+        reinterpret_cast<float4*>(table)[size_t(i) + 97u * size_t(instances)] =
+            make_float4(__uint_as_float(96u), __uint_as_float(32u), 362436.0f / 16777216.0f, 0.0f);     // (I97, J97, c, 0)
+}
+static __global__ void __launch_bounds__(128)
+ranmar_produce_kernel(float4* __restrict__ table, float4* __restrict__ prns, uint32_t instances, uint32_t samples) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= instances) return;
+    const float CD = 7654321.0f / 16777216.0f, CM = 16777213.0f / 16777216.0f;
+    float4 idx = table[size_t(i) + 97u * size_t(instances)];
+    uint32_t I97 = __float_as_uint(idx.x), J97 = __float_as_uint(idx.y);
+    float c = idx.z;
+    size_t dst = i;
+#pragma unroll 1
+    for (uint32_t s = 0; s < samples; s++) {
+        const float4 a = table[size_t(i) + size_t(I97) * instances], b = table[size_t(i) + size_t(J97) * instances];
+        float4 u = make_float4(__fsub_rn(a.x, b.x), __fsub_rn(a.y, b.y), __fsub_rn(a.z, b.z), __fsub_rn(a.w, b.w));
+        if (u.x < 0.0f) u.x = __fadd_rn(u.x, 1.0f);
+        if (u.y < 0.0f) u.y = __fadd_rn(u.y, 1.0f);
+        if (u.z < 0.0f) u.z = __fadd_rn(u.z, 1.0f);
+        if (u.w < 0.0f) u.w = __fadd_rn(u.w, 1.0f);
+        table[size_t(i) + size_t(I97) * instances] = u;
+        if (I97 == 0u) I97 = 97u;
+        if (J97 == 0u) J97 = 97u;
+        I97--; J97--;
+        c = __fsub_rn(c, CD);
+        if (c < 0.0f) c = __fadd_rn(c, CM);
+        u.x = __fsub_rn(u.x, c); u.y = __fsub_rn(u.y, c); u.z = __fsub_rn(u.z, c); u.w = __fsub_rn(u.w, c);
+        if (u.x < 0.0f) u.x = __fadd_rn(u.x, 1.0f);
+        if (u.y < 0.0f) u.y = __fadd_rn(u.y, 1.0f);
+        if (u.z < 0.0f) u.z = __fadd_rn(u.z, 1.0f);
+        if (u.w < 0.0f) u.w = __fadd_rn(u.w, 1.0f);
+        prns[dst] = u;
+        dst += instances;
+    }
+    idx.x = __uint_as_float(I97); idx.y = __uint_as_float(J97); idx.z = c;
+    table[size_t(i) + 97u * size_t(instances)] = idx;
 }
 template <class P>
 __global__ void __launch_bounds__(128)

@@ -16,6 +16,9 @@ enum PrnKind : int {
     PRN_PM       = 4,
     PRN_MRG32K3A = 5,
     PRN_RANLUX0  = 6, PRN_RANLUX1 = 7, PRN_RANLUX2 = 8, PRN_RANLUX4 = 9,   // buffered-only luxury levels
+    PRN_XOR7     = 10,  // fused or buffered (8 words of state)
+    PRN_RANECU   = 11,  // fused or buffered (8 words of state)
+    PRN_RANMAR   = 12,  // buffered only (97 float4 of state per instance, in global memory)
 };
 
 // CUtensorMap (128 bytes, 64-byte aligned) without pulling cuda.h into this header
@@ -77,6 +80,7 @@ cudaError_t launch_init_hot(int sun, int prec, void* table, const Geom&, const v
 cudaError_t launch_gramschmidt(int sun, int prec, void* table, const Geom&, cudaStream_t);
 
 cudaError_t launch_ranlux_init(const uint32_t* seeds, uint32_t* table, uint32_t instances, cudaStream_t);
+cudaError_t launch_ranmar_init(const uint32_t* seeds, float* table, uint32_t instances, cudaStream_t);    // seeds: uint4[2 x instances], table: float4[98 x instances]
 cudaError_t launch_prn_produce(int prn_kind, uint32_t* table, void* prns, uint32_t instances, uint32_t samples, cudaStream_t);
 // advance every RANLUX3 instance of a state table by `samples` float4 without producing them (one modular multiplication each)
 cudaError_t launch_ranlux_skip(uint32_t* table, uint32_t instances, uint64_t samples, cudaStream_t);

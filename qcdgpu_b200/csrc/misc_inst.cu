@@ -27,6 +27,10 @@ cudaError_t launch_ranlux_init(const uint32_t* seeds, uint32_t* table, uint32_t 
     ranlux_init_kernel<<<(instances + 127) / 128, 128, 0, st>>>(seeds, table, instances);
     return cudaGetLastError();
 }
+cudaError_t launch_ranmar_init(const uint32_t* seeds, float* table, uint32_t instances, cudaStream_t st) {
+    ranmar_init_kernel<<<(4u * instances + 127) / 128, 128, 0, st>>>(seeds, table, instances);
+    return cudaGetLastError();
+}
 cudaError_t launch_prn_produce(int kind, uint32_t* table, void* prns, uint32_t instances, uint32_t samples, cudaStream_t st) {
     dim3 grid((instances + 127) / 128), block(128);
     float4* out = static_cast<float4*>(prns);
@@ -39,6 +43,9 @@ cudaError_t launch_prn_produce(int kind, uint32_t* table, void* prns, uint32_t i
         case PRN_XOR128:  small_produce_kernel<PrnXor128><<<grid, block, 0, st>>>(table, out, instances, samples); break;
         case PRN_PM:      small_produce_kernel<PrnPM><<<grid, block, 0, st>>>(table, out, instances, samples); break;
         case PRN_MRG32K3A: small_produce_kernel<PrnMrg><<<grid, block, 0, st>>>(table, out, instances, samples); break;
+        case PRN_XOR7:    small_produce_kernel<PrnXor7><<<grid, block, 0, st>>>(table, out, instances, samples); break;
+        case PRN_RANECU:  small_produce_kernel<PrnRanecu><<<grid, block, 0, st>>>(table, out, instances, samples); break;
+        case PRN_RANMAR:  ranmar_produce_kernel<<<grid, block, 0, st>>>(reinterpret_cast<float4*>(table), out, instances, samples); break;
         default: return cudaErrorInvalidValue;
     }
     return cudaGetLastError();

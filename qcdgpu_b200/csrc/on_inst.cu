@@ -30,6 +30,16 @@ static cudaError_t on_update_t(const OnArgs& a, cudaStream_t st) {
             on_update_kernel<R, PrnMrg><<<grid, block, 0, st>>>(t, p, a.geom, a.skgroup, a.odd, pa, a.acc);
             break;
         }
+        case PRN_XOR7: {
+            PrnXor7::Args pa = { a.prn_table, a.prn_instances, a.prn_samples };
+            on_update_kernel<R, PrnXor7><<<grid, block, 0, st>>>(t, p, a.geom, a.skgroup, a.odd, pa, a.acc);
+            break;
+        }
+        case PRN_RANECU: {
+            PrnRanecu::Args pa = { a.prn_table, a.prn_instances, a.prn_samples };
+            on_update_kernel<R, PrnRanecu><<<grid, block, 0, st>>>(t, p, a.geom, a.skgroup, a.odd, pa, a.acc);
+            break;
+        }
         default: return cudaErrorInvalidValue;
     }
     return cudaGetLastError();

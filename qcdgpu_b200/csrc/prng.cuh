@@ -7,6 +7,7 @@
 //           host/device-consistent O(N) flavour: O(N)/random/random.cl:137-173, random.cpp:636-652)
 //   PM      (Park-Miller minimal standard, 4 independent lanes: prngcl_pm.cl:86-123)
 //   MRG32k3a(L'Ecuyer; prngcl_mrg32k3a.cl:73-150 -- no host code in the reference)
+//   XOR7, RANECU, RANMAR (prngcl_xor7.cl, prngcl_ranecu.cl, prngcl_ranmar.cl; host replicas random.cpp:773-816, 965-986, 1044-1068)
 //
 // New design: the reference keeps the 24 RANLUX seeds as fp32 multiples of 2^-24
 // and steps them with float compares; here they are 24-bit integers, one
@@ -459,6 +460,83 @@ struct ParkMiller {
     __device__ __forceinline__ void skip4() {
 #pragma unroll
         for (int k = 0; k < 4; k++) s[k] = step1(s[k]);
+    }
+};
+
+// ---------------------------------------------------------------- XOR7 (Panneton-L'Ecuyer seven-xorshift generator on eight words)
+// prngcl_xor7.cl:59-75 (device: the state as two uint4 that shift by one word per step) == random.cpp:975-986 (host: a ring of
+// eight words with a moving index).  s[0] is the oldest word, s[7] the one just produced.
+struct Xor7 {
+    uint32_t s[8];
+    __device__ __forceinline__ uint32_t step() {
+        uint32_t t, y;
+        t = s[7]; t ^= t << 13; y = t ^ (t << 9);
+        t = s[4]; y ^= t ^ (t << 7);
+        t = s[3]; y ^= t ^ (t >> 3);
+        t = s[1]; y ^= t ^ (t >> 10);
+        t = s[0]; t ^= t >> 7; y ^= t ^ (t << 24);
+#pragma unroll
+        for (int k = 0; k < 7; k++) s[k] = s[k + 1];
+        s[7] = y;
+        return y;
+    }
+    __device__ __forceinline__ F4 next4() {      // prngcl_xor7.cl:125-134: (float) y / 2^32 (an exact scaling; 1.0f is reachable)
+        F4 r;
+        r.x = __uint2float_rn(step()) / 4294967296.0f;
+        r.y = __uint2float_rn(step()) / 4294967296.0f;
+        r.z = __uint2float_rn(step()) / 4294967296.0f;
+        r.w = __uint2float_rn(step()) / 4294967296.0f;
+        return r;
+    }
+    __device__ __forceinline__ void skip4() { step(); step(); step(); step(); }
+};
+
+// ---------------------------------------------------------------- RANECU (L'Ecuyer's combined LCG, four independent lanes)
+// prngcl_ranecu.cl:77-103 (device, unsigned compares) / random.cpp:1049-1068 (host replica of lane x of instance 0, signed
+// arithmetic: the two agree unless an intermediate difference is exactly zero, probability 2^-31 per step; the device form is
+// what is followed, as for Park-Miller).
+struct Ranecu {
+    uint32_t a[4], b[4];
+    __device__ __forceinline__ F4 next4() {
+        float o[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            uint32_t q = a[k] / 53668u;
+            uint32_t t1 = 40014u * (a[k] - q * 53668u), t2 = q * 12211u;
+            a[k] = (t1 > t2) ? (t1 - t2) : (t1 - t2 + 2147483563u);
+            q = b[k] / 52774u;
+            t1 = 40692u * (b[k] - q * 52774u); t2 = q * 3791u;
+            b[k] = (t1 > t2) ? (t1 - t2) : (t1 - t2 + 2147483399u);
+            const uint32_t z = (a[k] > b[k]) ? (a[k] - b[k]) : (a[k] - b[k] + 2147483562u);
+            o[k] = __uint2float_rn(z) / 2147483648.0f;
+        }
+        return { o[0], o[1], o[2], o[3] };
+    }
+    __device__ __forceinline__ void skip4() { (void)next4(); }
+};
+
+// ---------------------------------------------------------------- RANMAR (Marsaglia-Zaman-Tsang lagged Fibonacci, four lanes)
+// prngcl_ranmar.cl:65-191: 97 float4 seeds per instance in global memory (seedtable[GID + n * instances]), a 98th element
+// (I97, J97 as integers, the arithmetic-sequence value c shared by the four lanes, 0).  Every value is a multiple of 2^-24
+// in [0, 1), so the float subtractions are exact and the stream equals the host replica's (random.cpp:801-816) bit for bit.
+struct RanmarLane4 {
+    // the 97 x 24 bits of one lane from its two seeds (ranmar_init / RANMAR_initialize_CPU, random.cpp:773-799)
+    static __device__ __forceinline__ void seed(uint32_t seed1, uint32_t seed2, float* out, size_t stride) {
+        uint32_t i = ((seed1 / 177u) % 177u) + 2u, j = (seed1 % 177u) + 2u, k = ((seed2 / 169u) % 178u) + 1u, l = seed2 % 169u;
+#pragma unroll 1
+        for (int n = 0; n < 97; n++) {
+            uint32_t s = 0u, t = 8388608u;
+#pragma unroll 1
+            for (int m = 0; m < 24; m++) {
+                uint32_t u = (i * j) % 179u;
+                u = (u * k) % 179u;
+                i = j; j = k; k = u;
+                l = (53u * l + 1u) % 169u;
+                if (((l * u) % 64u) >= 32u) s += t;
+                t >>= 1;
+            }
+            out[size_t(n) * stride] = __uint2float_rn(s) / 16777216.0f;
+        }
     }
 };
 

@@ -139,7 +139,7 @@ struct PrnSmemT {
 template <class P, class = void> struct HasParked { static constexpr bool value = false; };
 template <class P> struct HasParked<P, decltype((void)P::kParked)> { static constexpr bool value = P::kParked; };
 template <class Gen, int WORDS>
-struct PrnSmallState {   // XOR128 (4 words), PM (4 words), MRG32k3a (2 x uint4 rows)
+struct PrnSmallState {   // XOR128 (4 words), PM (4 words), MRG32k3a / XOR7 / RANECU (2 x uint4 rows)
     struct Args { uint32_t* table; uint32_t instances; uint32_t samples; };
     Gen gen; uint32_t used; uint32_t* table; uint32_t instances, samples, id;
     F4 ahead; bool have_ahead;     // peek(): the next sample, generated but not yet consumed
@@ -187,7 +187,30 @@ template <> __device__ __forceinline__ void PrnSmallState<Mrg32k3a, 8>::store() 
     s1.x = gen.a[0]; s1.y = gen.a[1]; s1.z = gen.a[2]; s2.x = gen.b[0]; s2.y = gen.b[1]; s2.z = gen.b[2];
     t[id] = s1; t[size_t(instances) + id] = s2;
 }
+// XOR7 / RANECU: seed_table[GID] and seed_table[GID + instances] (prngcl_xor7.cl:111-112,137-138; prngcl_ranecu.cl:139-140,160-161)
+template <> __device__ __forceinline__ void PrnSmallState<Xor7, 8>::load() {
+    uint4 s1 = reinterpret_cast<const uint4*>(table)[id];
+    uint4 s2 = reinterpret_cast<const uint4*>(table)[size_t(instances) + id];
+    gen.s[0] = s1.x; gen.s[1] = s1.y; gen.s[2] = s1.z; gen.s[3] = s1.w; gen.s[4] = s2.x; gen.s[5] = s2.y; gen.s[6] = s2.z; gen.s[7] = s2.w;
+}
+template <> __device__ __forceinline__ void PrnSmallState<Xor7, 8>::store() {
+    uint4* t = reinterpret_cast<uint4*>(table);
+    t[id] = make_uint4(gen.s[0], gen.s[1], gen.s[2], gen.s[3]);
+    t[size_t(instances) + id] = make_uint4(gen.s[4], gen.s[5], gen.s[6], gen.s[7]);
+}
+template <> __device__ __forceinline__ void PrnSmallState<Ranecu, 8>::load() {
+    uint4 s1 = reinterpret_cast<const uint4*>(table)[id];
+    uint4 s2 = reinterpret_cast<const uint4*>(table)[size_t(instances) + id];
+    gen.a[0] = s1.x; gen.a[1] = s1.y; gen.a[2] = s1.z; gen.a[3] = s1.w; gen.b[0] = s2.x; gen.b[1] = s2.y; gen.b[2] = s2.z; gen.b[3] = s2.w;
+}
+template <> __device__ __forceinline__ void PrnSmallState<Ranecu, 8>::store() {
+    uint4* t = reinterpret_cast<uint4*>(table);
+    t[id] = make_uint4(gen.a[0], gen.a[1], gen.a[2], gen.a[3]);
+    t[size_t(instances) + id] = make_uint4(gen.b[0], gen.b[1], gen.b[2], gen.b[3]);
+}
 using PrnXor128 = PrnSmallState<Xor128, 4>;
+using PrnXor7 = PrnSmallState<Xor7, 8>;
+using PrnRanecu = PrnSmallState<Ranecu, 8>;
 using PrnPM = PrnSmallState<ParkMiller, 4>;
 using PrnMrg = PrnSmallState<Mrg32k3a, 8>;
 

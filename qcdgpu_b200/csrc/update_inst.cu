@@ -180,6 +180,8 @@ static cudaError_t launch_tbc(const UpdateArgs& a, cudaStream_t st) {
         case PRN_XOR128:   { PrnXor128::Args pa = { a.prn_table, a.prn_instances, a.prn_samples }; return launch_one<TBC, PrnXor128>(a, pa, st); }
         case PRN_PM:       { PrnPM::Args pa = { a.prn_table, a.prn_instances, a.prn_samples }; return launch_one<TBC, PrnPM>(a, pa, st); }
         case PRN_MRG32K3A: { PrnMrg::Args pa = { a.prn_table, a.prn_instances, a.prn_samples }; return launch_one<TBC, PrnMrg>(a, pa, st); }
+        case PRN_XOR7:     { PrnXor7::Args pa = { a.prn_table, a.prn_instances, a.prn_samples }; return launch_one<TBC, PrnXor7>(a, pa, st); }
+        case PRN_RANECU:   { PrnRanecu::Args pa = { a.prn_table, a.prn_instances, a.prn_samples }; return launch_one<TBC, PrnRanecu>(a, pa, st); }
         default: return cudaErrorInvalidValue;
     }
 }
@@ -229,6 +231,8 @@ int REGS_NAME(int tbc, int prn_kind) {
         case PRN_XOR128:   return tbc ? regs_of<true, PrnXor128>() : regs_of<false, PrnXor128>();
         case PRN_PM:       return tbc ? regs_of<true, PrnPM>() : regs_of<false, PrnPM>();
         case PRN_MRG32K3A: return tbc ? regs_of<true, PrnMrg>() : regs_of<false, PrnMrg>();
+        case PRN_XOR7:     return tbc ? regs_of<true, PrnXor7>() : regs_of<false, PrnXor7>();
+        case PRN_RANECU:   return tbc ? regs_of<true, PrnRanecu>() : regs_of<false, PrnRanecu>();
         default: return -1;
     }
 }

@@ -12,10 +12,10 @@ import numpy as np
 from .capi import GPU, host_rand_fill, host_srand
 
 RL_NSKIP = {"RANLUX0": 24, "RANLUX1": 48, "RANLUX2": 97, "RANLUX3": 223, "RANLUX4": 389}
-GENERATORS = tuple(RL_NSKIP) + ("XOR128", "PM", "MRG32K3A")
+GENERATORS = tuple(RL_NSKIP) + ("XOR128", "PM", "MRG32K3A", "XOR7", "RANECU", "RANMAR")
 # convert_generator_to_uint (random.cpp:108-121); MRG32K3A has no number in the reference
 GENERATOR_IDS = {"XOR128": 1, "RANLUX0": 2, "RANLUX1": 3, "RANLUX2": 4, "RANLUX3": 5, "RANLUX4": 6,
-                 "RANLUX": 7, "PM": 9, "MRG32K3A": 12}
+                 "RANLUX": 7, "RANMAR": 8, "PM": 9, "XOR7": 10, "RANECU": 11, "MRG32K3A": 12}
 
 
 class PRNG:
@@ -75,8 +75,14 @@ class PRNG:
             self._small_initialize("pm", 2147483647, aligned=False)
         elif g == "MRG32K3A":
             self._mrg_initialize()
+        elif g == "XOR7":
+            self._xor7_initialize()
+        elif g == "RANECU":
+            self._ranecu_initialize()
+        elif g == "RANMAR":
+            self._ranmar_initialize()
         else:
-            raise ValueError(f"PRNG {g} is not supported (RANLUX0-4, XOR128, PM, MRG32K3A)")
+            raise ValueError(f"PRNG {g} is not supported (RANLUX0-4, XOR128, PM, MRG32K3A, XOR7, RANECU, RANMAR)")
         self.produce()     # random.cpp:276
 
     # RL_initialize_CPU + RL_initialize: random.cpp:425-522
@@ -125,6 +131,67 @@ class PRNG:
         self.PRNG_seed_table_id = gpu.buffer_init(GPU.buffer_type_IO, 2 * I, seeds, 16)
         self.PRNG_randoms_id = gpu.buffer_init(GPU.buffer_type_IO, I * self.PRNG_samples, None, 16)
         self.PRNG_randoms_kernel_id = gpu.kernel_init("mrg32k3a", 1, [I], None)
+        gpu.kernel_init_buffer(self.PRNG_randoms_kernel_id, self.PRNG_seed_table_id)
+        gpu.kernel_init_buffer(self.PRNG_randoms_kernel_id, self.PRNG_randoms_id)
+        gpu.kernel_init_constant(self.PRNG_randoms_kernel_id, int(self.PRNG_samples))
+
+    def _two_row_kernel(self, kernel: str, seeds: np.ndarray):
+        """seed table = uint4 row 1 [I] then uint4 row 2 [I]; producer kernel(seed_table, randoms, samples)."""
+        gpu, I = self.GPU0, self.PRNG_instances
+        self.seeds = seeds
+        gpu.program_create(None, "")
+        self.PRNG_seed_table_id = gpu.buffer_init(GPU.buffer_type_IO, 2 * I, seeds, 16)
+        self.PRNG_randoms_id = gpu.buffer_init(GPU.buffer_type_IO, I * self.PRNG_samples, None, 16)
+        self.PRNG_randoms_kernel_id = gpu.kernel_init(kernel, 1, [I], None)
+        gpu.kernel_init_buffer(self.PRNG_randoms_kernel_id, self.PRNG_seed_table_id)
+        gpu.kernel_init_buffer(self.PRNG_randoms_kernel_id, self.PRNG_randoms_id)
+        gpu.kernel_init_constant(self.PRNG_randoms_kernel_id, int(self.PRNG_samples))
+
+    # XOR7_initialize_CPU + XOR7_initialize: random.cpp:921-974.  Eight rand() for the host replica's state, then rows 1 .. 2I-1 of
+    # the table (row 0 is skipped, row I is drawn and then overwritten); instance 0 = the host replica.
+    def _xor7_initialize(self):
+        I = self.PRNG_instances
+        state = host_rand_fill(8)
+        seeds = np.zeros(8 * I, dtype=np.uint32)
+        seeds[4:] = host_rand_fill(8 * I - 4)
+        seeds[0:4] = state[0:4]
+        seeds[4 * I:4 * I + 4] = state[4:8]
+        self._two_row_kernel("xor7", seeds)
+
+    # RANECU_initialize_CPU + RANECU_initialize: random.cpp:1003-1048.  Lane x of instance 0 = the host replica.
+    def _ranecu_initialize(self):
+        I = self.PRNG_instances
+        jseed = host_rand_fill(2, 2147483647)
+        seeds = host_rand_fill(8 * I, 2147483647)
+        seeds[0] = jseed[0]
+        seeds[4 * I] = jseed[1]
+        self._two_row_kernel("ranecu", seeds)
+
+    # RANMAR_initialize_CPU + RANMAR_initialize: random.cpp:708-799.  Two seeds per lane; all four lanes of instance 0 carry the host
+    # replica's pair; per further instance four first seeds (% 31328) then four second seeds (% 30081).  The reference's host names
+    # the kernels "rmseed" / "rmproduce" (its .cl file: ranmar_init / ranmar); the backend binds both spellings.
+    def _ranmar_initialize(self):
+        gpu, I = self.GPU0, self.PRNG_instances
+        rm = np.array([host_rand_fill(1, 31328)[0], host_rand_fill(1, 30081)[0]], dtype=np.uint32)
+        seeds = np.zeros(8 * I, dtype=np.uint32)
+        seeds[0:4] = rm[0]
+        seeds[4 * I:4 * I + 4] = rm[1]
+        if I > 1:
+            raw = host_rand_fill(8 * (I - 1)).reshape(I - 1, 8)      # per instance: four first seeds, then four second seeds
+            seeds[4:4 * I] = (raw[:, :4] % 31328).reshape(-1)
+            seeds[4 * I + 4:] = (raw[:, 4:] % 30081).reshape(-1)
+        self.seeds = seeds
+        gpu.program_create(None, "")
+        seeds_size = 2 * I
+        seed_table_size = seeds_size * (97 + 1)       # random.cpp:719: twice what the kernels touch
+        self.PRNG_seed_id = gpu.buffer_init(GPU.buffer_type_Constant, seeds_size, seeds, 16)
+        self.PRNG_seed_table_id = gpu.buffer_init(GPU.buffer_type_IO, seed_table_size, None, 16)
+        self.PRNG_randoms_id = gpu.buffer_init(GPU.buffer_type_IO, I * self.PRNG_samples, None, 16)
+        self.PRNG_randoms_seed_id = gpu.kernel_init("rmseed", 1, [I], None)
+        gpu.kernel_init_buffer(self.PRNG_randoms_seed_id, self.PRNG_seed_id)
+        gpu.kernel_init_buffer(self.PRNG_randoms_seed_id, self.PRNG_seed_table_id)
+        gpu.kernel_run(self.PRNG_randoms_seed_id)
+        self.PRNG_randoms_kernel_id = gpu.kernel_init("rmproduce", 1, [I], None)
         gpu.kernel_init_buffer(self.PRNG_randoms_kernel_id, self.PRNG_seed_table_id)
         gpu.kernel_init_buffer(self.PRNG_randoms_kernel_id, self.PRNG_randoms_id)
         gpu.kernel_init_constant(self.PRNG_randoms_kernel_id, int(self.PRNG_samples))

@@ -8,7 +8,7 @@ writes are committed; nothing at test time needs the reference tree.
   ref_cpurun_*.json : the reference's CPU_RUN program run on an init.dat
                       (plaquette/action table, "% 16.13e" columns of its result file)
   ref_prng_*.json   : instance-0 streams of the reference's PRNG host replicas
-                      (RL_produce_one_CPU, PM_produce_one_CPU) as raw float bits
+                      (RL_produce_one_CPU, PM_produce_one_CPU, XOR7_ / RANECU_ / RANMAR_produce_one_CPU) as raw float bits
 """
 import glob
 import json
@@ -36,7 +36,8 @@ CPURUN_FIXTURES = {
 }
 
 PRNG_FIXTURES = [("RANLUX0", 54, 200), ("RANLUX1", 54, 200), ("RANLUX2", 54, 400), ("RANLUX3", 54, 1000),
-                 ("RANLUX4", 54, 1000), ("RANLUX3", 1420193282, 400), ("PM", 54, 400), ("PM", 7, 100)]
+                 ("RANLUX4", 54, 1000), ("RANLUX3", 1420193282, 400), ("PM", 54, 400), ("PM", 7, 100),
+                 ("XOR7", 54, 400), ("XOR7", 7, 100), ("RANECU", 54, 400), ("RANECU", 7, 100), ("RANMAR", 54, 400), ("RANMAR", 7, 300)]
 
 
 def run_cpurun(params):

@@ -18,7 +18,7 @@ LIB_PATH = os.path.join(ORACLE_DIR, "liboracle.so")
 REF_BIN = os.path.join(ORACLE_DIR, "_ref", "QCDGPU_cpu")
 
 PRNG_IDS = {"XOR128": 1, "RANLUX0": 2, "RANLUX1": 3, "RANLUX2": 4, "RANLUX3": 5,
-            "RANLUX4": 6, "PM": 9, "MRG32K3A": 12}
+            "RANLUX4": 6, "RANMAR": 8, "PM": 9, "XOR7": 10, "RANECU": 11, "MRG32K3A": 12}
 
 
 class OrcCfg(C.Structure):

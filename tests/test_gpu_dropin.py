@@ -75,6 +75,19 @@ def test_reference_host_runs_on_cuda_backend_and_verifies_itself(tmp_path, group
         assert plq_total[0] == float(group)
 
 
+@pytest.mark.parametrize("prng", ["XOR7", "RANECU", "RANMAR", "PM", "XOR128"])
+def test_reference_host_with_the_other_generators(tmp_path, prng):
+    """init.dat's PRNG key (random.cpp:146-153): the reference's host builds the seed tables and asks for the kernels by its own names
+    ("xor7", "ranecu", "rmseed" / "rmproduce" -- the latter two do not even exist in its .cl file, which defines ranmar_init / ranmar)."""
+    text, stdout = run_reference_host(tmp_path, group=3, ints=0, beta=6.0, prng=prng, ls=6, lt=4)
+    assert "Verification successfully passed" in text, text[-3000:]
+    if prng != "PM":        # print_generator has no line for Park-Miller (random.cpp:160-169)
+        assert re.search(r"PRN generator\s*:\s*" + prng, text), text[:3000]
+    rows = [l.split() for l in text.splitlines() if re.match(r"^\s+\d+\s+[-\d]", l)]
+    plq = [float(r[3]) for r in rows]
+    assert len(plq) == 4 and all(-0.5 < p < 3.0 for p in plq) and len(set(plq)) == 4 and plq[-1] > plq[0], plq
+
+
 def test_reference_host_twisted_run_verifies(tmp_path):
     """PHI != 0 (init.dat sample value 3.0): twisted loads in staples, measurements and the CPU check."""
     text, _ = run_reference_host(tmp_path, group=3, ints=0, beta=6.0, phi=3.0, ls=6, lt=4)

@@ -111,7 +111,7 @@ def test_update_trajectory_equals_the_oracle(precision, nhit, ints, prng):
     m.close()
 
 
-@pytest.mark.parametrize("prng", ["XOR128", "PM", "MRG32K3A"])
+@pytest.mark.parametrize("prng", ["XOR128", "PM", "MRG32K3A", "XOR7", "RANECU", "RANMAR"])
 @pytest.mark.parametrize("nhit", [10, 5])
 def test_fused_generator_equals_buffered(prng, nhit):
     """PRNG_instances == PRNGSTEP: the generator runs inside the update kernel (state in registers) and the PRN buffer is

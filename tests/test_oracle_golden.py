@@ -85,6 +85,24 @@ def test_prng_streams_bit_exact(path):
         ints_dev = np.round(buf.astype(np.float64) * 2147483648.0)
         ints_host = np.round(host.view(np.float32).astype(np.float64) * 2147483647.0)
         assert np.max(np.abs(ints_dev - ints_host)) <= 128  # float32 has 24 bits
+    if g["generator"] == "XOR7":
+        # four consecutive numbers per float4: instance 0 of the device-layout producer IS the host replica's stream
+        P = O.Prng("XOR7", g["randseries"], instances=8)
+        buf = P.produce(n // 4).reshape(n // 4, 8, 4)
+        np.testing.assert_array_equal(buf[:, 0, :].reshape(-1).view(np.uint32), want[: 4 * (n // 4)])
+    if g["generator"] in ("RANECU", "RANMAR"):
+        # four independent lanes per instance: lane x of instance 0 is the host replica (i_quads = 1, random.cpp:360-362)
+        P = O.Prng(g["generator"], g["randseries"], instances=8)
+        buf = P.produce(n).reshape(n, 8, 4)
+        np.testing.assert_array_equal(buf[:, 0, 0].view(np.uint32), want)
+        P2 = O.Prng(g["generator"], g["randseries"], instances=8)
+        a = P2.produce(7).reshape(7, 8, 4)
+        b = P2.produce(n - 7).reshape(n - 7, 8, 4)
+        np.testing.assert_array_equal(np.concatenate([a, b]), buf)
+        if g["generator"] == "RANMAR":       # all four lanes of instance 0 carry the replica's seeds
+            for lane in range(1, 4):
+                np.testing.assert_array_equal(buf[:, 0, lane], buf[:, 0, 0])
+        assert np.all(buf >= 0.0) and np.all(buf < 1.0)
 
 
 def test_xor128_known_answer():
