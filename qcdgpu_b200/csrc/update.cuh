@@ -811,9 +811,13 @@ __device__ __forceinline__ V4<R> block_dagger(const M3<R>& W, R& det) {
 // One Cabibbo-Marinari round over the subgroups (0,1), (0,2), (1,2) in the reference's order.  The loop is NOT unrolled:
 // the Kennedy-Pendleton code (log, cospi, sincospi, sqrt) is instantiated once; only the small block-extraction and
 // row-rotation pieces are per-subgroup (uniform switch, no divergence).
+#ifndef QCD_CM_UNROLL      // experiment knob: 3 = the three subgroup steps as straight-line code (Kennedy-Pendleton instantiated three times)
+#define QCD_CM_UNROLL 1
+#endif
+constexpr int kCmUnroll = QCD_CM_UNROLL;
 template <typename R, class Prn>
 __device__ __forceinline__ void cm_round(M3<R>& U, M3<R>& W, const Geom& g, R beta, Prn& prn) {
-#pragma unroll 1
+#pragma unroll kCmUnroll
     for (int sub = 0; sub < 3; sub++) {
         R idet;
         V4<R> aH;
