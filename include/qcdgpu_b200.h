@@ -163,6 +163,21 @@ int   qgpu_halo_copy(qgpu* dst, int dst_program, int dst_buffer, unsigned x_dst,
 int   qgpu_halo_pack(qgpu* h, int program, int buffer, unsigned x_src, int dir, void* packed_dev, size_t* bytes);
 int   qgpu_halo_unpack(qgpu* h, int program, int buffer, unsigned x_dst, int dir, const void* packed_dev);
 size_t qgpu_halo_bytes(qgpu* h, int program, int dir);
+/* Halo exchange FUSED into the update kernels (one process per GPU; no counterpart in the reference, whose model::UpdateEdges,
+ * suncl.cpp:4005-4062, copies the slices through mapped host memory after the pass).  The link table of a neighbouring part is
+ * opened as peer memory (CUDA IPC handle of its buffer, exchanged by the host over its own transport); an update / overrelaxation
+ * kernel that was given a peer then stores every link it updates in stored x-slice `src_x` (side 0: the first real slice, side 1:
+ * the last one) a second time, into x-slice `dst_x` of the peer table, over NVLink -- no pack kernel, no NCCL call, no unpack kernel.
+ * peer_table = NULL clears a side.  The hand-shake: qgpu_halo_signal (stream-ordered) writes `value` into one flag word of each
+ * neighbour (peer pointers into their flag buffers: word 0 = "from my left neighbour", word 1 = "from my right neighbour");
+ * qgpu_halo_wait (stream-ordered) holds the stream until both of MY words have reached `value`, or gives up after timeout_s and
+ * counts that in word 2 of the flag buffer (four 64-bit words, zeroed by the host). */
+int   qgpu_buffer_ipc_export(qgpu* h, int buffer_id, unsigned char handle[64]);
+void* qgpu_ipc_open(qgpu* h, const unsigned char handle[64]);
+int   qgpu_ipc_close(qgpu* h, void* peer_ptr);
+int   qgpu_kernel_set_peer_halo(qgpu* h, int kernel_id, int side, void* peer_table, unsigned src_x, unsigned dst_x, size_t peer_rowsize);
+int   qgpu_halo_signal(qgpu* h, void* peer_flag_a, void* peer_flag_b, unsigned long long value);
+int   qgpu_halo_wait(qgpu* h, int flags_buffer_id, unsigned long long value, double timeout_s);
 
 /* host helpers: glibc srand()/rand() in bulk (seed tables are defined through them, random.cpp:235,462-465) */
 void  qgpu_host_srand(unsigned seed);

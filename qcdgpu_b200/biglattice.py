@@ -20,6 +20,11 @@ What is new here:
   * optionally (QCDGPU_HALO_DIRECT=1) NCCL sends the boundary slices straight out of the link table and receives straight into the
     halo slices (a slice of a vec4 plane is contiguous): no pack / unpack kernels, no staging buffers -- measured slightly slower
     than the staged exchange, which stays the default;
+  * QCDGPU_HALO_FUSED=1 (one process per GPU): no exchange step at all.  Every part opens its neighbours' link tables as peer
+    memory (CUDA IPC), and the update kernel of a boundary slice stores each updated link twice: into its own table and, over NVLink,
+    into the neighbour's halo slice (Geom::peer_*, lattice.cuh).  A flag word per neighbour carries the pass number: a part waits for
+    "pass n - 1 written" from both sides before its boundary launch of pass n and announces n behind it (two one-warp kernels);
+    inside a pass the checkerboard already keeps writers and readers apart, across parts as within one;
   * observables are summed over parts with one small all-reduce.
 """
 from __future__ import annotations
@@ -140,6 +145,10 @@ class BigLattice:
         # the default
         self.direct_halo = os.environ.get("QCDGPU_HALO_DIRECT", "0") == "1"
         self.pair_launch = os.environ.get("QCDGPU_HALO_PAIR", "1") != "0"     # both boundary slices in one launch
+        # halo exchange fused into the update kernels (peer stores + flags); needs one process per GPU and equal slabs
+        self.fused_halo = os.environ.get("QCDGPU_HALO_FUSED", "0") == "1" and dist is not None and nparts > 1 and len(set(self.Nx_all)) == 1
+        self._peer = None
+        self._pass_no = 0
         self.halo_bytes_per_pass = 0
 
     # ------------------------------------------------------------------ set-up
@@ -167,6 +176,12 @@ class BigLattice:
             else:
                 p.GPU0.kernel_run(p.sun_init_id)
         self.finish_edges(self.update_edges(-1))          # a hot start fills halos with unrelated links: take the neighbours' real ones
+        if self.fused_halo:
+            # the start-up exchange went through NCCL, whose receive side may still be copying into my halos when a neighbour's first
+            # boundary launch stores into them: everybody finishes it before anybody starts a pass
+            self.synchronize()
+            self.dist.barrier()
+            self._setup_fused_halo()
         if self.dist is None and len(self.parts) > 1:
             # This exchange copies ALL planes of the neighbours' boundary slices on the READERS' streams; the owners' first update pass
             # writes direction X there.  Per-pass exchanges are ordered by plane separation, this one needs the readers to be done.
@@ -198,6 +213,37 @@ class BigLattice:
             planes = [dd + 4 * k for dd in ((d,) if d >= 0 else range(4)) for k in range(p.lattice_group_elements // 4)]
             t = self._chunks[key] = [table[(pl * row + x * n234) * vec: (pl * row + (x + 1) * n234) * vec] for pl in planes]
         return t
+
+    def _setup_fused_halo(self):
+        """Open the neighbours' link tables and flag words as peer memory and tell every update kernel where its boundary links go."""
+        dist, p = self.dist, self.parts[self.local[0]]
+        g = p.GPU0
+        self._flags = g.buffer_init(GPU.buffer_type_Global, 4, np.zeros(4, dtype=np.uint64), 8)
+        mine = (g.buffer_ipc_export(p.lattice_table), g.buffer_ipc_export(self._flags), int(p.lattice_table_row_size), int(p.Nx))
+        everyone = [None] * self.nparts
+        dist.all_gather_object(everyone, mine)
+        left, right = ring_neighbours(p.k, self.nparts)
+        opened = {}
+        for k in {left, right}:
+            th, fh, row, nx = everyone[k]
+            opened[k] = (g.ipc_open(th), g.ipc_open(fh), row, nx)
+        (lt, lf, lrow, lnx), (rt, rf, rrow, _) = opened[left], opened[right]
+        kids = list(p.sun_update_id.values()) + list(getattr(p, "sun_overrelax_id", {}).values())
+        for kid in kids:
+            g.kernel_set_peer_halo(kid, 0, lt, p.x_first_real, lnx + 1, lrow)     # my first real slice -> left neighbour's right halo
+            g.kernel_set_peer_halo(kid, 1, rt, p.x_last_real, 0, rrow)            # my last real slice  -> right neighbour's left halo
+        # the word I write at each neighbour: its "from my right" (word 1) at the left one, its "from my left" (word 0) at the right one
+        self._peer = {"opened": opened, "flag_left": lf + 8, "flag_right": rf}
+        self.halo_bytes_per_pass = 2 * g.halo_bytes(p.program_update, 0)
+        self.synchronize()
+        dist.barrier()
+
+    def _check_halo_timeouts(self):
+        if self._peer is not None:
+            p = self.parts[self.local[0]]
+            lost = int(p.GPU0.buffer_map(self._flags, np.uint64)[2])
+            if lost:
+                raise QcdGpuError(f"fused halo exchange: {lost} wait(s) for a neighbour's pass flag timed out")
 
     def update_edges(self, d: int):
         """Direction-d planes (all planes if d < 0) of every part's two boundary slices -> neighbours' halos."""
@@ -254,12 +300,39 @@ class BigLattice:
             p.GPU0.halo_unpack(p.program_update, p.lattice_table, p.x_right_halo, d, r_right.data_ptr())
 
     # ------------------------------------------------------------------ sweeps (lattice_simulate BIGLAT, suncl.cpp:4804-5210)
-    def _update_pass(self, par: str, d: str):
+    def _update_pass_fused(self, par: str, d: str, overrelax: bool = False):
+        """One pass with the exchange inside the kernels: wait for the neighbours' previous pass, boundary slices (stored here AND in
+        the neighbours' halos), announce the pass, interior slices."""
+        p = self.parts[self.local[0]]
+        g, kid = p.GPU0, (p.sun_overrelax_id if overrelax else p.sun_update_id)[(par, d)]
+        self._pass_no += 1
+        n = self._pass_no
+        if not overrelax:
+            p.PRNG0.produce()
+        g.halo_wait(self._flags, n - 1)
+        if p.Nx >= 3:
+            g.kernel_set_x_range(kid, 0, 2, p.Nx - 1)
+            g.kernel_run(kid)
+            g.halo_signal(self._peer["flag_left"], self._peer["flag_right"], n)
+            g.kernel_set_x_range(kid, 1, p.Nx - 2)
+            g.kernel_run(kid)
+        else:
+            g.kernel_set_x_range(kid, 0, -1)
+            g.kernel_run(kid)
+            g.halo_signal(self._peer["flag_left"], self._peer["flag_right"], n)
+
+    def _update_pass(self, par: str, d: str, overrelax: bool = False):
+        """One (parity, direction) pass of all local parts + the exchange of what it changed; overrelax: the PRNG-free overrelaxation
+        pass (`or_steps`) through the same schedule."""
+        if self._peer is not None:
+            return self._update_pass_fused(par, d, overrelax)
         di = DIRS.index(d)
         split = self.overlap and all(p.Nx >= 3 for p in self.parts.values())
+        kids = {k: (p.sun_overrelax_id if overrelax else p.sun_update_id)[(par, d)] for k, p in self.parts.items()}
         for p in self.parts.values():
-            p.PRNG0.produce()
-            kid = p.sun_update_id[(par, d)]
+            if not overrelax:
+                p.PRNG0.produce()
+            kid = kids[p.k]
             if split:
                 # boundary slices first so that their links can travel while the interior is updated: both in ONE launch (slices 0 and
                 # Nx - 1 = a range of two with stride Nx - 1; as two launches each pays its own ramp-up and tail, ~0.1 ms at 64^3)
@@ -278,14 +351,14 @@ class BigLattice:
             pending = self.update_edges(di)
             if split:
                 for p in self.parts.values():
-                    kid = p.sun_update_id[(par, d)]
+                    kid = kids[p.k]
                     p.GPU0.kernel_set_x_range(kid, 1, p.Nx - 2)
                     p.GPU0.kernel_run(kid)
             self.finish_edges(pending)
         else:
             if split:
                 for p in self.parts.values():
-                    kid = p.sun_update_id[(par, d)]
+                    kid = kids[p.k]
                     p.GPU0.kernel_set_x_range(kid, 1, p.Nx - 2)
                     p.GPU0.kernel_run(kid)
             self.update_edges(di)
@@ -294,9 +367,15 @@ class BigLattice:
         for par in ("odd", "even"):
             for d in DIRS:
                 self._update_pass(par, d)
+        for _ in range(next(iter(self.parts.values())).or_steps):
+            for par in ("odd", "even"):
+                for d in DIRS:
+                    self._update_pass(par, d, overrelax=True)
         if self.dist is None and len(self.parts) > 1:
             for p in self.parts.values():      # halo copies read neighbours' tables on the readers' streams
                 p.GPU0.synchronize()
+        if self._peer is not None:             # my halos hold the neighbours' last pass before anything else reads them
+            self.parts[self.local[0]].GPU0.halo_wait(self._flags, self._pass_no)
         for p in self.parts.values():
             if not p.turnoff_gramschmidt:
                 p.GPU0.kernel_run(p.sun_GramSchmidt_id)
@@ -311,6 +390,7 @@ class BigLattice:
             p.GPU0.synchronize()
         if self._stream is not None:
             self._stream.synchronize()
+        self._check_halo_timeouts()
 
     def lattice_simulate(self):
         self.lattice_start()
@@ -352,6 +432,14 @@ class BigLattice:
         return A
 
     def close(self):
+        if self._peer is not None:
+            self.synchronize()
+            self.dist.barrier()                 # nobody unmaps a table a neighbour may still be storing into
+            g = self.parts[self.local[0]].GPU0
+            for t, f, _, _ in self._peer["opened"].values():
+                g.ipc_close(t)
+                g.ipc_close(f)
+            self._peer = None
         for p in self.parts.values():
             p.close()
 
@@ -438,7 +526,9 @@ def bench_main(args, workload):
             "config": workload_config(world, dims),
             "details": {"sweeps_per_s": args.steps / (ms * 1e-3), "halo_bytes_per_pass_per_gpu": B.halo_bytes_per_pass,
                         "plaquette_after_run": float(plq.sum() / (6.0 * V_total)),
-                        "halo": ("NCCL send/recv straight from / into the link tables (contiguous slice per vec4 plane), overlapped with the interior update"
+                        "halo": ("fused into the update kernels: boundary links are stored into the neighbours' halo slices over NVLink peer memory (CUDA IPC), a flag word per neighbour carries the pass number"
+                                 if B._peer is not None else
+                                 "NCCL send/recv straight from / into the link tables (contiguous slice per vec4 plane), overlapped with the interior update"
                                  if B.direct_halo else "NCCL send/recv of packed boundary slices, overlapped with the interior update")},
             "roofline": {"bound": "hbm", "achieved": bytes_per_s, "peak": peak, "unit": "GB/s", "frac": bytes_per_s / peak,
                          "traffic": None, "peak_source": peak_kind, "note": "per GPU, whole sweep (update + halo + reunitarisation)"},

@@ -52,7 +52,8 @@ EXPORTS = [
     "qgpu_set_fused_prng", "qgpu_set_tile_x", "qgpu_set_fold_reunitarisation", "qgpu_profile_collect", "qgpu_set_stream", "qgpu_kernel_set_x_range", "qgpu_kernel_set_x_range_strided", "qgpu_buffer_device_ptr", "qgpu_stream", "qgpu_timer_start",
     "qgpu_timer_stop", "qgpu_launch_count", "qgpu_update_kernel_registers", "qgpu_halo_copy",
     "qgpu_halo_pack", "qgpu_halo_unpack", "qgpu_halo_bytes", "qgpu_host_srand", "qgpu_host_rand_fill",
-    "qgpu_ranlux_jump_table",
+    "qgpu_ranlux_jump_table", "qgpu_buffer_ipc_export", "qgpu_ipc_open", "qgpu_ipc_close", "qgpu_kernel_set_peer_halo",
+    "qgpu_halo_signal", "qgpu_halo_wait",
 ]
 
 
@@ -140,6 +141,13 @@ def load(build_if_missing: bool = True):
     L.qgpu_halo_pack.argtypes = [vp, ci, ci, cu, ci, vp, C.POINTER(sz)]
     L.qgpu_halo_unpack.argtypes = [vp, ci, ci, cu, ci, vp]
     L.qgpu_halo_bytes.argtypes = [vp, ci, ci]
+    L.qgpu_buffer_ipc_export.argtypes = [vp, ci, vp]
+    L.qgpu_ipc_open.argtypes = [vp, vp]
+    L.qgpu_ipc_open.restype = vp
+    L.qgpu_ipc_close.argtypes = [vp, vp]
+    L.qgpu_kernel_set_peer_halo.argtypes = [vp, ci, ci, vp, cu, cu, sz]
+    L.qgpu_halo_signal.argtypes = [vp, vp, vp, C.c_ulonglong]
+    L.qgpu_halo_wait.argtypes = [vp, ci, C.c_ulonglong, C.c_double]
     L.qgpu_halo_bytes.restype = sz
     L.qgpu_host_srand.argtypes = [cu]
     L.qgpu_host_rand_fill.argtypes = [vp, sz, C.c_uint32, C.c_uint32]
@@ -342,6 +350,31 @@ class GPU:
 
     def halo_unpack(self, program, buffer, x_dst, direction, packed_ptr: int):
         self._chk(self.L.qgpu_halo_unpack(self.h, program, buffer, x_dst, direction, C.c_void_p(packed_ptr)), "halo_unpack")
+
+    # -- halo exchange fused into the update kernels (peer memory through CUDA IPC)
+    def buffer_ipc_export(self, buffer: int) -> bytes:
+        h = (C.c_ubyte * 64)()
+        self._chk(self.L.qgpu_buffer_ipc_export(self.h, buffer, h), "buffer_ipc_export")
+        return bytes(h)
+
+    def ipc_open(self, handle: bytes) -> int:
+        h = (C.c_ubyte * 64).from_buffer_copy(handle)
+        p = self.L.qgpu_ipc_open(self.h, h)
+        if not p:
+            self._chk(-1, "ipc_open")
+        return int(p)
+
+    def ipc_close(self, ptr: int):
+        self._chk(self.L.qgpu_ipc_close(self.h, C.c_void_p(ptr)), "ipc_close")
+
+    def kernel_set_peer_halo(self, kernel: int, side: int, peer_table: int, src_x: int, dst_x: int, peer_rowsize: int):
+        self._chk(self.L.qgpu_kernel_set_peer_halo(self.h, kernel, side, C.c_void_p(peer_table or None), src_x, dst_x, peer_rowsize), "kernel_set_peer_halo")
+
+    def halo_signal(self, flag_a: int, flag_b: int, value: int):
+        self._chk(self.L.qgpu_halo_signal(self.h, C.c_void_p(flag_a or None), C.c_void_p(flag_b or None), value), "halo_signal")
+
+    def halo_wait(self, flags_buffer: int, value: int, timeout_s: float = 5.0):
+        self._chk(self.L.qgpu_halo_wait(self.h, flags_buffer, value, timeout_s), "halo_wait")
 
     def close(self):
         if self.h:

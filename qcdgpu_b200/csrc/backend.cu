@@ -73,6 +73,7 @@ struct Kernel {
     bool local_given = false;
     int x_first = 0, x_count = -1;   // update kernels: x-range of the launch inside the updated region (-1 = all)
     int x_stride = 1;                // distance between the slices of the range
+    struct PeerHalo { void* table = nullptr; uint32_t src_x = 0, dst_x = 0, rowsize = 0; } peer[2];   // qgpu_kernel_set_peer_halo
     std::vector<Arg> args;
     // profiling (GPU_debug.profiling)
     double t_sum = 0, t_sq = 0; int starts = 0;
@@ -463,6 +464,14 @@ int launch_kernel(qgpu* h, int kid) {
             if (!a.table || !a.params) return fail(h, "kernel %s: arguments (lattice_table, lattice_parameters) not set", k.name.c_str());
             a.geom = make_geom(c, h->tile_x); a.odd = k.odd; a.tbc = c.tbc ? 1 : 0;
             a.geom.fold_gs = (h->fold_gs && c.sun == 3) ? 1u : 0u;
+            for (int sd = 0; sd < 2; sd++) {     // halo exchange fused into the update: boundary-slice links also go to the neighbours' halo slices
+                if (!k.peer[sd].table) continue;
+                a.geom.peer_on = 1u;
+                a.geom.peer_table[sd] = (unsigned long long)(uintptr_t)k.peer[sd].table;
+                a.geom.peer_lo[sd] = k.peer[sd].src_x * a.geom.n234;
+                a.geom.peer_shift[sd] = (k.peer[sd].dst_x - k.peer[sd].src_x) * a.geom.n234;
+                a.geom.peer_rowsize[sd] = k.peer[sd].rowsize;
+            }
             const uint32_t nx_all = a.geom.upd_nx;
             if (k.x_count >= 0) {
                 if (k.x_stride < 1 || (k.x_count > 0 && (uint64_t)k.x_first + (uint64_t)(k.x_count - 1) * k.x_stride >= a.geom.upd_nx) || k.x_first < 0)
@@ -1230,6 +1239,59 @@ int qgpu_halo_copy(qgpu* dst, int dprog, int dbuf, unsigned xd, qgpu* src, int s
     if (!dst->async) CUDA_OK(dst, cudaStreamSynchronize(dst->stream));
     return 0;
 }
+// ---- halo exchange fused into the update kernels (one process per GPU): peer memory through CUDA IPC, flags for the hand-shake
+int qgpu_buffer_ipc_export(qgpu* h, int buffer, unsigned char handle[64]) {
+    if (!valid_buf(h, buffer) || !h->buffers[buffer].dptr) return fail(h, "ipc_export: bad buffer id %d", buffer);
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    cudaIpcMemHandle_t mh;
+    CUDA_OK(h, cudaSetDevice(h->device));
+    CUDA_OK(h, cudaIpcGetMemHandle(&mh, h->buffers[buffer].dptr));
+    memcpy(handle, &mh, 64);
+    return 0;
+}
+void* qgpu_ipc_open(qgpu* h, const unsigned char handle[64]) {
+    cudaIpcMemHandle_t mh;
+    memcpy(&mh, handle, 64);
+    void* p = nullptr;
+    if (cudaSetDevice(h->device) != cudaSuccess || cudaIpcOpenMemHandle(&p, mh, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+        fail(h, "ipc_open: %s", cudaGetErrorString(cudaGetLastError()));
+        return nullptr;
+    }
+    return p;
+}
+int qgpu_ipc_close(qgpu* h, void* ptr) {
+    if (!ptr) return 0;
+    CUDA_OK(h, cudaSetDevice(h->device));
+    CUDA_OK(h, cudaIpcCloseMemHandle(ptr));
+    return 0;
+}
+int qgpu_kernel_set_peer_halo(qgpu* h, int kid, int side, void* peer_table, unsigned src_x, unsigned dst_x, size_t peer_rowsize) {
+    if (!valid_kernel(h, kid)) return fail(h, "bad kernel id %d", kid);
+    Kernel& k = h->kernels[kid];
+    if (k.kind != K_UPDATE && k.kind != K_OVERRELAX) return fail(h, "kernel %s stores no links: no peer halo", k.name.c_str());
+    if (side < 0 || side > 1) return fail(h, "kernel %s: peer side %d (0 = first real slice, 1 = last real slice)", k.name.c_str(), side);
+    const ProgramCfg& c = h->programs[k.program];
+    if (peer_table && (!c.biglat || src_x < 1 || src_x + 1 >= c.n1)) return fail(h, "kernel %s: peer halo needs a -D BIGLAT program and a real source slice (got %u of %u)", k.name.c_str(), src_x, c.n1);
+    k.peer[side].table = peer_table; k.peer[side].src_x = src_x; k.peer[side].dst_x = dst_x; k.peer[side].rowsize = (uint32_t)peer_rowsize;
+    return 0;
+}
+int qgpu_halo_signal(qgpu* h, void* flag_a, void* flag_b, unsigned long long value) {
+    CUDA_OK(h, cudaSetDevice(h->device));
+    CUDA_OK(h, launch_halo_signal((unsigned long long*)flag_a, (unsigned long long*)flag_b, value, h->stream));
+    h->launches++;
+    return 0;
+}
+int qgpu_halo_wait(qgpu* h, int flags_buffer, unsigned long long value, double timeout_s) {
+    if (!valid_buf(h, flags_buffer) || h->buffers[flags_buffer].bytes < 32) return fail(h, "halo_wait: the flag buffer holds four 64-bit words (from the left, from the right, time-outs, spare)");
+    CUDA_OK(h, cudaSetDevice(h->device));
+    int khz = 0;
+    CUDA_OK(h, cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, h->device));
+    const unsigned long long clocks = (unsigned long long)(timeout_s * 1e3 * (double)khz);
+    CUDA_OK(h, launch_halo_wait((unsigned long long*)h->buffers[flags_buffer].dptr, value, clocks, h->stream));
+    h->launches++;
+    return 0;
+}
+
 int qgpu_halo_pack(qgpu* h, int program, int buffer, unsigned xs, int dir, void* packed, size_t* bytes) {
     if (program <= 0 || program >= (int)h->programs.size() || !valid_buf(h, buffer)) return fail(h, "halo_pack: bad id");
     const ProgramCfg& c = h->programs[program];

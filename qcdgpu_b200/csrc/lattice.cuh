@@ -37,6 +37,13 @@ struct Geom {
                                   // lattice_GramSchmidt pass would do to it later; the backend then skips that pass (backend.cu, gs_cover)
     uint32_t upd_x0, upd_nx;      // x-range of this launch inside the updated region (halo/interior split); nthreads = upd_nx*N4*N2/2*N3
     uint32_t upd_xstride;         // distance between the launch's slices (1; Nx - 1 for the two boundary slices in one launch; tile_x == 0 then)
+    // BIGLAT, halo exchange fused into the update (qgpu_kernel_set_peer_halo): an updated link of my first / last real x-slice is ALSO
+    // stored into the halo slice of the left / right neighbour's link table, a pointer into peer memory (NVLink).  peer_on == 0: none.
+    uint32_t peer_on;
+    uint32_t peer_lo[2];          // first site index of the source slice (my first real slice, my last real slice)
+    uint32_t peer_shift[2];       // added to the site index (mod 2^32): (neighbour's halo slice - source slice) * N2N3N4
+    uint32_t peer_rowsize[2];     // ROWSIZE of the neighbour's table
+    unsigned long long peer_table[2];   // 0: no neighbour on that side
 };
 
 struct Coord { uint32_t x, y, z, t; };
@@ -183,6 +190,15 @@ __device__ __forceinline__ V4<R> ld_plane(const R* table, const Geom& g, uint32_
 template <typename R>
 __device__ __forceinline__ void st_plane(R* table, const Geom& g, uint32_t gindex, uint32_t plane, const V4<R>& v) {
     stv4(table + 4 * (size_t(gindex) + size_t(plane) * g.rowsize), v);
+}
+
+// the same vec4 into the neighbours' halo slices when this site lies in a boundary slice (Geom::peer_*); callers test g.peer_on first
+template <typename R>
+__device__ __forceinline__ void st_plane_peer(const Geom& g, uint32_t gindex, uint32_t plane, const V4<R>& v) {
+#pragma unroll
+    for (int s = 0; s < 2; s++)
+        if (g.peer_table[s] != 0ull && (gindex - g.peer_lo[s]) < g.n234)
+            stv4(reinterpret_cast<R*>(g.peer_table[s]) + 4 * (size_t(gindex + g.peer_shift[s]) + size_t(plane) * g.peer_rowsize[s]), v);
 }
 
 // ---------------------------------------------------------------- complex + matrices
@@ -348,6 +364,11 @@ __device__ __forceinline__ void store3(R* table, const Geom& g, uint32_t gindex,
     st_plane(table, g, gindex, DIR + 0, a);
     st_plane(table, g, gindex, DIR + 4, b);
     st_plane(table, g, gindex, DIR + 8, c);
+    if (g.peer_on) {
+        st_plane_peer(g, gindex, DIR + 0, a);
+        st_plane_peer(g, gindex, DIR + 4, b);
+        st_plane_peer(g, gindex, DIR + 8, c);
+    }
 }
 
 // ---------------------------------------------------------------- Gram-Schmidt (su3_update_cl.cl:228-291)

@@ -80,6 +80,8 @@ cudaError_t launch_init_hot(int sun, int prec, void* table, const Geom&, const v
 cudaError_t launch_gramschmidt(int sun, int prec, void* table, const Geom&, cudaStream_t);
 
 cudaError_t launch_ranlux_init(const uint32_t* seeds, uint32_t* table, uint32_t instances, cudaStream_t);
+cudaError_t launch_halo_signal(unsigned long long* flag_a, unsigned long long* flag_b, unsigned long long value, cudaStream_t);
+cudaError_t launch_halo_wait(unsigned long long* flags, unsigned long long value, unsigned long long timeout_clocks, cudaStream_t);
 cudaError_t launch_ranmar_init(const uint32_t* seeds, float* table, uint32_t instances, cudaStream_t);    // seeds: uint4[2 x instances], table: float4[98 x instances]
 cudaError_t launch_prn_produce(int prn_kind, uint32_t* table, void* prns, uint32_t instances, uint32_t samples, cudaStream_t);
 // advance every RANLUX3 instance of a state table by `samples` float4 without producing them (one modular multiplication each)

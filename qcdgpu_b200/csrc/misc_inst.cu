@@ -57,6 +57,38 @@ cudaError_t launch_ranlux_skip(uint32_t* table, uint32_t instances, uint64_t sam
     return cudaGetLastError();
 }
 
+// Hand-shake of the halo exchange that is fused into the update kernels (Geom::peer_*): after its boundary launch of pass n a part
+// writes n into a flag word in each neighbour's memory; before its next boundary launch it waits until both neighbours have
+// announced the pass before.  The boundary kernel has completed when the signal kernel starts (same stream), so its stores into
+// peer memory are performed; the fence + system-scope release / acquire order them against the flag.
+static __global__ void halo_signal_kernel(unsigned long long* a, unsigned long long* b, unsigned long long value) {
+    __threadfence_system();
+    if (threadIdx.x == 0 && a) asm volatile("st.release.sys.global.u64 [%0], %1;" :: "l"(a), "l"(value) : "memory");
+    if (threadIdx.x == 1 && b) asm volatile("st.release.sys.global.u64 [%0], %1;" :: "l"(b), "l"(value) : "memory");
+}
+// flags[0] = from the left neighbour, flags[1] = from the right one; flags[2] counts waits that gave up after `timeout` clocks
+// (a neighbour that died must not hang this GPU: the host finds the count at its next synchronisation)
+static __global__ void halo_wait_kernel(unsigned long long* flags, unsigned long long value, unsigned long long timeout) {
+    if (threadIdx.x >= 2) return;
+    const unsigned long long* f = flags + threadIdx.x;
+    const long long t0 = clock64();
+    unsigned long long v;
+    for (;;) {
+        asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(f) : "memory");
+        if (v >= value) break;
+        if ((unsigned long long)(clock64() - t0) > timeout) { atomicAdd(flags + 2, 1ull); break; }
+        __nanosleep(200);
+    }
+}
+cudaError_t launch_halo_signal(unsigned long long* a, unsigned long long* b, unsigned long long value, cudaStream_t st) {
+    halo_signal_kernel<<<1, 32, 0, st>>>(a, b, value);
+    return cudaGetLastError();
+}
+cudaError_t launch_halo_wait(unsigned long long* flags, unsigned long long value, unsigned long long timeout_clocks, cudaStream_t st) {
+    halo_wait_kernel<<<1, 32, 0, st>>>(flags, value, timeout_clocks);
+    return cudaGetLastError();
+}
+
 // Halo exchange building block: copy `nplanes` vec4 planes of one x-slice (n234 elements each)
 // between two plane-strided arrays.  Plane k lives at (p0 + k*ps)*row_elems + x*n234.
 // Used table->table (peer pointers over NVLink), table->packed and packed->table.

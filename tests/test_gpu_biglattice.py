@@ -3,6 +3,7 @@ reproduce the unpartitioned one exactly (the reference only promises statistical
 involved, suncl.cpp:377-386); parts can share one device, as in the reference's init_2.dat."""
 import json
 import os
+import re
 import socket
 import subprocess
 import sys
@@ -25,20 +26,26 @@ def _configure(sun, beta, ints, iters, prec=1, fused=False, prng="RANLUX3"):
     return f
 
 
-@pytest.mark.parametrize("sun,dims,nparts", [(3, (4, 6, 2, 8), 1), (3, (4, 6, 2, 8), 2), (3, (12, 4, 2, 4), 3), (2, (8, 4, 8, 2), 2)])
-def test_gid_start_partitioned_equals_single(sun, dims, nparts):
+@pytest.mark.parametrize("sun,dims,nparts,or_steps", [(3, (4, 6, 2, 8), 1, 0), (3, (4, 6, 2, 8), 2, 0), (3, (12, 4, 2, 4), 3, 0), (2, (8, 4, 8, 2), 2, 0),
+                                                     (3, (12, 4, 2, 4), 3, 2), (2, (8, 4, 8, 2), 2, 1)])
+def test_gid_start_partitioned_equals_single(sun, dims, nparts, or_steps):
+    """or_steps > 0: overrelaxation passes after each heat-bath sweep go through the same boundary-first schedule and exchange."""
     from qcdgpu_b200 import Model
     from qcdgpu_b200.biglattice import BigLattice
     beta = 5.7 if sun == 3 else 2.3
     m = Model()
     m.lattice_group, m.lattice_full_size, m.precision, m.ints, m.BETA, m.ITER, m.PL_level = sun, list(dims), 1, 2, beta, 4, 0
+    m.or_steps = or_steps
     m.lattice_init()
     m.lattice_simulate()
     m.lattice_analysis()
     want = np.array([[m.Analysis[c]["data"][i] for c in ("Plq_spat", "Plq_temp", "S_spat", "S_temp")] for i in range(4)])
     m.close()
     for overlap in (False, True):
-        B = BigLattice(dims, nparts, configure=_configure(sun, beta, 2, 4))
+        def conf(p, base=_configure(sun, beta, 2, 4)):
+            base(p)
+            p.or_steps = or_steps
+        B = BigLattice(dims, nparts, configure=conf)
         B.overlap = overlap
         B.lattice_init()
         B.lattice_simulate()
@@ -177,3 +184,54 @@ def test_nccl_two_gpus_gid(tmp_path, direct):
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
     rows = json.loads([l for l in r.stdout.splitlines() if l.startswith("ROWS ")][0][5:])
     np.testing.assert_allclose(np.array(rows), np.array(gold["rows"]), rtol=5e-6)
+
+
+FUSED_WORKER = r'''
+import os, sys, json, hashlib
+import numpy as np, torch, torch.distributed as dist
+sys.path.insert(0, os.environ["QCD_ROOT"])
+from qcdgpu_b200.biglattice import BigLattice
+rank = int(os.environ["RANK"]); world = int(os.environ["WORLD_SIZE"])
+torch.cuda.set_device(rank)
+dist.init_process_group("nccl", device_id=torch.device(f"cuda:{rank}"))
+dims = tuple(int(x) for x in os.environ["QCD_DIMS"].split("x"))
+def conf(p):
+    p.lattice_group, p.precision, p.ints, p.BETA, p.ITER, p.NAV = int(os.environ["QCD_GROUP"]), int(os.environ["QCD_PREC"]), 0, 5.7, 3, 1
+    p.fused_prng = True
+    p.or_steps = int(os.environ.get("QCD_OR", "0"))
+    p.desired_device = rank
+B = BigLattice(dims, world, dist=dist, configure=conf, devices=[rank])
+B.lattice_init(); B.lattice_simulate(); A = B.lattice_analysis()
+p = B.parts[rank]
+t = p.table_numpy()
+print("HASH %d %s %s %d;" % (rank, hashlib.sha256(t.tobytes()).hexdigest(), "peer" if B._peer is not None else "nccl", int(p.GPU0.launch_count())), flush=True)
+if rank == 0:
+    print("PLQ " + json.dumps([float(x) for x in A["Plq_total"]["data"]]))
+B.close(); dist.destroy_process_group()
+'''
+
+
+@pytest.mark.parametrize("group,prec,dims,orx", [(3, 1, "12x64x4x4", 0), (3, 1, "4x6x2x8", 0), (2, 0, "8x8x4x6", 0), (3, 1, "8x64x2x4", 1)])
+def test_fused_halo_exchange_two_gpus(tmp_path, group, prec, dims, orx):
+    """QCDGPU_HALO_FUSED=1: the boundary-slice update kernels store their links into the neighbours' halo slices over peer memory
+    (no pack / NCCL / unpack), a flag word per neighbour carries the pass number.  Same seeds, hot start, three sweeps: every
+    rank's link table -- halo slices included -- must equal the NCCL exchange's bit for bit (TMA-staged kernels, the unsplit launch
+    of two-slice parts, SU(2) fp32 and overrelaxation passes all take the peer path)."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
+    script = tmp_path / "w.py"
+    script.write_text(FUSED_WORKER)
+    out = {}
+    for mode in ("0", "1"):
+        s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+        env = dict(os.environ, QCD_ROOT=ROOT, QCDGPU_HALO_FUSED=mode, QCD_DIMS=dims, QCD_GROUP=str(group), QCD_PREC=str(prec), QCD_OR=str(orx))
+        r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+                            "--master-port", str(port), str(script)], capture_output=True, text=True, env=env, timeout=600)
+        assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
+        h = sorted(list(x) for x in re.findall(r"HASH (\d+) ([0-9a-f]{64}) (peer|nccl) (\d+);", r.stdout))     # the ranks' lines may run into each other
+        assert len(h) == 2 and all(x[2] == ("peer" if mode == "1" else "nccl") for x in h), h
+        out[mode] = ([x[1] for x in h], re.findall(r"PLQ (\[[^\]]*\])", r.stdout)[0], [int(x[3]) for x in h])
+    assert out["0"][0] == out["1"][0], (out["0"], out["1"])
+    assert out["0"][1] == out["1"][1]
+    assert out["1"][2][0] < out["0"][2][0]          # fewer launches: no pack / unpack kernels
