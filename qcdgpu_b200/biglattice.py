@@ -146,7 +146,8 @@ class BigLattice:
         self.direct_halo = os.environ.get("QCDGPU_HALO_DIRECT", "0") == "1"
         self.pair_launch = os.environ.get("QCDGPU_HALO_PAIR", "1") != "0"     # both boundary slices in one launch
         # halo exchange fused into the update kernels (peer stores + flags); needs one process per GPU and equal slabs
-        self.fused_halo = os.environ.get("QCDGPU_HALO_FUSED", "0") == "1" and dist is not None and nparts > 1 and len(set(self.Nx_all)) == 1
+        # (default in that case since it was measured: 28.25 against 29.67 ms per 64^4-slab sweep on 2 B200; QCDGPU_HALO_FUSED=0: NCCL)
+        self.fused_halo = os.environ.get("QCDGPU_HALO_FUSED", "1") != "0" and dist is not None and nparts > 1 and len(set(self.Nx_all)) == 1
         self._peer = None
         self._pass_no = 0
         self.halo_bytes_per_pass = 0
@@ -219,14 +220,32 @@ class BigLattice:
         dist, p = self.dist, self.parts[self.local[0]]
         g = p.GPU0
         self._flags = g.buffer_init(GPU.buffer_type_Global, 4, np.zeros(4, dtype=np.uint64), 8)
-        mine = (g.buffer_ipc_export(p.lattice_table), g.buffer_ipc_export(self._flags), int(p.lattice_table_row_size), int(p.Nx))
+        try:
+            mine = (g.buffer_ipc_export(p.lattice_table), g.buffer_ipc_export(self._flags), int(p.lattice_table_row_size), int(p.Nx))
+        except QcdGpuError:
+            mine = None
         everyone = [None] * self.nparts
         dist.all_gather_object(everyone, mine)
         left, right = ring_neighbours(p.k, self.nparts)
         opened = {}
-        for k in {left, right}:
-            th, fh, row, nx = everyone[k]
-            opened[k] = (g.ipc_open(th), g.ipc_open(fh), row, nx)
+        try:
+            if any(e is None for e in everyone):
+                raise QcdGpuError("a part could not export its link table")
+            for k in {left, right}:
+                th, fh, row, nx = everyone[k]
+                opened[k] = (g.ipc_open(th), g.ipc_open(fh), row, nx)
+            ok = 1
+        except QcdGpuError:
+            ok = 0
+        # all parts or none: a part without peer access to a neighbour (or neighbours in other containers) sends everybody back to NCCL
+        agreed = self._torch.tensor([ok], device=f"cuda:{p.desired_device}")
+        dist.all_reduce(agreed, op=dist.ReduceOp.MIN)
+        if int(agreed.item()) == 0:
+            for t, f, _, _ in opened.values():
+                g.ipc_close(t)
+                g.ipc_close(f)
+            self.fused_halo = False
+            return
         (lt, lf, lrow, lnx), (rt, rf, rrow, _) = opened[left], opened[right]
         kids = list(p.sun_update_id.values()) + list(getattr(p, "sun_overrelax_id", {}).values())
         for kid in kids:

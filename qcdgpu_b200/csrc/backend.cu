@@ -1284,8 +1284,9 @@ int qgpu_halo_signal(qgpu* h, void* flag_a, void* flag_b, unsigned long long val
 int qgpu_halo_wait(qgpu* h, int flags_buffer, unsigned long long value, double timeout_s) {
     if (!valid_buf(h, flags_buffer) || h->buffers[flags_buffer].bytes < 32) return fail(h, "halo_wait: the flag buffer holds four 64-bit words (from the left, from the right, time-outs, spare)");
     CUDA_OK(h, cudaSetDevice(h->device));
-    int khz = 0;
-    CUDA_OK(h, cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, h->device));
+    static int khz_of[64] = { 0 };      // cudaDevAttrClockRate is a driver query of about a millisecond: once per device
+    int& khz = khz_of[h->device & 63];
+    if (!khz) CUDA_OK(h, cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, h->device));
     const unsigned long long clocks = (unsigned long long)(timeout_s * 1e3 * (double)khz);
     CUDA_OK(h, launch_halo_wait((unsigned long long*)h->buffers[flags_buffer].dptr, value, clocks, h->stream));
     h->launches++;

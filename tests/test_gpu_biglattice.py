@@ -168,10 +168,11 @@ B.close(); dist.destroy_process_group()
 '''
 
 
-@pytest.mark.parametrize("direct", ["1", "0"])
+@pytest.mark.parametrize("direct", ["1", "0", "fused"])
 def test_nccl_two_gpus_gid(tmp_path, direct):
     """Two processes, NCCL send/recv of the boundary slices after every pass -- straight from / into the link tables (direct) or
-    staged through packed buffers -- against the reference's CPU_RUN table of the same deterministic (INTS = 2) run."""
+    staged through packed buffers -- or the exchange fused into the update kernels (the default), against the reference's CPU_RUN
+    table of the same deterministic (INTS = 2) run."""
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
@@ -180,35 +181,13 @@ def test_nccl_two_gpus_gid(tmp_path, direct):
     script.write_text(NCCL_WORKER)
     s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
-                        "--master-port", str(port), str(script)], capture_output=True, text=True, env=dict(os.environ, QCD_ROOT=ROOT, QCDGPU_HALO_DIRECT=direct), timeout=600)
+                        "--master-port", str(port), str(script)], capture_output=True, text=True, env=dict(os.environ, QCD_ROOT=ROOT, QCDGPU_HALO_DIRECT="1" if direct == "1" else "0", QCDGPU_HALO_FUSED="1" if direct == "fused" else "0"), timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
     rows = json.loads([l for l in r.stdout.splitlines() if l.startswith("ROWS ")][0][5:])
     np.testing.assert_allclose(np.array(rows), np.array(gold["rows"]), rtol=5e-6)
 
 
-FUSED_WORKER = r'''
-import os, sys, json, hashlib
-import numpy as np, torch, torch.distributed as dist
-sys.path.insert(0, os.environ["QCD_ROOT"])
-from qcdgpu_b200.biglattice import BigLattice
-rank = int(os.environ["RANK"]); world = int(os.environ["WORLD_SIZE"])
-torch.cuda.set_device(rank)
-dist.init_process_group("nccl", device_id=torch.device(f"cuda:{rank}"))
-dims = tuple(int(x) for x in os.environ["QCD_DIMS"].split("x"))
-def conf(p):
-    p.lattice_group, p.precision, p.ints, p.BETA, p.ITER, p.NAV = int(os.environ["QCD_GROUP"]), int(os.environ["QCD_PREC"]), 0, 5.7, 3, 1
-    p.fused_prng = True
-    p.or_steps = int(os.environ.get("QCD_OR", "0"))
-    p.desired_device = rank
-B = BigLattice(dims, world, dist=dist, configure=conf, devices=[rank])
-B.lattice_init(); B.lattice_simulate(); A = B.lattice_analysis()
-p = B.parts[rank]
-t = p.table_numpy()
-print("HASH %d %s %s %d;" % (rank, hashlib.sha256(t.tobytes()).hexdigest(), "peer" if B._peer is not None else "nccl", int(p.GPU0.launch_count())), flush=True)
-if rank == 0:
-    print("PLQ " + json.dumps([float(x) for x in A["Plq_total"]["data"]]))
-B.close(); dist.destroy_process_group()
-'''
+FUSED_WORKER = open(os.path.join(ROOT, "tools", "halo_check.py")).read()
 
 
 @pytest.mark.parametrize("group,prec,dims,orx", [(3, 1, "12x64x4x4", 0), (3, 1, "4x6x2x8", 0), (2, 0, "8x8x4x6", 0), (3, 1, "8x64x2x4", 1)])
