@@ -24,7 +24,8 @@ What is new here:
     memory (CUDA IPC), and the update kernel of a boundary slice stores each updated link twice: into its own table and, over NVLink,
     into the neighbour's halo slice (Geom::peer_*, lattice.cuh).  A flag word per neighbour carries the pass number: a part waits for
     "pass n - 1 written" from both sides before its boundary launch of pass n and announces n behind it (two one-warp kernels);
-    inside a pass the checkerboard already keeps writers and readers apart, across parts as within one;
+    inside a pass the checkerboard already keeps writers and readers apart, across parts as within one; what reads the halos between
+    sweeps (measurements) is fenced by a pass number of its own at the head of each sweep;
   * observables are summed over parts with one small all-reduce.
 """
 from __future__ import annotations
@@ -238,7 +239,7 @@ class BigLattice:
         except QcdGpuError:
             ok = 0
         # all parts or none: a part without peer access to a neighbour (or neighbours in other containers) sends everybody back to NCCL
-        agreed = self._torch.tensor([ok], device=f"cuda:{p.desired_device}")
+        agreed = self._torch.tensor([ok], device=f"cuda:{p.desired_device}" if self._torch.cuda.is_available() else "cpu")
         dist.all_reduce(agreed, op=dist.ReduceOp.MIN)
         if int(agreed.item()) == 0:
             for t, f, _, _ in opened.values():
@@ -340,6 +341,13 @@ class BigLattice:
             g.kernel_run(kid)
             g.halo_signal(self._peer["flag_left"], self._peer["flag_right"], n)
 
+    def _halo_fence(self):
+        """Between sweeps a part reads its halo slices outside the passes (measurements, a real reunitarisation launch).  A neighbour
+        that is already in its next sweep must not store into them meanwhile: what this part has enqueued so far is announced as a pass of
+        its own, and the neighbours' first boundary launch of the sweep waits for it like for any other pass."""
+        self._pass_no += 1
+        self.parts[self.local[0]].GPU0.halo_signal(self._peer["flag_left"], self._peer["flag_right"], self._pass_no)
+
     def _update_pass(self, par: str, d: str, overrelax: bool = False):
         """One (parity, direction) pass of all local parts + the exchange of what it changed; overrelax: the PRNG-free overrelaxation
         pass (`or_steps`) through the same schedule."""
@@ -383,6 +391,8 @@ class BigLattice:
             self.update_edges(di)
 
     def lattice_sweep(self):
+        if self._peer is not None:
+            self._halo_fence()
         for par in ("odd", "even"):
             for d in DIRS:
                 self._update_pass(par, d)

@@ -373,7 +373,11 @@ class GPU:
     def halo_signal(self, flag_a: int, flag_b: int, value: int):
         self._chk(self.L.qgpu_halo_signal(self.h, C.c_void_p(flag_a or None), C.c_void_p(flag_b or None), value), "halo_signal")
 
-    def halo_wait(self, flags_buffer: int, value: int, timeout_s: float = 5.0):
+    def halo_wait(self, flags_buffer: int, value: int, timeout_s: float | None = None):
+        """timeout_s: how long the stream may be held before the wait gives up and is counted (env QCDGPU_HALO_TIMEOUT_S, default 30 s:
+        long enough for a neighbour that writes a state file between two sweeps, short enough that a lost neighbour does not hang the GPU)."""
+        if timeout_s is None:
+            timeout_s = float(os.environ.get("QCDGPU_HALO_TIMEOUT_S", "30"))
         self._chk(self.L.qgpu_halo_wait(self.h, flags_buffer, value, timeout_s), "halo_wait")
 
     def close(self):

@@ -70,6 +70,7 @@ static __global__ void halo_signal_kernel(unsigned long long* a, unsigned long l
 // (a neighbour that died must not hang this GPU: the host finds the count at its next synchronisation)
 static __global__ void halo_wait_kernel(unsigned long long* flags, unsigned long long value, unsigned long long timeout) {
     if (threadIdx.x >= 2) return;
+    if (*reinterpret_cast<volatile unsigned long long*>(flags + 2) != 0ull) return;     // a neighbour was lost before: every later wait would time out too
     const unsigned long long* f = flags + threadIdx.x;
     const long long t0 = clock64();
     unsigned long long v;

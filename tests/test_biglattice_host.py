@@ -81,3 +81,137 @@ def test_ring_exchange_gloo(world, tmp_path):
                        capture_output=True, text=True, env=env, timeout=300)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
     assert f"HALO-OK {world}" in r.stdout
+
+
+FUSED_PROTOCOL_WORKER = r'''
+"""The host side of the fused halo exchange (BigLattice._setup_fused_halo / _update_pass_fused / lattice_sweep) on gloo, with a stand-in
+for the device: link tables and flag words live in shared memory (one value per x-slice: the number of the pass that wrote it), the
+"kernels" run synchronously in Python.  What is checked is the protocol: which slice goes where in a ring whose left and right
+neighbours differ, which flag word is written, and that a boundary launch of pass n finds pass n - 1 or n in its halos, never anything else."""
+import os, sys, time
+import numpy as np
+from multiprocessing import shared_memory
+import torch, torch.distributed as dist
+sys.path.insert(0, os.environ["QCD_ROOT"])
+import qcdgpu_b200.biglattice as BL
+dist.init_process_group("gloo")
+rank, world = dist.get_rank(), dist.get_world_size()
+NX = 4
+
+class FakeGPU:
+    def __init__(self):
+        self.shm, self.arr, self.opened, self.peer, self.xr, self.log = {}, {}, {}, {}, {}, []
+        self.pass_no = 0
+    def buffer_init(self, kind, size, host, size_of):
+        bid = len(self.shm) + 100
+        self._make(bid, size * size_of)
+        return bid
+    def _make(self, bid, nbytes):
+        m = shared_memory.SharedMemory(create=True, size=max(nbytes, 64))
+        self.shm[bid] = m
+        self.arr[bid] = np.ndarray((max(nbytes, 64) // 8,), dtype=np.float64 if bid == TABLE else np.uint64, buffer=m.buf)
+        self.arr[bid][:] = 0
+    def buffer_ipc_export(self, bid):
+        return self.shm[bid].name.encode().ljust(64, b"\0")
+    def ipc_open(self, handle):
+        m = shared_memory.SharedMemory(name=handle.rstrip(b"\0").decode())
+        key = (len(self.opened) + 1) << 32
+        self.opened[key] = m
+        return key
+    def ipc_close(self, ptr):
+        self.opened.pop(ptr).close()
+    def _peer_array(self, ptr, dtype):
+        m = self.opened[ptr & ~0xffffffff]
+        return np.ndarray((m.size // 8,), dtype=dtype, buffer=m.buf), (ptr & 0xffffffff) // 8
+    def kernel_set_peer_halo(self, kid, side, table, src_x, dst_x, rowsize):
+        self.peer[(kid, side)] = (table, src_x, dst_x)
+    def kernel_set_x_range(self, kid, first, count, stride=1):
+        self.xr[kid] = (first, count, stride)
+    def kernel_run(self, kid):
+        if kid == "gs":
+            return
+        first, count, stride = self.xr[kid]
+        xs = [1 + first + i * stride for i in range(NX if count < 0 else count)]
+        t = self.arr[TABLE]
+        n = B._pass_no
+        if 1 in xs or NX in xs:          # a boundary launch reads its halos: they hold the neighbours' previous pass (n - 2 behind a
+            ok = (n - 1, n) if (n % 9) != 2 else (n - 2, n)       # sweep's fence, which stores no links), or already this one
+            assert t[0] in ok and t[NX + 1] in ok, (rank, n, t.tolist())
+            assert self.arr[B._flags][0] >= n - 1 and self.arr[B._flags][1] >= n - 1
+        for x in xs:
+            t[x] = n
+            for side in (0, 1):
+                table, src_x, dst_x = self.peer[(kid, side)]
+                if x == src_x:
+                    a, off = self._peer_array(table, np.float64)
+                    a[off + dst_x] = n
+        self.log.append((n, tuple(xs)))
+    def halo_signal(self, a, b, value):
+        for ptr in (a, b):
+            arr, off = self._peer_array(ptr, np.uint64)
+            arr[off] = value
+    def halo_wait(self, flags, value, timeout_s=5.0):
+        t0 = time.time()
+        f = self.arr[flags]
+        while f[0] < value or f[1] < value:
+            assert time.time() - t0 < 20, ("wait timed out", rank, value, f[:3].tolist())
+            time.sleep(0.0005)
+    def halo_bytes(self, program, d): return 1
+    def buffer_map(self, bid, dtype): return self.arr[bid]
+    def synchronize(self): pass
+    def close(self): pass
+
+TABLE = 7
+class FakePRNG:
+    def produce(self): pass
+class FakePart:
+    pass
+B = BL.BigLattice.__new__(BL.BigLattice)
+B.nparts, B.dist, B.local, B.Nx_all = world, dist, [rank], [NX] * world
+B._torch, B._stream, B._peer, B._pass_no, B.fused_halo, B.halo_bytes_per_pass = torch, None, None, 0, True, 0
+p = FakePart()
+p.k, p.Nx, p.desired_device, p.lattice_table, p.lattice_table_row_size, p.program_update = rank, NX, 0, TABLE, 64, 1
+p.x_first_real, p.x_last_real, p.or_steps, p.turnoff_gramschmidt, p.sun_GramSchmidt_id = 1, NX, 0, False, "gs"
+p.PRNG0 = FakePRNG()
+p.sun_update_id = {(par, d): f"{par}{d}" for par in ("odd", "even") for d in BL.DIRS}
+g = p.GPU0 = FakeGPU()
+g._make(TABLE, (NX + 2) * 8)
+B.parts = {rank: p}
+B._setup_fused_halo()
+assert B._peer is not None
+left, right = BL.ring_neighbours(rank, world)
+for sweep in range(3):
+    if rank == (sweep % world):
+        time.sleep(0.05)            # one rank lags: the others must wait for it, not run ahead by more than a pass
+    B.lattice_sweep()
+    n = B._pass_no
+    assert n == 9 * (sweep + 1)         # a fence + 8 passes
+    t = g.arr[TABLE].copy()
+    time.sleep(0.02)                    # "measurement": the neighbours may be done with theirs -- they must not touch my halos yet
+    assert np.array_equal(t, g.arr[TABLE])
+    assert t[0] == n and t[NX + 1] == n and all(t[1:NX + 1] == n), t.tolist()     # halos complete when the sweep returns
+# every pass: boundary slices (1 and NX) in one launch first, then the interior
+assert [x for _, x in g.log[:2]] == [(1, NX), tuple(range(2, NX))] and g.log[0][0] == 2
+dist.barrier()
+B._peer and [g.ipc_close(k) for k in list(g.opened)]
+dist.barrier()
+for m in g.shm.values():
+    m.close(); m.unlink()
+if rank == 0:
+    print("FUSED-PROTOCOL-OK", world)
+dist.destroy_process_group()
+'''
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_fused_halo_protocol_gloo(world, tmp_path):
+    """QCDGPU_HALO_FUSED host logic without a GPU: ring of 2 (left == right) and 3 (left != right) processes."""
+    script = tmp_path / "worker.py"
+    script.write_text(FUSED_PROTOCOL_WORKER)
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    env = dict(os.environ, QCD_ROOT=ROOT, OMP_NUM_THREADS="1")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
+                        "--master-addr", "127.0.0.1", "--master-port", str(port), str(script)],
+                       capture_output=True, text=True, env=env, timeout=300)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
+    assert f"FUSED-PROTOCOL-OK {world}" in r.stdout
