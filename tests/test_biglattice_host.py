@@ -114,6 +114,8 @@ class FakeGPU:
     def buffer_ipc_export(self, bid):
         return self.shm[bid].name.encode().ljust(64, b"\0")
     def ipc_open(self, handle):
+        if os.environ.get("QCD_FAIL_OPEN") == str(rank):
+            raise BL.QcdGpuError("ipc_open: peer access not available (simulated)")
         m = shared_memory.SharedMemory(name=handle.rstrip(b"\0").decode())
         key = (len(self.opened) + 1) << 32
         self.opened[key] = m
@@ -178,6 +180,16 @@ g = p.GPU0 = FakeGPU()
 g._make(TABLE, (NX + 2) * 8)
 B.parts = {rank: p}
 B._setup_fused_halo()
+if os.environ.get("QCD_FAIL_OPEN"):
+    # one rank cannot open its neighbours' tables: ALL ranks must end up on the NCCL path, with nothing left open
+    assert B._peer is None and B.fused_halo is False and not g.opened, (rank, B._peer, g.opened)
+    dist.barrier()
+    for m in g.shm.values():
+        m.close(); m.unlink()
+    if rank == 0:
+        print("FUSED-PROTOCOL-OK", world)
+    dist.destroy_process_group()
+    sys.exit(0)
 assert B._peer is not None
 left, right = BL.ring_neighbours(rank, world)
 for sweep in range(3):
@@ -203,13 +215,14 @@ dist.destroy_process_group()
 '''
 
 
-@pytest.mark.parametrize("world", [2, 3])
-def test_fused_halo_protocol_gloo(world, tmp_path):
-    """QCDGPU_HALO_FUSED host logic without a GPU: ring of 2 (left == right) and 3 (left != right) processes."""
+@pytest.mark.parametrize("world,fail", [(2, ""), (3, ""), (3, "1")])
+def test_fused_halo_protocol_gloo(world, fail, tmp_path):
+    """QCDGPU_HALO_FUSED host logic without a GPU: ring of 2 (left == right) and 3 (left != right) processes; fail: that rank cannot
+    open peer memory and everybody falls back to the NCCL exchange."""
     script = tmp_path / "worker.py"
     script.write_text(FUSED_PROTOCOL_WORKER)
     s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
-    env = dict(os.environ, QCD_ROOT=ROOT, OMP_NUM_THREADS="1")
+    env = dict(os.environ, QCD_ROOT=ROOT, OMP_NUM_THREADS="1", QCD_FAIL_OPEN=fail)
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
                         "--master-addr", "127.0.0.1", "--master-port", str(port), str(script)],
                        capture_output=True, text=True, env=env, timeout=300)
