@@ -128,6 +128,20 @@ int GPU::buffer_init(int buffer_type, int size, void* host_ptr, int size_of) {
     return GPU_current_buffer = qgpu_buffer_init(H(this), buffer_type, (size_t)(unsigned int)size, host_ptr, (size_t)size_of);
 }
 unsigned int* GPU::buffer_map(int buffer_id) { return static_cast<unsigned int*>(qgpu_buffer_map(H(this), buffer_id)); }
+#ifdef BIGLAT
+// The members only the reference's BIGLAT build declares (clinterface.h:197-260).  `k` / `ndev` only name the files of its
+// program-binary cache (clinterface.cpp:433-441, 750-790), which does not exist here.  Mapped ranges: clEnqueueMapBuffer(CL_MAP_WRITE,
+// blocking) = read the range into host memory, clEnqueueUnmapMemObject = write it back; model::UpdateEdges (suncl.cpp:4005-4062)
+// copies boundary slices between two such ranges.  One mapped range per buffer at a time, which is what the sequential
+// (non-USE_OPENMP) BIGLAT host loop needs with two or more parts.
+int GPU::device_initialize(int) { return device_initialize(); }
+int GPU::program_create_ndev(const char* source, const char* options, int) { return program_create(source, options); }
+unsigned int* GPU::buffer_map(int buffer_id, size_t offset, size_t size) { return static_cast<unsigned int*>(qgpu_buffer_map_range(H(this), buffer_id, offset, size)); }
+void* GPU::buffer_map_part(int buffer_id, size_t start, size_t size) { return qgpu_buffer_map_range(H(this), buffer_id, start, size); }
+void* GPU::buffer_map_void(int buffer_id) { return qgpu_buffer_map(H(this), buffer_id); }
+void GPU::buffer_unmap(int buffer_id, void* ptr) { qgpu_buffer_unmap(H(this), buffer_id, ptr); }
+void GPU::print_actual_hardware(void) { print_available_hardware(); }
+#endif
 cl_float4* GPU::buffer_map_float4(int buffer_id) { return static_cast<cl_float4*>(qgpu_buffer_map(H(this), buffer_id)); }
 int GPU::buffer_kill(int buffer_id) { return qgpu_buffer_kill(H(this), buffer_id); }
 unsigned int GPU::buffer_size_align(unsigned int size) { return buffer_size_align(size, (unsigned int)GPU_info.max_workgroup_size); }
@@ -173,6 +187,20 @@ GPU::GPU_init_parameters* GPU::get_init_file(char finitf[]) {
         snprintf(res[n].txtVarVal, LENGTH, "%s", val);
         res[n].iVarVal = atoi(val);
         res[n].fVarVal = atof(val);
+#ifdef BIGLAT
+        {   // "{a, b, ...}": one integer per part (clinterface.cpp:2122-2142)
+            const char* q = strchr(val, '{');
+            q = q ? q + 1 : val;
+            for (int j = 0; j < NPARTS; j++) {
+                while (*q == ' ' || *q == ',' || *q == '\t') q++;
+                char* end = NULL;
+                long v = strtol(q, &end, 10);
+                if (end == q) break;
+                res[n].ivVarVal[j] = (int)v;
+                q = end;
+            }
+        }
+#endif
         if (n) res[n - 1].final = false;
         res[n].final = true;
         n++;

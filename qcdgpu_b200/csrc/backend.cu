@@ -160,6 +160,7 @@ bool valid_kernel(qgpu* h, int id) { return id > 0 && id < (int)h->kernels.size(
 // "-D NAME=VALUE", "-D NAME", "-DNAME=VALUE", "-I path", "-Werror"
 void parse_options(const char* opt, ProgramCfg& c) {
     c.options = opt ? opt : "";
+    bool nhit_given = false;
     std::vector<std::string> tok;
     { std::string cur; for (const char* p = c.options.c_str();; p++) { if (*p == ' ' || *p == '\t' || *p == 0) { if (!cur.empty()) tok.push_back(cur); cur.clear(); if (!*p) break; } else cur += *p; } }
     for (size_t i = 0; i < tok.size(); i++) {
@@ -181,7 +182,7 @@ void parse_options(const char* opt, ProgramCfg& c) {
         else if (name == "ROWSIZE") c.rowsize = (uint32_t)v;
         else if (name == "PRNGSTEP") c.prngstep = (uint32_t)v;
         else if (name == "PRECISION") c.precision = (int)v;
-        else if (name == "NHIT") c.nhit = (int)v;
+        else if (name == "NHIT") { c.nhit = (int)v; nhit_given = true; }
         else if (name == "NHITPar") c.nhitpar = (int)v;
         else if (name == "TBC") c.tbc = true;
         else if (name == "GID_UPD") c.gid_upd = true;
@@ -209,6 +210,11 @@ void parse_options(const char* opt, ProgramCfg& c) {
         else if (name == "SKGROUP") c.skgroup = (uint32_t)v;
         else if (name == "N1EXACT") c.n1exact = (uint32_t)v;
     }
+    // The reference's BIGLAT host builds its update program with N1 = Nx + 2 (halo slices included, suncl.cpp:2422) and its measurement,
+    // Polyakov and Wilson programs with N1 = Nx (suncl.cpp:2597, 2889; their kernels test gindex < (N1 + 1) N2N3N4,
+    // sun_measurements_cl.cl:211), both with -D BIGLAT and the ROWSIZE of the stored part.  The update program is the one that carries
+    // -D NHIT; everything below works on the stored extent.
+    if (c.biglat && !nhit_given) c.n1 += 2;
 }
 
 Geom make_geom(const ProgramCfg& c, int tile_override = -1) {

@@ -441,8 +441,12 @@ class Model:
         self.LOAD_state += 1
 
     # ------------------------------------------------------------------ lattice_make_programs (suncl.cpp:3265-3648)
-    def options_common(self) -> str:
-        n = self.lattice_domain_size
+    def options_common(self, measuring: bool = False) -> str:
+        """measuring: the option string of the measurement / Polyakov / Wilson programs.  In the BIGLAT build the reference gives those
+        N1 = Nx, the real slices (suncl.cpp:2597, 2889), and only the update program N1 = Nx + 2 (suncl.cpp:2422)."""
+        n = list(self.lattice_domain_size)
+        if self.biglat and measuring:
+            n[0] -= 2
         o = "-Werror"
         if self.ints == model_start_gid:
             o += " -D GID_UPD"
@@ -497,7 +501,7 @@ class Model:
                     g.kernel_init_buffer(k, self.lattice_parameters)
                     self.sun_overrelax_id[(par, d)] = k
         # measurements
-        om = oc                                                    # suncl.cpp:3398-3408
+        om = oc = self.options_common(measuring=True)              # suncl.cpp:3398-3408; from here on the measuring programs
         if self.get_Fmunu: om += " -D FMUNU"
         if self.get_F0mu: om += " -D F0MU"
         if self.get_Fmunu or self.get_F0mu:

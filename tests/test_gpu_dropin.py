@@ -120,3 +120,61 @@ def test_reference_sample_configuration_wilson_fmunu_polyakov_slices(tmp_path, g
     assert "Differentiated Polyakov loop data" in text
     row = [l for l in text.splitlines() if l.startswith("PL             ")][0].split()[1:]
     assert len(row) == 8
+
+
+BIN_BIGLAT = os.path.join(ROOT, "integration", "_build", "QCDGPU_b200_biglat")
+INIT_BIGLAT = """\tPLATFORM = {{0, 0}}
+\tDEVICE= {{0, 0}}
+\tFINISHPATH=./
+\tOUTPUTPATH=./
+\tGROUP = {group}
+\tND = 4
+\tLT = {lt}
+\tLS = {ls}
+\tL1 = {l1}
+\tN1 = {{{n1a}, {n1b}}}
+\tITER = {iter}
+\tNITER = 1
+\tNHIT = 10
+\tBETA = {beta:.13e}
+\tNAV = {nav}
+\tINTS = {ints}
+\tPRNG = RANLUX3
+\tRANDSERIES = {{54, 1054}}
+\tPL_LEVEL = {pl}
+"""
+
+
+def _table_rows(text):
+    return np.array([[float(v) for v in l.split()[1:7]] for l in text.splitlines() if re.match(r"^\s+\d+\s+[-\d]", l)])
+
+
+@pytest.mark.parametrize("group,beta,n1", [(3, 6.0, (8, 4)), (2, 2.5, (6, 6)), (3, 5.7, (2, 10))])
+def test_reference_biglat_host_runs_on_cuda_backend(tmp_path, group, beta, n1):
+    """The reference's BIGLAT build (Makefile:45-48; -D BIGLAT -D NPARTS=2 -D NDEV=2, both parts on device 0 like its init_2.dat): its own
+    partition (SubLattice, N1 = {a, b}), per-part programs (-D BIGLAT -D N1 -D LEFT_SITES -D FULL_SITES), per-part kernel launches and
+    model::UpdateEdges -- halo slices copied through mapped ranges of the link tables (buffer_map(id, offset, size) / buffer_unmap) --
+    over this library.  With the deterministic INTS = 2 start the table must equal the single-lattice build's, which verifies itself
+    against the reference's CPU re-measurement."""
+    if not os.path.exists(BIN_BIGLAT):
+        pytest.skip("integration/_build/QCDGPU_b200_biglat not built (needs the reference tree: make -C integration)")
+    cfg = dict(group=group, ls=6, lt=4, l1=sum(n1), n1a=n1[0], n1b=n1[1], iter=4, beta=beta, nav=0, ints=2, pl=0)
+    d = tmp_path / "big"
+    d.mkdir()
+    (d / "init.dat").write_text(INIT_BIGLAT.format(**cfg))
+    r = subprocess.run([BIN_BIGLAT, "init.dat"], cwd=d, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    out = glob.glob(str(d / "su*-*.txt"))
+    assert len(out) == 1, (out, r.stdout[-2000:])
+    big = _table_rows(open(out[0]).read())
+    s = tmp_path / "single"
+    s.mkdir()
+    single_cfg = dict(group=group, ls=6, lt=4, iter=4, beta=beta, nav=0, ints=2, prng="RANLUX3", phi=0.0, pl=0, extra="\tL1 = %d\n" % sum(n1))
+    (s / "init.dat").write_text(INIT.format(**single_cfg))
+    r1 = subprocess.run([BIN, "init.dat"], cwd=s, capture_output=True, text=True, timeout=600)
+    assert r1.returncode == 0, r1.stdout[-3000:] + r1.stderr[-3000:]
+    text = open(glob.glob(str(s / "su*-*.txt"))[0]).read()
+    assert "Verification successfully passed" in text
+    one = _table_rows(text)
+    assert big.shape == one.shape == (4, 6), (big.shape, one.shape)
+    np.testing.assert_allclose(big, one, rtol=1e-11)
