@@ -97,7 +97,7 @@ class SubLattice(Model):
         self.Nx = Nx_all[k]
         self.left_x = sum(Nx_all[:k])
         self.desired_device = device
-        self.PL_level = 0
+        self.PL_level = 0            # 1, 2: Polyakov loops per part, summed in BigLattice.lattice_analysis (3, the slice-resolved loops: single lattice only)
 
     # x index (in the stored part, halos included) of the slices involved in the exchange
     @property
@@ -440,23 +440,36 @@ class BigLattice:
         p0 = next(iter(self.parts.values()))
         ITER = p0.ITER
         sums = {}
-        for name, buf in (("S", "lattice_energies"), ("Plq", "lattice_energies_plq")):
+        names = [("S", "lattice_energies", 0), ("Plq", "lattice_energies_plq", 0)]
+        if p0.PL_level > 0:      # Polyakov loops close inside a part (the t direction is not cut): per-part sums of Re, Im (and |P|^2, |P|^4) add up
+            names.append(("PL", "lattice_polyakov_loop", 0))
+            if p0.PL_level > 1:
+                names.append(("PL24", "lattice_polyakov_loop", p0.lattice_polyakov_loop_size))
+        for name, buf, off in names:
             acc = np.zeros((ITER, 2))
             for p in self.parts.values():
-                acc += p.GPU0.buffer_map(getattr(p, buf), np.float64).reshape(-1, 2)[:ITER]
+                acc += p.GPU0.buffer_map(getattr(p, buf), np.float64).reshape(-1, 2)[off: off + ITER]
             sums[name] = acc
         if self.dist is not None:
             torch = self._torch
-            flat = torch.tensor(np.concatenate([sums["S"].ravel(), sums["Plq"].ravel()]), device=f"cuda:{p0.desired_device}")
+            flat = torch.tensor(np.concatenate([sums[n].ravel() for n, _, _ in names]), device=f"cuda:{p0.desired_device}")
             self.dist.all_reduce(flat)
             flat = flat.cpu().numpy()
-            sums["S"], sums["Plq"] = flat[: 2 * ITER].reshape(ITER, 2), flat[2 * ITER:].reshape(ITER, 2)
+            for i, (n, _, _) in enumerate(names):
+                sums[n] = flat[2 * ITER * i: 2 * ITER * (i + 1)].reshape(ITER, 2)
         den = float(np.prod(self.full_size) * 3)
         A = {}
         for name in ("S", "Plq"):
             A[f"{name}_spat"] = Model._series(sums[name][:, 0].copy(), den)
             A[f"{name}_temp"] = Model._series(sums[name][:, 1].copy(), den)
             A[f"{name}_total"] = Model._joint(A[f"{name}_spat"], A[f"{name}_temp"])
+        if p0.PL_level > 0:      # model::lattice_analysis, suncl.cpp:1440-1480: normalised by the full spatial volume and powers of N
+            v3, N = float(np.prod(self.full_size[:3])), float(p0.lattice_group)
+            A["Polyakov_loop"] = Model._series(sums["PL"][:, 0].copy(), v3 * N)
+            A["Polyakov_loop_im"] = Model._series(sums["PL"][:, 1].copy(), v3 * N)
+            if p0.PL_level > 1:
+                A["Polyakov_loop_P2"] = Model._series(sums["PL24"][:, 0].copy(), v3 * N ** 2)
+                A["Polyakov_loop_P4"] = Model._series(sums["PL24"][:, 1].copy(), v3 * N ** 4)
         self.Analysis = A
         return A
 

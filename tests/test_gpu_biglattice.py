@@ -36,22 +36,25 @@ def test_gid_start_partitioned_equals_single(sun, dims, nparts, or_steps):
     m = Model()
     m.lattice_group, m.lattice_full_size, m.precision, m.ints, m.BETA, m.ITER, m.PL_level = sun, list(dims), 1, 2, beta, 4, 0
     m.or_steps = or_steps
+    m.PL_level = 2
     m.lattice_init()
     m.lattice_simulate()
     m.lattice_analysis()
-    want = np.array([[m.Analysis[c]["data"][i] for c in ("Plq_spat", "Plq_temp", "S_spat", "S_temp")] for i in range(4)])
+    cols = ("Plq_spat", "Plq_temp", "S_spat", "S_temp", "Polyakov_loop", "Polyakov_loop_im", "Polyakov_loop_P2", "Polyakov_loop_P4")
+    want = np.array([[m.Analysis[c]["data"][i] for c in cols] for i in range(4)])
     m.close()
     for overlap in (False, True):
         def conf(p, base=_configure(sun, beta, 2, 4)):
             base(p)
             p.or_steps = or_steps
+            p.PL_level = 2
         B = BigLattice(dims, nparts, configure=conf)
         B.overlap = overlap
         B.lattice_init()
         B.lattice_simulate()
         A = B.lattice_analysis()
-        got = np.array([[A[c]["data"][i] for c in ("Plq_spat", "Plq_temp", "S_spat", "S_temp")] for i in range(4)])
-        np.testing.assert_allclose(got, want, rtol=1e-12)
+        got = np.array([[A[c]["data"][i] for c in cols] for i in range(4)])
+        np.testing.assert_allclose(got, want, rtol=1e-12, atol=1e-14)     # Polyakov loops of the parts add up to the single lattice's
         B.close()
 
 
