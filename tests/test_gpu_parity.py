@@ -345,10 +345,11 @@ def test_fused_prng_equals_buffered(gen, sun, prec):
         states.append(m.GPU0.buffer_map(m.PRNG0.PRNG_seed_table_id, np.uint32).copy())
         m.close()
     np.testing.assert_array_equal(states[0], states[1])           # the generators stand at the same point, bit for bit
-    if gen in ("XOR7", "RANECU") and prec == 1:
-        # Same PTX arithmetic in both kernels (989 fma / 965 mul / 640 add + sub per SU(3) fp64 instantiation), but ptxas contracts the
-        # remaining mul + add pairs per kernel: these two instantiations differ in a few last bits (4e-15 after two sweeps), where the
-        # four older generators happen to come out identical.  Integers are bit-exact, floating point within the stated tolerance.
+    if gen != "RANLUX3" and sun == 3 and prec == 1:
+        # Same PTX arithmetic in every instantiation of update_kernel (989 fma / 965 mul / 640 add + sub for SU(3) fp64), but ptxas
+        # contracts the remaining mul + add pairs kernel by kernel: the instantiation with the generator in registers and the one that
+        # reads the buffer may differ in a few last bits (4e-15 after two sweeps; which generators come out identical changes with
+        # unrelated edits of the kernel).  Integers are bit-exact, floating point within the stated tolerance.
         np.testing.assert_allclose(tables[0], tables[1], rtol=0, atol=1e-12)
         return
     np.testing.assert_array_equal(tables[0].view(np.uint8), tables[1].view(np.uint8))
