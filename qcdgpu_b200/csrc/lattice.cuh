@@ -192,7 +192,12 @@ __device__ __forceinline__ void st_plane(R* table, const Geom& g, uint32_t ginde
     stv4(table + 4 * (size_t(gindex) + size_t(plane) * g.rowsize), v);
 }
 
-// the same vec4 into the neighbours' halo slices when this site lies in a boundary slice (Geom::peer_*); callers test g.peer_on first
+// the same vec4 into the neighbours' halo slices when this site lies in a boundary slice (Geom::peer_*); callers test QCD_PEER_ON(g) first
+#ifdef QCD_NO_PEER_STORES      // measurement knob: the update kernels without the peer-store branch
+#define QCD_PEER_ON(g) false
+#else
+#define QCD_PEER_ON(g) ((g).peer_on != 0u)
+#endif
 template <typename R>
 __device__ __forceinline__ void st_plane_peer(const Geom& g, uint32_t gindex, uint32_t plane, const V4<R>& v) {
 #pragma unroll
@@ -364,7 +369,7 @@ __device__ __forceinline__ void store3(R* table, const Geom& g, uint32_t gindex,
     st_plane(table, g, gindex, DIR + 0, a);
     st_plane(table, g, gindex, DIR + 4, b);
     st_plane(table, g, gindex, DIR + 8, c);
-    if (g.peer_on) {
+    if (QCD_PEER_ON(g)) {
         st_plane_peer(g, gindex, DIR + 0, a);
         st_plane_peer(g, gindex, DIR + 4, b);
         st_plane_peer(g, gindex, DIR + 8, c);

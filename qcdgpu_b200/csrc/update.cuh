@@ -1273,14 +1273,14 @@ __device__ __forceinline__ void update_site_su2(R* table, const Geom& g, R beta,
     V4<R> d;
     if (kp_heatbath<R, Prn>(prn, g, aH, R(0.5) * in * InvBeta<R>::get(), d)) {     // 1 / (beta 2 |S|)
         st_plane(table, g, gindex, MU, d);
-        if (g.peer_on) st_plane_peer(g, gindex, MU, d);
+        if (QCD_PEER_ON(g)) st_plane_peer(g, gindex, MU, d);
     }
     // on NHIT rejections the old (untwisted, stored) link stays -- su2_update_cl.cl:541-548.  With TBC the
     // reference would store the twisted m0 back; that only differs on the x = N1-1 Y-links.
     else if (TBC && MU == 1) {
         V4<R> m0 = load2<R, MU, TBC>(table, g, gindex, p.x, tw);
         st_plane(table, g, gindex, MU, m0);
-        if (g.peer_on) st_plane_peer(g, gindex, MU, m0);
+        if (QCD_PEER_ON(g)) st_plane_peer(g, gindex, MU, m0);
     }
 }
 template <typename R, int MU>
@@ -1308,7 +1308,7 @@ __device__ __forceinline__ void overrelax_site_su2(R* table, const Geom& g, uint
     V4<R> aH = { S.x * in, -S.y * in, -S.z * in, -S.w * in };
     V4<R> r = su2_mul(su2_mul(aH, su2_dag(m0)), aH);
     st_plane(table, g, gindex, MU, r);
-    if (g.peer_on) st_plane_peer(g, gindex, MU, r);
+    if (QCD_PEER_ON(g)) st_plane_peer(g, gindex, MU, r);
 }
 
 
