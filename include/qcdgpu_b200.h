@@ -176,6 +176,11 @@ int   qgpu_buffer_ipc_export(qgpu* h, int buffer_id, unsigned char handle[64]);
 void* qgpu_ipc_open(qgpu* h, const unsigned char handle[64]);
 int   qgpu_ipc_close(qgpu* h, void* peer_ptr);
 int   qgpu_kernel_set_peer_halo(qgpu* h, int kernel_id, int side, void* peer_table, unsigned src_x, unsigned dst_x, size_t peer_rowsize);
+/* the same peer stores for parts that live in ONE process (the reference's mode: several devices, one host program): the peer table is
+ * simply the other handle's qgpu_buffer_device_ptr; qgpu_enable_peer_access lets h's device store into other's, and qgpu_halo_order
+ * (an event) makes waiter's stream continue once what signaller's stream holds so far has completed. */
+int   qgpu_enable_peer_access(qgpu* h, qgpu* other);
+int   qgpu_halo_order(qgpu* waiter, qgpu* signaller);
 int   qgpu_halo_signal(qgpu* h, void* peer_flag_a, void* peer_flag_b, unsigned long long value);
 int   qgpu_halo_wait(qgpu* h, int flags_buffer_id, unsigned long long value, double timeout_s);
 

@@ -151,6 +151,9 @@ class BigLattice:
         self.fused_halo = os.environ.get("QCDGPU_HALO_FUSED", "1") != "0" and dist is not None and nparts > 1 and len(set(self.Nx_all)) == 1
         self._peer = None
         self._pass_no = 0
+        # the same peer stores for parts of THIS process (one or several devices): events instead of flags
+        self.fused_inproc = os.environ.get("QCDGPU_HALO_FUSED", "1") != "0" and dist is None
+        self._inproc = False
         self.halo_bytes_per_pass = 0
 
     # ------------------------------------------------------------------ set-up
@@ -189,6 +192,8 @@ class BigLattice:
             # writes direction X there.  Per-pass exchanges are ordered by plane separation, this one needs the readers to be done.
             for p in self.parts.values():
                 p.GPU0.synchronize()
+        if self.fused_inproc and len(self.parts) == self.nparts:
+            self._setup_fused_inprocess()
         self.measure()
         for p in self.parts.values():
             p.ITER_counter += 1
@@ -257,6 +262,31 @@ class BigLattice:
         self.halo_bytes_per_pass = 2 * g.halo_bytes(p.program_update, 0)
         self.synchronize()
         dist.barrier()
+
+    def _setup_fused_inprocess(self):
+        """All parts in this process: every update kernel gets its neighbours' tables (plain device pointers; the part's own table
+        when it is its own neighbour), the writer's device is given access to the neighbour's."""
+        for p in self.parts.values():
+            p.GPU0.synchronize()
+        for k, p in self.parts.items():
+            left, right = ring_neighbours(k, self.nparts)
+            L, R = self.parts[left], self.parts[right]
+            for nb in (L, R):
+                if nb is not p:
+                    p.GPU0.enable_peer_access(nb.GPU0)
+            lt, rt = L.GPU0.buffer_device_ptr(L.lattice_table), R.GPU0.buffer_device_ptr(R.lattice_table)
+            for kid in list(p.sun_update_id.values()) + list(getattr(p, "sun_overrelax_id", {}).values()):
+                p.GPU0.kernel_set_peer_halo(kid, 0, lt, p.x_first_real, L.Nx + 1, L.lattice_table_row_size)
+                p.GPU0.kernel_set_peer_halo(kid, 1, rt, p.x_last_real, 0, R.lattice_table_row_size)
+            self.halo_bytes_per_pass = 2 * p.GPU0.halo_bytes(p.program_update, 0)
+        self._inproc = True
+
+    def _order_neighbours(self):
+        """every part's stream waits for what its neighbours' streams hold so far"""
+        for k, p in self.parts.items():
+            for nb in set(ring_neighbours(k, self.nparts)):
+                if nb != k:
+                    p.GPU0.halo_order(self.parts[nb].GPU0)
 
     def _check_halo_timeouts(self):
         if self._peer is not None:
@@ -374,6 +404,16 @@ class BigLattice:
             else:
                 p.GPU0.kernel_set_x_range(kid, 0, -1)
                 p.GPU0.kernel_run(kid)
+        if self._inproc:
+            # the launches above stored the boundary links into the neighbours' halos as well: what is left of the exchange is order --
+            # nothing of a part's stream that follows (its next pass reads the halos) before the neighbours' launches of this pass
+            self._order_neighbours()
+            if split:
+                for p in self.parts.values():
+                    kid = kids[p.k]
+                    p.GPU0.kernel_set_x_range(kid, 1, p.Nx - 2)
+                    p.GPU0.kernel_run(kid)
+            return
         if self.dist is not None:
             pending = self.update_edges(di)
             if split:
@@ -393,6 +433,8 @@ class BigLattice:
     def lattice_sweep(self):
         if self._peer is not None:
             self._halo_fence()
+        if self._inproc:
+            self._order_neighbours()           # the same fence with events: the neighbours' measurements are done with my boundary slices' copies
         for par in ("odd", "even"):
             for d in DIRS:
                 self._update_pass(par, d)

@@ -53,7 +53,7 @@ EXPORTS = [
     "qgpu_timer_stop", "qgpu_launch_count", "qgpu_update_kernel_registers", "qgpu_halo_copy",
     "qgpu_halo_pack", "qgpu_halo_unpack", "qgpu_halo_bytes", "qgpu_host_srand", "qgpu_host_rand_fill",
     "qgpu_ranlux_jump_table", "qgpu_buffer_ipc_export", "qgpu_ipc_open", "qgpu_ipc_close", "qgpu_kernel_set_peer_halo",
-    "qgpu_halo_signal", "qgpu_halo_wait",
+    "qgpu_halo_signal", "qgpu_halo_wait", "qgpu_enable_peer_access", "qgpu_halo_order",
 ]
 
 
@@ -147,6 +147,8 @@ def load(build_if_missing: bool = True):
     L.qgpu_ipc_close.argtypes = [vp, vp]
     L.qgpu_kernel_set_peer_halo.argtypes = [vp, ci, ci, vp, cu, cu, sz]
     L.qgpu_halo_signal.argtypes = [vp, vp, vp, C.c_ulonglong]
+    L.qgpu_enable_peer_access.argtypes = [vp, vp]
+    L.qgpu_halo_order.argtypes = [vp, vp]
     L.qgpu_halo_wait.argtypes = [vp, ci, C.c_ulonglong, C.c_double]
     L.qgpu_halo_bytes.restype = sz
     L.qgpu_host_srand.argtypes = [cu]
@@ -369,6 +371,13 @@ class GPU:
 
     def kernel_set_peer_halo(self, kernel: int, side: int, peer_table: int, src_x: int, dst_x: int, peer_rowsize: int):
         self._chk(self.L.qgpu_kernel_set_peer_halo(self.h, kernel, side, C.c_void_p(peer_table or None), src_x, dst_x, peer_rowsize), "kernel_set_peer_halo")
+
+    def enable_peer_access(self, other: "GPU"):
+        self._chk(self.L.qgpu_enable_peer_access(self.h, other.h), "enable_peer_access")
+
+    def halo_order(self, signaller: "GPU"):
+        """this handle's stream waits for what `signaller`'s stream holds so far"""
+        self._chk(self.L.qgpu_halo_order(self.h, signaller.h), "halo_order")
 
     def halo_signal(self, flag_a: int, flag_b: int, value: int):
         self._chk(self.L.qgpu_halo_signal(self.h, C.c_void_p(flag_a or None), C.c_void_p(flag_b or None), value), "halo_signal")

@@ -1281,6 +1281,26 @@ int qgpu_kernel_set_peer_halo(qgpu* h, int kid, int side, void* peer_table, unsi
     k.peer[side].table = peer_table; k.peer[side].src_x = src_x; k.peer[side].dst_x = dst_x; k.peer[side].rowsize = (uint32_t)peer_rowsize;
     return 0;
 }
+// Parts of ONE process (several handles, one or several devices): the writer's device must reach the other part's memory, and the
+// hand-shake is an event -- `waiter`'s stream continues once everything queued on `signaller`'s stream so far has completed.
+int qgpu_enable_peer_access(qgpu* h, qgpu* other) {
+    if (h->device == other->device) return 0;
+    CUDA_OK(h, cudaSetDevice(h->device));
+    int can = 0; CUDA_OK(h, cudaDeviceCanAccessPeer(&can, h->device, other->device));
+    if (!can) return fail(h, "device %d cannot access device %d peer memory", h->device, other->device);
+    cudaError_t e = cudaDeviceEnablePeerAccess(other->device, 0);
+    if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) return fail(h, "cudaDeviceEnablePeerAccess: %s", cudaGetErrorString(e));
+    cudaGetLastError();
+    return 0;
+}
+int qgpu_halo_order(qgpu* waiter, qgpu* signaller) {
+    if (waiter == signaller || waiter->stream == signaller->stream) return 0;
+    CUDA_OK(waiter, cudaSetDevice(signaller->device));
+    CUDA_OK(waiter, cudaEventRecord(signaller->ev_halo, signaller->stream));
+    CUDA_OK(waiter, cudaSetDevice(waiter->device));
+    CUDA_OK(waiter, cudaStreamWaitEvent(waiter->stream, signaller->ev_halo, 0));
+    return 0;
+}
 int qgpu_halo_signal(qgpu* h, void* flag_a, void* flag_b, unsigned long long value) {
     CUDA_OK(h, cudaSetDevice(h->device));
     CUDA_OK(h, launch_halo_signal((unsigned long long*)flag_a, (unsigned long long*)flag_b, value, h->stream));

@@ -28,7 +28,7 @@ def _configure(sun, beta, ints, iters, prec=1, fused=False, prng="RANLUX3"):
 
 @pytest.mark.parametrize("sun,dims,nparts,or_steps", [(3, (4, 6, 2, 8), 1, 0), (3, (4, 6, 2, 8), 2, 0), (3, (12, 4, 2, 4), 3, 0), (2, (8, 4, 8, 2), 2, 0),
                                                      (3, (12, 4, 2, 4), 3, 2), (2, (8, 4, 8, 2), 2, 1)])
-def test_gid_start_partitioned_equals_single(sun, dims, nparts, or_steps):
+def test_gid_start_partitioned_equals_single(sun, dims, nparts, or_steps, monkeypatch):
     """or_steps > 0: overrelaxation passes after each heat-bath sweep go through the same boundary-first schedule and exchange."""
     from qcdgpu_b200 import Model
     from qcdgpu_b200.biglattice import BigLattice
@@ -43,7 +43,10 @@ def test_gid_start_partitioned_equals_single(sun, dims, nparts, or_steps):
     cols = ("Plq_spat", "Plq_temp", "S_spat", "S_temp", "Polyakov_loop", "Polyakov_loop_im", "Polyakov_loop_P2", "Polyakov_loop_P4")
     want = np.array([[m.Analysis[c]["data"][i] for c in cols] for i in range(4)])
     m.close()
-    for overlap in (False, True):
+    for overlap, fused_halo in ((False, "1"), (True, "1"), (True, "0")):
+        # fused_halo: boundary links stored into the neighbours' halos by the update kernels (events between the parts' streams), or
+        # copy kernels over peer memory behind the pass
+        monkeypatch.setenv("QCDGPU_HALO_FUSED", fused_halo)
         def conf(p, base=_configure(sun, beta, 2, 4)):
             base(p)
             p.or_steps = or_steps
@@ -52,6 +55,7 @@ def test_gid_start_partitioned_equals_single(sun, dims, nparts, or_steps):
         B.overlap = overlap
         B.lattice_init()
         B.lattice_simulate()
+        assert B._inproc == (fused_halo == "1")
         A = B.lattice_analysis()
         got = np.array([[A[c]["data"][i] for c in cols] for i in range(4)])
         np.testing.assert_allclose(got, want, rtol=1e-12, atol=1e-14)     # Polyakov loops of the parts add up to the single lattice's
@@ -110,7 +114,7 @@ def test_tma_staged_links_in_slabs():
         np.testing.assert_array_equal(a.view(np.uint8), b.view(np.uint8))
 
 
-def test_two_devices_in_one_process_n2_64():
+def test_two_devices_in_one_process_n2_64(monkeypatch):
     """Several parts in ONE process on different GPUs (devices=[0, 1], P2P halo copies), N2 = 64: every device launches the kernels
     that need more than 48 KB of dynamic shared memory (TMA-staged update, 63 KB), and the opt-in is per device
     (update_inst.cu, ensure_smem).  Same links as with both parts on device 0."""
@@ -119,11 +123,15 @@ def test_two_devices_in_one_process_n2_64():
         pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
     from qcdgpu_b200.biglattice import BigLattice
     tables = []
-    for devices in ([0, 0], [0, 1], [1, 0]):
+    for devices, fused_halo in (([0, 0], "1"), ([0, 1], "1"), ([1, 0], "1"), ([0, 1], "0")):
+        # fused_halo "1": the update kernels store boundary links into the other device's halo slices (peer stores, events);
+        # "0": copy kernels reading peer memory behind the pass
+        monkeypatch.setenv("QCDGPU_HALO_FUSED", fused_halo)
         B = BigLattice((8, 64, 2, 2), 2, configure=_configure(3, 5.7, 0, 3, fused=True), devices=devices)
         B.overlap = True
         B.lattice_init()
         B.lattice_simulate()
+        assert B._inproc == (fused_halo == "1")
         tables.append([p.table_numpy() for p in B.parts.values()])
         B.close()
     for t in tables[1:]:
