@@ -114,12 +114,15 @@ class BigLattice:
     """The driver: parts of this process + transport to the ring neighbours."""
 
     def __init__(self, full_size, nparts: int, local_parts: list[int] | None = None, devices: list[int] | None = None,
-                 dist=None, configure=None, randseries: list[int] | None = None):
+                 dist=None, configure=None, randseries: list[int] | None = None, Nx_all: list[int] | None = None):
         """`dist`: a torch.distributed module with an initialised process group when parts live in other
-        processes (then this process owns exactly part `dist.get_rank()`), else None (all parts local)."""
+        processes (then this process owns exactly part `dist.get_rank()`), else None (all parts local).
+        `Nx_all`: the x-slices of every part (init.dat's N1 = {a, b, ...}); default: as equal as possible."""
         self.full_size = list(full_size)
         self.nparts = nparts
-        self.Nx_all = split_slabs(full_size[0], nparts)
+        self.Nx_all = list(Nx_all) if Nx_all is not None else split_slabs(full_size[0], nparts)
+        if len(self.Nx_all) != nparts or sum(self.Nx_all) != full_size[0] or min(self.Nx_all) < 1:
+            raise QcdGpuError(f"x-slabs {self.Nx_all} do not cut {full_size[0]} x-slices into {nparts} parts")
         if nparts > 1 and not parity_consistent(self.Nx_all):
             raise QcdGpuError(f"x-slabs {self.Nx_all}: every part needs an even number of x-slices for a consistent checkerboard")
         self.dist = dist
@@ -622,3 +625,81 @@ def bench_main(args, workload):
         print(json.dumps(out))
     B.close()
     dist.destroy_process_group()
+
+
+# ---------------------------------------------------------------------------------------------- init.dat of the BIGLAT build
+def init_file_vectors(path: str) -> dict:
+    """The keys a BIGLAT init.dat gives one value per part, `KEY = {a, b, ...}` (clinterface.cpp:2122-2142, suncl.cpp:307-386):
+    PLATFORM, DEVICE, N1, RANDSERIES.  A plain number counts as a one-element list."""
+    from .model import get_init_file
+    out = {}
+    for key, ival, _, text in get_init_file(path):
+        if key in ("PLATFORM", "DEVICE", "N1", "RANDSERIES"):
+            t = text.strip()
+            if t.startswith("{"):
+                out[key] = [int(x) for x in t.strip("{}").replace(",", " ").split()]
+            else:
+                out[key] = [ival]
+    return out
+
+
+def from_init_file(path: str, dist=None) -> "BigLattice":
+    """A BigLattice from the reference's BIGLAT init.dat (its sample: SU(N)/init_2.dat): N1 = {a, b, ...} are the parts' x-slices (their
+    sum is L1), DEVICE = {...} their devices (all parts in this process, like the reference's single host program; several parts may
+    share a device), RANDSERIES = {...} their random series.  Everything else is read by every part as model::lattice_get_init_file does."""
+    from .model import Model
+    v = init_file_vectors(path)
+    probe = Model.__new__(Model)
+    Model.__init__(probe)
+    probe.lattice_get_init_file(path)
+    full = list(probe.lattice_full_size)
+    probe.close()
+    nx = v.get("N1")
+    if not nx:
+        raise QcdGpuError(f"{path}: a BIGLAT init file names the parts' x-slices, N1 = {{a, b, ...}}")
+    nparts = len(nx)
+    devices = (v.get("DEVICE") or [0]) * nparts if len(v.get("DEVICE") or [0]) == 1 else v["DEVICE"]
+    series = v.get("RANDSERIES")
+    if series is not None and len(series) == 1:
+        series = [series[0] + 1000 * k for k in range(nparts)]
+
+    def configure(p):
+        dev, k, rs = p.desired_device, p.k, p.PRNG0.PRNG_randseries
+        p.lattice_get_init_file(path)                 # scalar keys; the per-part ones come back as 0 and are restored
+        p.desired_device, p.desired_platform = dev, 0
+        p.PRNG0.PRNG_randseries = rs
+        p.lattice_full_size = list(full)
+        if p.PL_level > 2:
+            p.PL_level = 2                            # the slice-resolved loops exist for the single lattice only
+        # measured for the single lattice only (DESIGN.md section 7): a BIGLAT file that asks for them still runs, without those columns
+        p.get_wilson_loop = p.get_Fmunu = p.get_F0mu = p.get_actions_diff = False
+
+    return BigLattice(full, nparts, devices=devices[:nparts], dist=dist, configure=configure, randseries=series, Nx_all=nx)
+
+
+def main(argv=None):
+    """The BIGLAT build's main (QCDGPU.cpp:60-266): init.dat -> init -> simulate -> analysis -> table."""
+    import sys
+    argv = sys.argv[1:] if argv is None else argv
+    if not argv:
+        raise SystemExit("usage: python -m qcdgpu_b200.biglattice init.dat   (BIGLAT format: N1 = {a, b}, DEVICE = {0, 1}, ...)")
+    t0 = time.time()
+    B = from_init_file(argv[0])
+    B.lattice_init()
+    p0 = next(iter(B.parts.values()))
+    print(p0.header)
+    print(f" parts (x-slices)            : {B.Nx_all}   devices: {[p.desired_device for p in B.parts.values()]}")
+    B.lattice_simulate()
+    A = B.lattice_analysis()
+    cols = [c for c in p0.columns() if c in A]
+    print(" #     " + " ".join(f"{c:>14s}" for c in cols))
+    for i in range(p0.ITER):
+        print(f"[{i:5d}]: " + " ".join(f"{A[c]['data'][i]:14.8f}" for c in cols))
+    p0.Analysis, p0.elapsed = A, time.time() - t0
+    out = p0.lattice_write_results()
+    print(f"\nresults: {out}\nEXECUTION TIME: {time.time() - t0:f} sec\n")
+    B.close()
+
+
+if __name__ == "__main__":
+    main()

@@ -35,6 +35,32 @@ def test_sublattice_geometry_matches_reference_options():
     assert f"-D FULL_SITES={12 * 6 * 6 * 4}" in o and f"-D LEFT_SITES={6 * 6 * 6 * 4}" in o
 
 
+def test_biglat_init_file(tmp_path):
+    """The BIGLAT build's init.dat (SU(N)/init_2.dat): per-part values in braces, everything else as in the single-lattice file."""
+    from qcdgpu_b200.biglattice import from_init_file, init_file_vectors
+    f = tmp_path / "init_2.dat"
+    f.write_text("\tPLATFORM = {0, 0}\n\tDEVICE= {0, 1}\n\tGROUP = 3\n\tND = 4\n\tLT = 4\n\tLS = 6\n\tL1 = 12\n\tN1 = {8, 4}\n\tITER = 5\n"
+                 "\tNHIT = 7\n\tBETA = 6.3690000000000e+00\n\tNAV = 3\n\tINTS = 2\n\tPRNG = RANLUX4\n\tRANDSERIES = {1420193282, 45}\n"
+                 "\tPL_LEVEL = 3\n\tFMUNU = 1   # measured for the single lattice only\n")
+    assert init_file_vectors(str(f)) == {"PLATFORM": [0, 0], "DEVICE": [0, 1], "N1": [8, 4], "RANDSERIES": [1420193282, 45]}
+    B = from_init_file(str(f))
+    assert B.full_size == [12, 6, 6, 4] and B.Nx_all == [8, 4] and B.nparts == 2
+    p0, p1 = B.parts[0], B.parts[1]
+    assert (p0.Nx, p0.left_x, p0.desired_device, p0.PRNG0.PRNG_randseries) == (8, 0, 0, 1420193282)
+    assert (p1.Nx, p1.left_x, p1.desired_device, p1.PRNG0.PRNG_randseries) == (4, 8, 1, 45)
+    for p in (p0, p1):
+        assert (p.lattice_group, p.ITER, p.NHIT, p.NAV, p.ints, p.PL_level) == (3, 5, 7, 3, 2, 2) and abs(p.BETA - 6.369) < 1e-12
+        assert p.PRNG0.PRNG_generator == "RANLUX4" and p.lattice_full_size == [12, 6, 6, 4] and not p.get_Fmunu
+    B.close()
+    f.write_text("\tGROUP = 3\n\tLS = 6\n\tLT = 4\n\tL1 = 12\n\tN1 = {7, 5}\n")
+    from qcdgpu_b200.capi import QcdGpuError
+    with pytest.raises(QcdGpuError):
+        from_init_file(str(f))                  # odd slabs: the parts' checkerboards would not line up
+    f.write_text("\tGROUP = 3\n\tLS = 6\n\tLT = 4\n\tL1 = 12\n\tN1 = {8, 6}\n")
+    with pytest.raises(QcdGpuError):
+        from_init_file(str(f))                  # 8 + 6 != L1
+
+
 WORKER = r'''
 import os, sys
 import numpy as np

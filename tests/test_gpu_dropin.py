@@ -7,6 +7,7 @@ import glob
 import os
 import re
 import subprocess
+import sys
 
 import numpy as np
 import pytest
@@ -176,5 +177,16 @@ def test_reference_biglat_host_runs_on_cuda_backend(tmp_path, group, beta, n1, p
     text = open(glob.glob(str(s / "su*-*.txt"))[0]).read()
     assert "Verification successfully passed" in text
     one = _table_rows(text)
+    # the Python driver reads the same BIGLAT file (python -m qcdgpu_b200.biglattice init.dat): same partition, same table
+    m = tmp_path / "mirror"
+    m.mkdir()
+    (m / "init.dat").write_text(INIT_BIGLAT.format(**cfg))
+    rm = subprocess.run([sys.executable, "-m", "qcdgpu_b200.biglattice", "init.dat"], cwd=m, capture_output=True, text=True, timeout=600,
+                        env=dict(os.environ, PYTHONPATH=ROOT))
+    assert rm.returncode == 0, rm.stdout[-3000:] + rm.stderr[-3000:]
+    assert f"[{n1[0]}, {n1[1]}]" in rm.stdout
+    mir = _table_rows(open(glob.glob(str(m / "su*-*.txt"))[0]).read())
+    assert mir.shape == big.shape, (mir.shape, big.shape)
+    np.testing.assert_allclose(mir, big, rtol=1e-11, atol=1e-15)
     assert big.shape == one.shape and big.shape[0] == 4 and big.shape[1] >= (6 if pl == 0 else 8), (big.shape, one.shape)
     np.testing.assert_allclose(big, one, rtol=1e-11, atol=1e-15)          # pl > 0: the Polyakov-loop columns too
