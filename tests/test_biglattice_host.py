@@ -196,7 +196,7 @@ class FakePart:
     pass
 B = BL.BigLattice.__new__(BL.BigLattice)
 B.nparts, B.dist, B.local, B.Nx_all = world, dist, [rank], [NX] * world
-B._torch, B._stream, B._peer, B._pass_no, B.fused_halo, B.halo_bytes_per_pass = torch, None, None, 0, True, 0
+B._torch, B._stream, B._peer, B._pass_no, B.fused_halo, B.halo_bytes_per_pass, B._inproc = torch, None, None, 0, True, 0, False
 p = FakePart()
 p.k, p.Nx, p.desired_device, p.lattice_table, p.lattice_table_row_size, p.program_update = rank, NX, 0, TABLE, 64, 1
 p.x_first_real, p.x_last_real, p.or_steps, p.turnoff_gramschmidt, p.sun_GramSchmidt_id = 1, NX, 0, False, "gs"
