@@ -66,6 +66,32 @@ def test_program_options_are_validated_like_compile_errors():
     assert g.buffer_size_align(65, 64) == 128 and g.buffer_size_align(64, 64) == 64 and g.buffer_size_align(1, 64) == 64
 
 
+def test_biglat_programs_follow_the_reference_n1_convention():
+    """The reference's BIGLAT host gives its update program N1 = Nx + 2 (halo slices included, suncl.cpp:2422) and its measuring
+    programs N1 = Nx (suncl.cpp:2597, 2889), both with -D BIGLAT; the update program is the one with -D NHIT.  Seen from outside
+    through the range check of qgpu_kernel_set_peer_halo (the source slice must be a real one: 1 <= x < stored N1 - 1) -- no device
+    is needed -- and through the kernel names of the rest of init.dat's PRNG key."""
+    from qcdgpu_b200 import GPU, QcdGpuError
+    g = GPU()
+    common = "-D SUN=3 -D ND=4 -D N2=4 -D N3=4 -D N4=4 -D ROWSIZE=512 -D PRECISION=1 -D BIGLAT -D FULL_SITES=1024 -D LEFT_SITES=0"
+    g.program_create(None, common + " -D N1=6 -D NHIT=10 -D NHITPar=1 -D PRNGSTEP=256")          # update program: 4 real slices
+    k = g.kernel_init("update_odd_X", 1, [128], None)
+    g.kernel_set_peer_halo(k, 1, 0x1000, 4, 0, 512)
+    with pytest.raises(QcdGpuError, match="real source slice"):
+        g.kernel_set_peer_halo(k, 1, 0x1000, 5, 0, 512)
+    g.program_create(None, common + " -D N1=6")                                                 # measuring program: 6 real slices
+    k2 = g.kernel_init("overrelax_odd_X", 1, [128], None)
+    g.kernel_set_peer_halo(k2, 1, 0x1000, 6, 0, 512)
+    with pytest.raises(QcdGpuError, match="real source slice"):
+        g.kernel_set_peer_halo(k2, 1, 0x1000, 7, 0, 512)
+    with pytest.raises(QcdGpuError, match="no peer halo"):
+        g.kernel_set_peer_halo(g.kernel_init("lattice_measurement", 1, [128], [64]), 0, 0x1000, 1, 0, 512)
+    g.program_create(None, "")
+    for name in ("xor7", "ranecu", "ranmar", "rmproduce", "ranmar_init", "rmseed", "pm", "xor128", "mrg32k3a"):
+        assert g.kernel_init(name, 1, [64], None) > 0
+    g.close()
+
+
 def test_init_dat_keys(tmp_path):
     """The reference's sample init.dat (SU(N)/init.dat) keys, `KEY = value # comment` syntax."""
     from qcdgpu_b200.model import Model
