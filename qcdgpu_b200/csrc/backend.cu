@@ -1313,6 +1313,7 @@ int qgpu_halo_wait(qgpu* h, int flags_buffer, unsigned long long value, double t
     static int khz_of[64] = { 0 };      // cudaDevAttrClockRate is a driver query of about a millisecond: once per device
     int& khz = khz_of[h->device & 63];
     if (!khz) CUDA_OK(h, cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, h->device));
+    if (!(timeout_s > 0.0)) timeout_s = 30.0;       // no or a nonsensical time-out: the default, never an endless spin on a lost neighbour
     const unsigned long long clocks = (unsigned long long)(timeout_s * 1e3 * (double)khz);
     CUDA_OK(h, launch_halo_wait((unsigned long long*)h->buffers[flags_buffer].dptr, value, clocks, h->stream));
     h->launches++;
