@@ -497,7 +497,8 @@ class BigLattice:
             sums[name] = acc
         if self.dist is not None:
             torch = self._torch
-            flat = torch.tensor(np.concatenate([sums[n].ravel() for n, _, _ in names]), device=f"cuda:{p0.desired_device}")
+            flat = torch.tensor(np.concatenate([sums[n].ravel() for n, _, _ in names]),
+                                device=f"cuda:{p0.desired_device}" if torch.cuda.is_available() else "cpu")
             self.dist.all_reduce(flat)
             flat = flat.cpu().numpy()
             for i, (n, _, _) in enumerate(names):

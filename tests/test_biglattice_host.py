@@ -254,3 +254,56 @@ def test_fused_halo_protocol_gloo(world, fail, tmp_path):
                        capture_output=True, text=True, env=env, timeout=300)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
     assert f"FUSED-PROTOCOL-OK {world}" in r.stdout
+
+
+ANALYSIS_WORKER = r'''
+"""BigLattice.lattice_analysis across processes (gloo): per-part raw sums of action, plaquettes and Polyakov loops are packed into one
+all-reduce and normalised by the FULL lattice -- checked against the sums a single process would see."""
+import os, sys
+import numpy as np, torch, torch.distributed as dist
+sys.path.insert(0, os.environ["QCD_ROOT"])
+import qcdgpu_b200.biglattice as BL
+dist.init_process_group("gloo")
+rank, world = dist.get_rank(), dist.get_world_size()
+ITER, OFF = 5, 8
+def raw(k):                       # what part k's device buffers hold: (ITER, 2) doubles per observable, Polyakov |P|^2 / |P|^4 behind OFF
+    r = np.random.default_rng(100 + k)
+    pl = np.zeros((2 * OFF, 2)); pl[:ITER] = r.normal(size=(ITER, 2)); pl[OFF:OFF + ITER] = r.uniform(size=(ITER, 2))
+    return {"lattice_energies": r.uniform(size=(ITER + 3, 2)), "lattice_energies_plq": r.uniform(size=(ITER + 3, 2)), "lattice_polyakov_loop": pl}
+class FakeGPU:
+    def __init__(self, k): self.bufs = raw(k)
+    def buffer_map(self, name, dtype): return self.bufs[name].reshape(-1)
+class Part: pass
+p = Part()
+p.ITER, p.PL_level, p.lattice_polyakov_loop_size, p.lattice_group, p.desired_device = ITER, 2, OFF, 3, 0
+p.lattice_energies, p.lattice_energies_plq, p.lattice_polyakov_loop = "lattice_energies", "lattice_energies_plq", "lattice_polyakov_loop"
+p.GPU0 = FakeGPU(rank)
+B = BL.BigLattice.__new__(BL.BigLattice)
+B.full_size, B.nparts, B.dist, B._torch, B.parts = [4 * world, 6, 2, 8], world, dist, torch, {rank: p}
+A = B.lattice_analysis()
+tot = {k: sum(raw(j)[k] for j in range(world)) for k in raw(0)}
+V, v3 = float(np.prod(B.full_size)), float(np.prod(B.full_size[:3]))
+np.testing.assert_allclose(A["S_spat"]["data"], tot["lattice_energies"][:ITER, 0] / (3 * V), rtol=1e-14)
+np.testing.assert_allclose(A["Plq_temp"]["data"], tot["lattice_energies_plq"][:ITER, 1] / (3 * V), rtol=1e-14)
+np.testing.assert_allclose(A["Polyakov_loop"]["data"], tot["lattice_polyakov_loop"][:ITER, 0] / (v3 * 3), rtol=1e-13)
+np.testing.assert_allclose(A["Polyakov_loop_im"]["data"], tot["lattice_polyakov_loop"][:ITER, 1] / (v3 * 3), rtol=1e-13)
+np.testing.assert_allclose(A["Polyakov_loop_P2"]["data"], tot["lattice_polyakov_loop"][OFF:OFF + ITER, 0] / (v3 * 9), rtol=1e-13)
+np.testing.assert_allclose(A["Polyakov_loop_P4"]["data"], tot["lattice_polyakov_loop"][OFF:OFF + ITER, 1] / (v3 * 81), rtol=1e-13)
+dist.barrier()
+if rank == 0:
+    print("ANALYSIS-OK", world)
+dist.destroy_process_group()
+'''
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_biglattice_analysis_all_reduce_gloo(world, tmp_path):
+    script = tmp_path / "worker.py"
+    script.write_text(ANALYSIS_WORKER)
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    env = dict(os.environ, QCD_ROOT=ROOT, OMP_NUM_THREADS="1")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
+                        "--master-addr", "127.0.0.1", "--master-port", str(port), str(script)],
+                       capture_output=True, text=True, env=env, timeout=300)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
+    assert f"ANALYSIS-OK {world}" in r.stdout
